@@ -1,0 +1,344 @@
+// basis_generic.cu -- K2/K3 (table-driven): basis evaluation with analytic
+// derivatives for any body-order 2..5 / any monomial table, and the deterministic
+// gather into the E / F / V rows of the column-major LSQ matrix.
+//
+// Replaces energy/forces/virial(B::IPBasis, at) (reference call sites
+// src/datatypes.jl:28,40,65) + vec_obs (src/datatypes.jl:26,42-50,69-76) +
+// the block placement db.Psi[irows,:] = ... (src/lsq_db.jl:268-278).
+//
+// Decomposition ("own-leg"): one thread per ORDERED neighbour pair p = (i, j).
+// With position 1 of every cluster pinned to the thread's own neighbour j, the
+// thread loops over all unordered sets K of the other N-2 neighbours of i and
+// accumulates, per basis function b,
+//     S0 = sum_K FC' P_b            S1 = sum_K FC' dP_b/dx_1
+//     T  = sum_K FC' sum_c dP_b/dw_1c (Rhat_c - w_1c Rhat_j)          FC' = prod_{k in K} fc_k
+// so that   g_p = dV_b(i)/dR_ij = (fc_j' S0 + fc_j x_j' S1) Rhat_j + fc_j/r_j T
+//           e_p = fc_j S0 / (N-1)       (each cluster is visited once per leg)
+// No atomics: (g_p, e_p) go to an L2-resident scratch tile owned by the CTA and
+// are gathered in a fixed order:
+//     E_b      = sum_p e_p
+//     F_b[a]   = sum_{p in out(a)} (g_p - g_rev(p))          rev(i,j,S) = (j,i,-S)
+//     Vir_b    = - sum_p g_p (x) R_p
+#include "ipf_common.cuh"
+
+namespace {
+
+constexpr int REC = 8;   // doubles per pair record: Rh[3], 1/r, x, dx/dr, fc, dfc/dr
+constexpr double kPi = 3.14159265358979323846;
+
+__global__ void pair_record_kernel(int64_t npairs, const double* __restrict__ pR, int transform, double a,
+                                   double r0, double rc1, double rc2, int maxdeg, double* __restrict__ rec,
+                                   double* __restrict__ xpow) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    const double Rx = pR[3 * p], Ry = pR[3 * p + 1], Rz = pR[3 * p + 2];
+    const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(Rx, Rx), __dmul_rn(Ry, Ry)), __dmul_rn(Rz, Rz)));
+    double x, dx, fc, dfc;
+    if (transform == 0) {
+        x = exp(-a * (r / r0 - 1.0));
+        dx = -a / r0 * x;
+    } else {
+        x = pow(r0 / r, a);
+        dx = -a * x / r;
+    }
+    if (r <= rc1) { fc = 1.0; dfc = 0.0; }
+    else if (r >= rc2) { fc = 0.0; dfc = 0.0; }
+    else {
+        const double w = rc2 - rc1, s = (r - rc1) / w;
+        fc = 0.5 * (1.0 + cos(kPi * s));
+        dfc = -0.5 * kPi / w * sin(kPi * s);
+    }
+    double* o = rec + REC * p;
+    o[0] = Rx / r; o[1] = Ry / r; o[2] = Rz / r; o[3] = 1.0 / r;
+    o[4] = x; o[5] = dx; o[6] = fc; o[7] = dfc;
+    double v = 1.0;
+    for (int e = 0; e <= maxdeg; ++e) { xpow[(int64_t)e * npairs + p] = v; v *= x; }
+}
+
+__device__ __forceinline__ double ipow(double w, int e) {
+    double v = 1.0;
+    for (int k = 0; k < e; ++k) v *= w;
+    return v;
+}
+
+struct GenArgs {
+    int nb, unit, nunits, maxpairs;
+    int64_t nitems, ncfg;
+    const int32_t* mono_start;
+    const uint8_t* mono_exp;
+    const int64_t* atom_off;
+    const int64_t* cfg_pair_off;   // [ncfg+1]
+    const int64_t* site_off;
+    const int32_t* pi;
+    const int32_t* prev;
+    const double* pR;
+    const double* rec;
+    const double* xpow;
+    int64_t npairs;
+    const int64_t* rowE;
+    const int64_t* rowF;
+    const int64_t* rowV;
+    double* Psi;
+    int64_t ld, col0;
+    double* scratch;       // [gridDim][unit][maxpairs][4]
+    int* counter;
+};
+
+constexpr int GEN_THREADS = 256;
+constexpr int MAX_UNIT_MONO = 1024;
+
+// One cluster: own leg p + NX-1 others (chunk-global pair indices in oth[]).
+// Accumulates S0, S1, T for basis function with monomials [m0, m1).
+template <int NX>
+__device__ __forceinline__ void cluster_accumulate(const GenArgs& A, int64_t p, const int64_t* oth,
+                                                   const double* __restrict__ ownrec, const uint8_t* __restrict__ sexp,
+                                                   int m0, int m1, double& S0, double& S1, double* T) {
+    constexpr int NO = NX - 1;
+    constexpr int NPAIR = NX * (NX - 1) / 2;
+    double orec_rh[NO > 0 ? NO : 1][3];
+    double FCp = 1.0;
+#pragma unroll
+    for (int c = 0; c < NO; ++c) {
+        const double* r = A.rec + REC * oth[c];
+        orec_rh[c][0] = r[0]; orec_rh[c][1] = r[1]; orec_rh[c][2] = r[2];
+        FCp *= r[6];
+    }
+    // w variables in lexicographic pair order (0,1),(0,2),..,(1,2),..  position 0 = own leg
+    double w[NPAIR > 0 ? NPAIR : 1];
+    {
+        int k = 0;
+#pragma unroll
+        for (int a = 0; a < NX; ++a)
+#pragma unroll
+            for (int c = a + 1; c < NX; ++c) {
+                const double* ra = (a == 0) ? ownrec : orec_rh[a - 1];
+                const double* rc = orec_rh[c - 1];
+                w[k++] = ra[0] * rc[0] + ra[1] * rc[1] + ra[2] * rc[2];
+            }
+    }
+    double P = 0.0, dPx = 0.0;
+    double dPw[NO > 0 ? NO : 1];
+#pragma unroll
+    for (int c = 0; c < NO; ++c) dPw[c] = 0.0;
+    for (int m = m0; m < m1; ++m) {
+        const uint8_t* ex = sexp + m * IPF_MAX_VARS;
+        const int e0 = ex[0];
+        const double Aown = A.xpow[(int64_t)e0 * A.npairs + p];
+        const double dAown = e0 > 0 ? (double)e0 * A.xpow[(int64_t)(e0 - 1) * A.npairs + p] : 0.0;
+        double rest = 1.0;
+#pragma unroll
+        for (int c = 0; c < NO; ++c) rest *= A.xpow[(int64_t)ex[1 + c] * A.npairs + oth[c]];
+        // w pairs not touching the own leg
+#pragma unroll
+        for (int k = NO; k < NPAIR; ++k) rest *= ipow(w[k], ex[NX + k]);
+        double wv[NO > 0 ? NO : 1], dwv[NO > 0 ? NO : 1];
+        double W0 = 1.0;
+#pragma unroll
+        for (int c = 0; c < NO; ++c) {
+            const int e = ex[NX + c];
+            const double wm1 = e > 0 ? ipow(w[c], e - 1) : 0.0;
+            wv[c] = e > 0 ? wm1 * w[c] : 1.0;
+            dwv[c] = (double)e * wm1;
+            W0 *= wv[c];
+        }
+        const double base = rest * W0;
+        P += Aown * base;
+        dPx += dAown * base;
+#pragma unroll
+        for (int c = 0; c < NO; ++c) {
+            double o = Aown * rest * dwv[c];
+#pragma unroll
+            for (int c2 = 0; c2 < NO; ++c2) if (c2 != c) o *= wv[c2];
+            dPw[c] += o;
+        }
+    }
+    S0 += FCp * P;
+    S1 += FCp * dPx;
+#pragma unroll
+    for (int c = 0; c < NO; ++c) {
+        const double g = FCp * dPw[c];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) T[d] += g * (orec_rh[c][d] - w[c] * ownrec[d]);
+    }
+}
+
+template <int NX>
+__global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs A) {
+    __shared__ int s_item;
+    __shared__ int s_mstart[64 + 1];
+    __shared__ uint8_t s_exp[MAX_UNIT_MONO * IPF_MAX_VARS];
+    const int tid = threadIdx.x;
+    double* G = A.scratch + (size_t)blockIdx.x * A.unit * A.maxpairs * 4;
+    for (;;) {
+        if (tid == 0) s_item = atomicAdd(A.counter, 1);
+        __syncthreads();
+        const int64_t item = s_item;
+        if (item >= A.nitems) break;
+        const int64_t c = item / A.nunits;
+        const int u = (int)(item % A.nunits);
+        const int b0 = u * A.unit;
+        const int nbu = min(A.nb - b0, A.unit);
+        const int mbase = A.mono_start[b0];
+        for (int k = tid; k <= nbu; k += blockDim.x) s_mstart[k] = A.mono_start[b0 + k] - mbase;
+        const int nm = A.mono_start[b0 + nbu] - mbase;
+        for (int k = tid; k < nm * IPF_MAX_VARS; k += blockDim.x) s_exp[k] = A.mono_exp[(size_t)mbase * IPF_MAX_VARS + k];
+        __syncthreads();
+        const int64_t P0 = A.cfg_pair_off[c], P1 = A.cfg_pair_off[c + 1];
+        const int npc = (int)(P1 - P0);
+        const int64_t a0 = A.atom_off[c];
+        const int nat = (int)(A.atom_off[c + 1] - a0);
+        // ---- phase A: per ordered pair, per basis function ----
+        for (int pl = tid; pl < npc; pl += blockDim.x) {
+            const int64_t p = P0 + pl;
+            double own[REC];
+#pragma unroll
+            for (int k = 0; k < REC; ++k) own[k] = A.rec[REC * p + k];
+            const int64_t s = a0 + A.pi[p];
+            const int64_t o0 = A.site_off[s], o1 = A.site_off[s + 1];
+            for (int bl = 0; bl < nbu; ++bl) {
+                const int m0 = s_mstart[bl], m1 = s_mstart[bl + 1];
+                double S0 = 0.0, S1 = 0.0, T[3] = {0.0, 0.0, 0.0};
+                int64_t oth[3] = {0, 0, 0};
+                if (NX == 1) {
+                    cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                } else if (NX == 2) {
+                    for (int64_t k = o0; k < o1; ++k) {
+                        if (k == p) continue;
+                        oth[0] = k;
+                        cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                    }
+                } else if (NX == 3) {
+                    for (int64_t k = o0; k < o1; ++k) {
+                        if (k == p) continue;
+                        for (int64_t l = k + 1; l < o1; ++l) {
+                            if (l == p) continue;
+                            oth[0] = k; oth[1] = l;
+                            cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                        }
+                    }
+                } else {
+                    for (int64_t k = o0; k < o1; ++k) {
+                        if (k == p) continue;
+                        for (int64_t l = k + 1; l < o1; ++l) {
+                            if (l == p) continue;
+                            for (int64_t q = l + 1; q < o1; ++q) {
+                                if (q == p) continue;
+                                oth[0] = k; oth[1] = l; oth[2] = q;
+                                cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                            }
+                        }
+                    }
+                }
+                const double radial = own[7] * S0 + own[6] * own[5] * S1;
+                const double tang = own[6] * own[3];
+                double* g = G + ((size_t)bl * A.maxpairs + pl) * 4;
+                g[0] = radial * own[0] + tang * T[0];
+                g[1] = radial * own[1] + tang * T[1];
+                g[2] = radial * own[2] + tang * T[2];
+                g[3] = own[6] * S0 / (double)NX;
+            }
+        }
+        __syncthreads();
+        // ---- phase B: deterministic gather into Psi ----
+        const int64_t rE = A.rowE[c], rF = A.rowF[c], rV = A.rowV[c];
+        if (rF) {
+            const int nrow = 3 * nat;
+            for (int idx = tid; idx < nbu * nrow; idx += blockDim.x) {
+                const int bl = idx / nrow, rd = idx - bl * nrow;
+                const int at = rd / 3, d = rd - 3 * at;
+                const int64_t s = a0 + at;
+                const double* Gb = G + (size_t)bl * A.maxpairs * 4;
+                double acc = 0.0;
+                for (int64_t p = A.site_off[s]; p < A.site_off[s + 1]; ++p)
+                    acc += Gb[(p - P0) * 4 + d] - Gb[((int64_t)A.prev[p] - P0) * 4 + d];
+                A.Psi[(size_t)(A.col0 + b0 + bl) * A.ld + (rF - 1) + rd] = acc;
+            }
+        }
+        {
+            // warp per (bl, comp): comp 0 = E, 1..6 = Voigt (xx,yy,zz,zy,zx,yx)
+            const int warp = tid >> 5, lane = tid & 31, nwarp = blockDim.x >> 5;
+            for (int t = warp; t < nbu * 7; t += nwarp) {
+                const int bl = t / 7, comp = t - 7 * bl;
+                if (comp == 0 ? !rE : !rV) continue;
+                const double* Gb = G + (size_t)bl * A.maxpairs * 4;
+                double acc = 0.0;
+                if (comp == 0) {
+                    for (int pl = lane; pl < npc; pl += 32) acc += Gb[(size_t)pl * 4 + 3];
+                } else {
+                    const int pp = (comp == 1) ? 0 : (comp == 2) ? 1 : (comp == 3) ? 2 : (comp == 4) ? 2 : (comp == 5) ? 2 : 1;
+                    const int qq = (comp == 1) ? 0 : (comp == 2) ? 1 : (comp == 3) ? 2 : (comp == 4) ? 1 : (comp == 5) ? 0 : 0;
+                    for (int pl = lane; pl < npc; pl += 32) acc -= Gb[(size_t)pl * 4 + pp] * A.pR[3 * (P0 + pl) + qq];
+                }
+                acc = warp_sum(acc);
+                if (lane == 0) {
+                    const int64_t row = (comp == 0) ? (rE - 1) : (rV - 1 + comp - 1);
+                    A.Psi[(size_t)(A.col0 + b0 + bl) * A.ld + row] = acc;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                               ipf_matrix* Psi) {
+    cudaStream_t st = ctx->stream;
+    if (ch.ncfg == 0 || blk.nb == 0) return IPF_OK;
+    const int64_t npairs = nl.npairs;
+    // pair records + power table for this descriptor
+    void *rec = nullptr, *xpow = nullptr, *scr = nullptr, *cpo = nullptr, *cnt = nullptr;
+    IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * REC * (size_t)(npairs + 1), &rec));
+    IPF_CHECK(ipf_scratch(ctx, 2, sizeof(double) * (size_t)(blk.maxdeg + 1) * (size_t)(npairs + 1), &xpow));
+    if (npairs > 0) {
+        pair_record_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(
+            npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, (double*)rec, (double*)xpow);
+        ctx->launches++;
+    }
+    // unit size: bounded by the shared-memory monomial table and by 64 functions
+    int unit = 64;
+    {
+        // largest unit such that any run of `unit` consecutive functions has <= MAX_UNIT_MONO monomials
+        for (;;) {
+            bool ok = true;
+            for (int b0 = 0; b0 < blk.nb && ok; b0 += unit) {
+                const int b1 = std::min(blk.nb, b0 + unit);
+                if (blk.h_mono_start[b1] - blk.h_mono_start[b0] > MAX_UNIT_MONO) ok = false;
+            }
+            if (ok || unit == 1) break;
+            unit /= 2;
+        }
+    }
+    // keep units small enough that there are a few work items per SM
+    while (unit > 4 && (int64_t)((blk.nb + unit - 1) / unit) * ch.ncfg < 4LL * ctx->sm_count) unit /= 2;
+    const int nunits = (blk.nb + unit - 1) / unit;
+    const int grid = (int)std::min<int64_t>((int64_t)ch.ncfg * nunits, 2LL * ctx->sm_count);
+    const int maxpairs = std::max(1, nl.maxpairs_cfg);
+    IPF_CHECK(ipf_scratch(ctx, 3, sizeof(double) * 4 * (size_t)grid * unit * maxpairs, &scr));
+    IPF_CHECK(ipf_scratch(ctx, 4, sizeof(int64_t) * (size_t)(ch.ncfg + 1), &cpo));
+    IPF_CHECK(ipf_scratch(ctx, 5, 256, &cnt));
+    IPF_CUDA(ctx, cudaMemcpyAsync(cpo, nl.h_cfg_pair_off.data(), sizeof(int64_t) * (ch.ncfg + 1),
+                                  cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int), st));
+    GenArgs A;
+    A.nb = blk.nb; A.unit = unit; A.nunits = nunits; A.maxpairs = maxpairs;
+    A.nitems = (int64_t)ch.ncfg * nunits; A.ncfg = ch.ncfg;
+    A.mono_start = blk.mono_start; A.mono_exp = blk.mono_exp;
+    A.atom_off = ch.atom_off.p; A.cfg_pair_off = (const int64_t*)cpo; A.site_off = nl.site_off.p;
+    A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = (const double*)rec; A.xpow = (const double*)xpow;
+    A.npairs = npairs; A.rowE = ch.rowE.p; A.rowF = ch.rowF.p; A.rowV = ch.rowV.p;
+    A.Psi = Psi->d; A.ld = Psi->ld; A.col0 = blk.col0; A.scratch = (double*)scr; A.counter = (int*)cnt;
+    switch (blk.N) {
+        case 2: site_deriv_generic_kernel<1><<<grid, GEN_THREADS, 0, st>>>(A); break;
+        case 3: site_deriv_generic_kernel<2><<<grid, GEN_THREADS, 0, st>>>(A); break;
+        case 4: site_deriv_generic_kernel<3><<<grid, GEN_THREADS, 0, st>>>(A); break;
+        case 5: site_deriv_generic_kernel<4><<<grid, GEN_THREADS, 0, st>>>(A); break;
+        default: return ipf_set_error(ctx, IPF_EINVAL, "body-order %d not supported", blk.N);
+    }
+    ctx->launches++;
+    IPF_CUDA(ctx, cudaGetLastError());
+    // the host copy of cfg_pair_off must outlive the async copy
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    return IPF_OK;
+}

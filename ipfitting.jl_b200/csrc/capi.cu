@@ -1,0 +1,331 @@
+// capi.cu -- extern "C" entry points of libipf_b200 (see include/ipf_b200.h).
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+
+#include "ipf_common.cuh"
+
+int ipf_set_error(ipf_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out) {
+    if (bytes == 0) bytes = 16;
+    if (ctx->scratch_bytes[slot] < bytes) {
+        if (ctx->scratch[slot]) {
+            IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->scratch[slot]);
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_bytes[slot] = 0;
+        }
+        size_t want = bytes + bytes / 4;
+        IPF_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], want));
+        ctx->scratch_bytes[slot] = want;
+    }
+    *out = ctx->scratch[slot];
+    return IPF_OK;
+}
+
+extern "C" {
+
+int32_t ipf_init(int32_t device, ipf_ctx** out) {
+    if (!out) return IPF_EINVAL;
+    *out = nullptr;
+    ipf_ctx* ctx = new (std::nothrow) ipf_ctx();
+    if (!ctx) return IPF_ENOMEM;
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int sm = 0;
+        e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
+        if (e == cudaSuccess && sm > 0) ctx->sm_count = sm;
+    }
+    if (e != cudaSuccess) {
+        // leave the ctx alive so that the caller can read the message
+        ipf_set_error(ctx, IPF_ECUDA, "ipf_init(device=%d): %s", device, cudaGetErrorString(e));
+        *out = ctx;
+        return IPF_ECUDA;
+    }
+    *out = ctx;
+    return IPF_OK;
+}
+
+int32_t ipf_destroy(ipf_ctx* ctx) {
+    if (!ctx) return IPF_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int k = 0; k < 8; ++k)
+        if (ctx->scratch[k]) cudaFree(ctx->scratch[k]);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return IPF_OK;
+}
+
+const char* ipf_last_error(ipf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int64_t ipf_launch_count(ipf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* ipf_stream(ipf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+// ---------------------------------------------------------------- basis
+int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* blocks, ipf_basis** out) {
+    if (!ctx || !out || nblocks <= 0 || !blocks) return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: bad arguments");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    ipf_basis* B = new (std::nothrow) ipf_basis();
+    if (!B) return IPF_ENOMEM;
+    int64_t col = 0;
+    for (int k = 0; k < nblocks; ++k) {
+        const ipf_block_spec& s = blocks[k];
+        const int nx = s.N - 1, nv = nx + nx * (nx - 1) / 2;
+        if (s.N < 2 || s.N > 5 || s.nb <= 0 || s.nmono < s.nb || !s.mono_b || !s.mono_exp ||
+            !(s.rc1 > 0.0 && s.rc2 > s.rc1) || !(s.r0 > 0.0) || (s.transform != 0 && s.transform != 1)) {
+            delete B;
+            return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d has invalid parameters", k);
+        }
+        BlockDev b;
+        b.N = s.N; b.nb = s.nb; b.nmono = s.nmono; b.transform = s.transform;
+        b.a = s.a; b.r0 = s.r0; b.rc1 = s.rc1; b.rc2 = s.rc2; b.col0 = col;
+        b.h_mono_start.assign(s.nb + 1, 0);
+        b.h_mono_exp.assign(s.mono_exp, s.mono_exp + (size_t)s.nmono * IPF_MAX_VARS);
+        int prevb = 0;
+        for (int m = 0; m < s.nmono; ++m) {
+            const int bb = s.mono_b[m];
+            if (bb < prevb || bb >= s.nb || bb > prevb + 1) {
+                delete B;
+                return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: mono_b must be non-decreasing without gaps", k);
+            }
+            prevb = bb;
+            b.h_mono_start[bb + 1]++;
+            int deg = 0;
+            for (int v = 0; v < IPF_MAX_VARS; ++v) {
+                const int e = s.mono_exp[(size_t)m * IPF_MAX_VARS + v];
+                if (v >= nv && e != 0) {
+                    delete B;
+                    return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: exponent on unused variable", k);
+                }
+                deg = std::max(deg, e);
+            }
+            b.maxdeg = std::max(b.maxdeg, deg);
+        }
+        if (b.maxdeg > IPF_MAX_DEGREE) {
+            delete B;
+            return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: degree > %d", IPF_MAX_DEGREE);
+        }
+        for (int i = 0; i < s.nb; ++i) {
+            if (b.h_mono_start[i + 1] == 0) {
+                delete B;
+                return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: basis function %d has no monomial", k, i);
+            }
+            b.h_mono_start[i + 1] += b.h_mono_start[i];
+        }
+        B->blocks.push_back(std::move(b));
+        col += s.nb;
+    }
+    B->ncols = col;
+    for (auto& b : B->blocks) {
+        cudaError_t e = cudaMalloc((void**)&b.mono_start, sizeof(int32_t) * (b.nb + 1));
+        if (e == cudaSuccess) e = cudaMalloc((void**)&b.mono_exp, (size_t)b.nmono * IPF_MAX_VARS);
+        if (e == cudaSuccess) e = cudaMemcpy(b.mono_start, b.h_mono_start.data(), sizeof(int32_t) * (b.nb + 1), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(b.mono_exp, b.h_mono_exp.data(), (size_t)b.nmono * IPF_MAX_VARS, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            ipf_basis_destroy(ctx, B);
+            return ipf_set_error(ctx, IPF_ECUDA, "ipf_basis_create: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = B;
+    return IPF_OK;
+}
+
+int32_t ipf_basis_destroy(ipf_ctx* ctx, ipf_basis* B) {
+    if (!B) return IPF_OK;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (auto& b : B->blocks) {
+        if (b.mono_start) cudaFree(b.mono_start);
+        if (b.mono_exp) cudaFree(b.mono_exp);
+    }
+    delete B;
+    return IPF_OK;
+}
+
+int64_t ipf_basis_length(const ipf_basis* B) { return B ? B->ncols : 0; }
+
+// ---------------------------------------------------------------- matrix
+int32_t ipf_matrix_create(ipf_ctx* ctx, int64_t nrows, int64_t ncols, ipf_matrix** out) {
+    if (!ctx || !out || nrows < 0 || ncols < 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_matrix_create: bad arguments");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    ipf_matrix* M = new (std::nothrow) ipf_matrix();
+    if (!M) return IPF_ENOMEM;
+    M->nrows = nrows; M->ncols = ncols; M->ld = nrows;
+    const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(1, nrows * ncols);
+    cudaError_t e = cudaMalloc((void**)&M->d, bytes);
+    if (e != cudaSuccess) {
+        delete M;
+        return ipf_set_error(ctx, IPF_ENOMEM, "ipf_matrix_create(%lld x %lld): %s", (long long)nrows, (long long)ncols, cudaGetErrorString(e));
+    }
+    IPF_CUDA(ctx, cudaMemsetAsync(M->d, 0, bytes, ctx->stream));
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = M;
+    return IPF_OK;
+}
+
+int32_t ipf_matrix_destroy(ipf_ctx* ctx, ipf_matrix* M) {
+    if (!M) return IPF_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (M->d) cudaFree(M->d);
+    delete M;
+    return IPF_OK;
+}
+
+int32_t ipf_matrix_to_host(ipf_ctx* ctx, const ipf_matrix* M, double* host, int64_t ld) {
+    if (!ctx || !M || !host || ld < M->nrows) return ipf_set_error(ctx, IPF_EINVAL, "ipf_matrix_to_host: bad arguments");
+    if (M->nrows == 0 || M->ncols == 0) return IPF_OK;
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    IPF_CUDA(ctx, cudaMemcpy2DAsync(host, sizeof(double) * ld, M->d, sizeof(double) * M->ld,
+                                    sizeof(double) * M->nrows, M->ncols, cudaMemcpyDeviceToHost, ctx->stream));
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPF_OK;
+}
+
+int32_t ipf_matrix_from_host(ipf_ctx* ctx, ipf_matrix* M, const double* host, int64_t ld) {
+    if (!ctx || !M || !host || ld < M->nrows) return ipf_set_error(ctx, IPF_EINVAL, "ipf_matrix_from_host: bad arguments");
+    if (M->nrows == 0 || M->ncols == 0) return IPF_OK;
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    IPF_CUDA(ctx, cudaMemcpy2DAsync(M->d, sizeof(double) * M->ld, host, sizeof(double) * ld,
+                                    sizeof(double) * M->nrows, M->ncols, cudaMemcpyHostToDevice, ctx->stream));
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPF_OK;
+}
+
+int64_t ipf_matrix_rows(const ipf_matrix* M) { return M ? M->nrows : 0; }
+int64_t ipf_matrix_cols(const ipf_matrix* M) { return M ? M->ncols : 0; }
+int64_t ipf_matrix_ld(const ipf_matrix* M) { return M ? M->ld : 0; }
+void* ipf_matrix_device_ptr(const ipf_matrix* M) { return M ? (void*)M->d : nullptr; }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- chunk upload
+static int upload_chunk(ipf_ctx* ctx, int64_t c0, int64_t c1, const int64_t* atom_off, const double* pos,
+                        const double* cell, const uint8_t* pbc, const int64_t* rowE, const int64_t* rowF,
+                        const int64_t* rowV, ChunkDev& ch) {
+    cudaStream_t st = ctx->stream;
+    const int64_t ncfg = c1 - c0;
+    const int64_t a0 = atom_off[c0], natoms = atom_off[c1] - a0;
+    ch.ncfg = ncfg; ch.natoms = natoms;
+    ch.h_atom_off.resize(ncfg + 1);
+    for (int64_t c = 0; c <= ncfg; ++c) ch.h_atom_off[c] = atom_off[c0 + c] - a0;
+    std::vector<int64_t> zeros(ncfg, 0);
+    IPF_CUDA(ctx, ch.atom_off.alloc(ncfg + 1));
+    IPF_CUDA(ctx, ch.pos.alloc(3 * natoms));
+    IPF_CUDA(ctx, ch.cell.alloc(9 * ncfg));
+    IPF_CUDA(ctx, ch.pbc.alloc(3 * ncfg));
+    IPF_CUDA(ctx, ch.rowE.alloc(ncfg));
+    IPF_CUDA(ctx, ch.rowF.alloc(ncfg));
+    IPF_CUDA(ctx, ch.rowV.alloc(ncfg));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ch.atom_off.p, ch.h_atom_off.data(), sizeof(int64_t) * (ncfg + 1), cudaMemcpyHostToDevice, st));
+    if (natoms) IPF_CUDA(ctx, cudaMemcpyAsync(ch.pos.p, pos + 3 * a0, sizeof(double) * 3 * natoms, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ch.cell.p, cell + 9 * c0, sizeof(double) * 9 * ncfg, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ch.pbc.p, pbc + 3 * c0, 3 * ncfg, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ch.rowE.p, rowE ? rowE + c0 : zeros.data(), sizeof(int64_t) * ncfg, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ch.rowF.p, rowF ? rowF + c0 : zeros.data(), sizeof(int64_t) * ncfg, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ch.rowV.p, rowV ? rowV + c0 : zeros.data(), sizeof(int64_t) * ncfg, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    return IPF_OK;
+}
+
+static int validate_configs(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
+                            const double* cell) {
+    if (atom_off[0] != 0) return ipf_set_error(ctx, IPF_EINVAL, "atom_off[0] must be 0");
+    for (int64_t c = 0; c < ncfg; ++c) {
+        const int64_t n = atom_off[c + 1] - atom_off[c];
+        if (n < 0 || n > IPF_MAX_ATOMS)
+            return ipf_set_error(ctx, IPF_EINVAL, "config %lld has %lld atoms (limit %d)", (long long)c, (long long)n, IPF_MAX_ATOMS);
+        const double* C = cell + 9 * c;
+        const double det = C[0] * (C[4] * C[8] - C[5] * C[7]) - C[1] * (C[3] * C[8] - C[5] * C[6]) + C[2] * (C[3] * C[7] - C[4] * C[6]);
+        if (!(std::fabs(det) > 0.0) || !std::isfinite(det))
+            return ipf_set_error(ctx, IPF_EINVAL, "config %lld has a singular cell", (long long)c);
+    }
+    const int64_t nat = atom_off[ncfg];
+    for (int64_t k = 0; k < 3 * nat; ++k)
+        if (!std::isfinite(pos[k])) return ipf_set_error(ctx, IPF_EINVAL, "non-finite position");
+    return IPF_OK;
+}
+
+extern "C" {
+
+int32_t ipf_neighbours(ipf_ctx* ctx, int32_t nat, const double* pos, const double* cell, const uint8_t* pbc,
+                       double rcut, int64_t cap, int64_t* n, int32_t* I, int32_t* J, int32_t* S, double* R) {
+    if (!ctx || nat < 0 || !pos || !cell || !pbc || !n || !(rcut > 0.0))
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_neighbours: bad arguments");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    int64_t off[2] = {0, nat};
+    IPF_CHECK(validate_configs(ctx, 1, off, pos, cell));
+    ChunkDev ch;
+    IPF_CHECK(upload_chunk(ctx, 0, 1, off, pos, cell, pbc, nullptr, nullptr, nullptr, ch));
+    NeighList nl;
+    IPF_CHECK(ipf_build_neighbours(ctx, ch, rcut, nl));
+    *n = nl.npairs;
+    const int64_t m = std::min<int64_t>(cap, nl.npairs);
+    if (m > 0) {
+        if (I) IPF_CUDA(ctx, cudaMemcpy(I, nl.pi.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+        if (J) IPF_CUDA(ctx, cudaMemcpy(J, nl.pj.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
+        if (S) IPF_CUDA(ctx, cudaMemcpy(S, nl.pS.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost));
+        if (R) IPF_CUDA(ctx, cudaMemcpy(R, nl.pR.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+    }
+    return IPF_OK;
+}
+
+int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg, const int64_t* atom_off,
+                     const double* pos, const double* cell, const uint8_t* pbc, const int32_t* Z,
+                     const int64_t* rowE, const int64_t* rowF, const int64_t* rowV, ipf_matrix* Psi) {
+    (void)Z;
+    if (!ctx || !basis || ncfg < 0 || !atom_off || !cell || !pbc || !rowE || !rowF || !rowV || !Psi)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: bad arguments");
+    if (Psi->ncols != basis->ncols)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: Psi has %lld columns, basis has %lld",
+                             (long long)Psi->ncols, (long long)basis->ncols);
+    if (ncfg == 0) return IPF_OK;
+    if (!pos && atom_off[ncfg] > 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: pos is NULL");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    IPF_CHECK(validate_configs(ctx, ncfg, atom_off, pos, cell));
+    // row blocks must lie inside the matrix
+    for (int64_t c = 0; c < ncfg; ++c) {
+        const int64_t nat = atom_off[c + 1] - atom_off[c];
+        const int64_t r[3] = {rowE[c], rowF[c], rowV[c]};
+        const int64_t len[3] = {1, 3 * nat, 6};
+        for (int k = 0; k < 3; ++k)
+            if (r[k] < 0 || (r[k] > 0 && r[k] - 1 + len[k] > Psi->nrows))
+                return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: config %lld: row block out of range", (long long)c);
+    }
+    // chunks of configurations: bounded scratch, one neighbour list per distinct cutoff
+    const int64_t max_atoms_chunk = 1 << 16;
+    int64_t c0 = 0;
+    while (c0 < ncfg) {
+        int64_t c1 = c0 + 1;
+        while (c1 < ncfg && atom_off[c1 + 1] - atom_off[c0] <= max_atoms_chunk) ++c1;
+        ChunkDev ch;
+        IPF_CHECK(upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, ch));
+        std::vector<double> done_rcut;
+        for (size_t k = 0; k < basis->blocks.size(); ++k) {
+            const double rc = basis->blocks[k].rc2;
+            if (std::find(done_rcut.begin(), done_rcut.end(), rc) != done_rcut.end()) continue;
+            done_rcut.push_back(rc);
+            NeighList nl;
+            IPF_CHECK(ipf_build_neighbours(ctx, ch, rc, nl));
+            for (size_t k2 = k; k2 < basis->blocks.size(); ++k2)
+                if (basis->blocks[k2].rc2 == rc)
+                    IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], ch, nl, Psi));
+        }
+        c0 = c1;
+    }
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPF_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+// ipf_common.cuh -- shared internals of libipf_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/ipf_b200.h"
+
+struct ipf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int64_t launches = 0;
+    int sm_count = 148;
+    // reusable device scratch (grown on demand, freed with the ctx)
+    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+struct ipf_matrix {
+    int64_t nrows = 0, ncols = 0, ld = 0;
+    double* d = nullptr;
+};
+
+struct BlockDev {
+    int N = 0, nb = 0, nmono = 0, transform = 0, maxdeg = 0;
+    double a = 1, r0 = 1, rc1 = 0, rc2 = 0;
+    int64_t col0 = 0;
+    int32_t* mono_start = nullptr;   // device [nb+1]
+    uint8_t* mono_exp = nullptr;     // device [nmono][IPF_MAX_VARS]
+    std::vector<int32_t> h_mono_start;
+    std::vector<uint8_t> h_mono_exp;
+};
+
+struct ipf_basis {
+    std::vector<BlockDev> blocks;
+    int64_t ncols = 0;
+};
+
+int ipf_set_error(ipf_ctx* ctx, int code, const char* fmt, ...);
+
+#define IPF_CUDA(ctx, call)                                                                  \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess)                                                              \
+            return ipf_set_error((ctx), e__ == cudaErrorMemoryAllocation ? IPF_ENOMEM : IPF_ECUDA, \
+                                 "%s:%d: %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+#define IPF_CHECK(call)                \
+    do {                               \
+        int rc__ = (call);             \
+        if (rc__ != IPF_OK) return rc__; \
+    } while (0)
+
+// grow-only scratch slot
+int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out);
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    cudaError_t alloc(size_t count) {
+        if (p) { cudaFree(p); p = nullptr; }
+        n = count;
+        return cudaMalloc((void**)&p, sizeof(T) * (count ? count : 1));
+    }
+};
+
+// ---- neighbour list of a chunk of configurations (device resident) -------
+struct NeighList {
+    int64_t nsites = 0;       // atoms in the chunk
+    int64_t npairs = 0;
+    int32_t maxpairs_cfg = 0; // max pairs of one config
+    double rcut = 0;
+    DevBuf<int64_t> site_off;     // [nsites+1] pair offsets (chunk-global)
+    DevBuf<int32_t> pi;           // [npairs] centre atom, local index in its config
+    DevBuf<int32_t> pj;           // [npairs] neighbour atom, local index in its config
+    DevBuf<int32_t> pS;           // [npairs*3] image shift
+    DevBuf<double> pR;            // [npairs*3] bond vector R_ij = X_j + S C - X_i
+    DevBuf<int32_t> prev;         // [npairs] chunk-global index of the reverse pair (j,i,-S)
+    std::vector<int64_t> h_cfg_pair_off;   // [ncfg+1] host copy of per-config pair offsets
+};
+
+// Config chunk resident on the device
+struct ChunkDev {
+    int64_t ncfg = 0, natoms = 0;
+    DevBuf<int64_t> atom_off;   // [ncfg+1], chunk-local
+    DevBuf<double> pos;         // [3*natoms]
+    DevBuf<double> cell;        // [9*ncfg]
+    DevBuf<uint8_t> pbc;        // [3*ncfg]
+    DevBuf<int64_t> rowE, rowF, rowV;   // [ncfg] 1-based, 0 = absent
+    std::vector<int64_t> h_atom_off;
+};
+
+int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighList& nl);
+int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
+                               const NeighList& nl, ipf_matrix* Psi);
+
+// ---- device helpers ---------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,306 @@
+// neigh.cu -- K1: per-configuration linked-cell neighbour build with periodic images.
+//
+// Replaces JuLIP.neighbourlist(at, rcut) as called inside energy/forces/virial
+// (reference call sites src/datatypes.jl:28,40,65; src/preconditioners.jl:56).
+// Output is the canonical CSR: for every centre atom i all (j, S) with
+// |X_j + S C - X_i| < rcut, (j,S) != (i,0), sorted by (j, Sx, Sy, Sz).
+// The accept test uses individually rounded operations in the same order as the
+// oracle (oracle/ipf_oracle.c: bond()), so the list is bit-exact, including the
+// borderline pairs.  Candidate generation (binning, images) is free to differ.
+#include <cub/device/device_scan.cuh>
+
+#include "ipf_common.cuh"
+
+namespace {
+
+constexpr int NC_MAX = 8;                      // cells per direction
+constexpr int NCELL_MAX = NC_MAX * NC_MAX * NC_MAX;
+constexpr int SHIFT_BIAS = 512;
+
+struct GridInfo {          // per config
+    int ncell[3];
+    int m[3];              // search range in cells
+    double Ci[9];          // inverse cell (s = X * Ci)
+};
+
+__device__ __forceinline__ void inv3(const double* C, double* Ci) {
+    double a = C[0], b = C[1], c = C[2], d = C[3], e = C[4], f = C[5], g = C[6], h = C[7], k = C[8];
+    double det = a * (e * k - f * h) - b * (d * k - f * g) + c * (d * h - e * g);
+    double id = 1.0 / det;
+    Ci[0] = (e * k - f * h) * id; Ci[1] = (c * h - b * k) * id; Ci[2] = (b * f - c * e) * id;
+    Ci[3] = (f * g - d * k) * id; Ci[4] = (a * k - c * g) * id; Ci[5] = (c * d - a * f) * id;
+    Ci[6] = (d * h - e * g) * id; Ci[7] = (b * g - a * h) * id; Ci[8] = (a * e - b * d) * id;
+}
+
+// one CTA per config: grid geometry, wrap counts, cell ids, cell-sorted atom list
+__global__ void nl_bin_kernel(const int64_t* __restrict__ atom_off, const double* __restrict__ pos,
+                              const double* __restrict__ cell, const uint8_t* __restrict__ pbc,
+                              double rcut, GridInfo* __restrict__ grid, int32_t* __restrict__ cell_start,
+                              int32_t* __restrict__ cell_atoms, int32_t* __restrict__ atom_cell,
+                              int32_t* __restrict__ atom_wrap) {
+    const int c = blockIdx.x;
+    const int64_t a0 = atom_off[c];
+    const int nat = (int)(atom_off[c + 1] - a0);
+    __shared__ GridInfo g;
+    __shared__ int cnt[NCELL_MAX + 1];
+    if (threadIdx.x == 0) {
+        const double* C = cell + 9 * c;
+        inv3(C, g.Ci);
+        for (int a = 0; a < 3; ++a) {
+            if (!pbc[3 * c + a]) { g.ncell[a] = 1; g.m[a] = 0; continue; }
+            double n2 = g.Ci[a] * g.Ci[a] + g.Ci[3 + a] * g.Ci[3 + a] + g.Ci[6 + a] * g.Ci[6 + a];
+            double h = 1.0 / sqrt(n2);
+            int nc = (int)floor(h / (0.5 * rcut));
+            nc = nc < 1 ? 1 : (nc > NC_MAX ? NC_MAX : nc);
+            g.ncell[a] = nc;
+            g.m[a] = (int)floor(rcut / (h / nc)) + 1;
+        }
+        grid[c] = g;
+    }
+    for (int k = threadIdx.x; k <= NCELL_MAX; k += blockDim.x) cnt[k] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < nat; i += blockDim.x) {
+        const double* X = pos + 3 * (a0 + i);
+        int cid = 0;
+        for (int a = 0; a < 3; ++a) {
+            int n = 0, ci = 0;
+            if (pbc[3 * c + a]) {
+                double s = X[0] * g.Ci[a] + X[1] * g.Ci[3 + a] + X[2] * g.Ci[6 + a];
+                double fl = floor(s);
+                n = (int)fl;
+                ci = (int)((s - fl) * g.ncell[a]);
+                if (ci >= g.ncell[a]) ci = g.ncell[a] - 1;
+                if (ci < 0) ci = 0;
+            }
+            atom_wrap[3 * (a0 + i) + a] = n;
+            cid = cid * g.ncell[a] + ci;
+        }
+        atom_cell[a0 + i] = cid;
+        atomicAdd(&cnt[cid], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        const int nctot = g.ncell[0] * g.ncell[1] * g.ncell[2];
+        for (int k = 0; k < nctot; ++k) { int v = cnt[k]; cnt[k] = acc; cell_start[(int64_t)c * (NCELL_MAX + 1) + k] = acc; acc += v; }
+        for (int k = nctot; k <= NCELL_MAX; ++k) cell_start[(int64_t)c * (NCELL_MAX + 1) + k] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nat; i += blockDim.x) {
+        int slot = atomicAdd(&cnt[atom_cell[a0 + i]], 1);
+        cell_atoms[a0 + slot] = i;
+    }
+}
+
+__device__ __forceinline__ int floordiv(int a, int b) {
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// exact bond arithmetic (mirrors oracle bond())
+__device__ __forceinline__ double bond(const double* __restrict__ Xi, const double* __restrict__ Xj,
+                                       const double* __restrict__ C, int sx, int sy, int sz, double* R) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        double sh = __dadd_rn(__dadd_rn(__dmul_rn((double)sx, C[d]), __dmul_rn((double)sy, C[3 + d])),
+                              __dmul_rn((double)sz, C[6 + d]));
+        R[d] = __dadd_rn(__dsub_rn(Xj[d], Xi[d]), sh);
+    }
+    return __dadd_rn(__dadd_rn(__dmul_rn(R[0], R[0]), __dmul_rn(R[1], R[1])), __dmul_rn(R[2], R[2]));
+}
+
+// thread per centre atom.  FILL = false: count; true: write (key, S, R) in discovery order.
+template <bool FILL>
+__global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site_cfg,
+                                const int64_t* __restrict__ atom_off, const double* __restrict__ pos,
+                                const double* __restrict__ cell, double rc2,
+                                const GridInfo* __restrict__ grid, const int32_t* __restrict__ cell_start,
+                                const int32_t* __restrict__ cell_atoms, const int32_t* __restrict__ atom_cell,
+                                const int32_t* __restrict__ atom_wrap, int64_t* __restrict__ counts,
+                                const int64_t* __restrict__ site_off, unsigned long long* __restrict__ keys,
+                                double* __restrict__ Rtmp) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsites) return;
+    const int c = site_cfg[s];
+    const int64_t a0 = atom_off[c];
+    const int i = (int)(s - a0);
+    const GridInfo g = grid[c];
+    const double* C = cell + 9 * c;
+    const double* Xi = pos + 3 * s;
+    const int32_t* cs = cell_start + (int64_t)c * (NCELL_MAX + 1);
+    int cid = atom_cell[s];
+    const int cz = cid % g.ncell[2]; cid /= g.ncell[2];
+    const int cy = cid % g.ncell[1];
+    const int cx = cid / g.ncell[1];
+    const int nix = atom_wrap[3 * s], niy = atom_wrap[3 * s + 1], niz = atom_wrap[3 * s + 2];
+    int64_t n = 0;
+    const int64_t o0 = FILL ? site_off[s] : 0;
+    for (int ox = -g.m[0]; ox <= g.m[0]; ++ox) {
+        const int tx = cx + ox, sx = floordiv(tx, g.ncell[0]), ccx = tx - sx * g.ncell[0];
+        for (int oy = -g.m[1]; oy <= g.m[1]; ++oy) {
+            const int ty = cy + oy, sy = floordiv(ty, g.ncell[1]), ccy = ty - sy * g.ncell[1];
+            for (int oz = -g.m[2]; oz <= g.m[2]; ++oz) {
+                const int tz = cz + oz, sz = floordiv(tz, g.ncell[2]), ccz = tz - sz * g.ncell[2];
+                const int cc = (ccx * g.ncell[1] + ccy) * g.ncell[2] + ccz;
+                for (int q = cs[cc]; q < cs[cc + 1]; ++q) {
+                    const int j = cell_atoms[a0 + q];
+                    const int Sx = sx - atom_wrap[3 * (a0 + j)] + nix;
+                    const int Sy = sy - atom_wrap[3 * (a0 + j) + 1] + niy;
+                    const int Sz = sz - atom_wrap[3 * (a0 + j) + 2] + niz;
+                    if (j == i && Sx == 0 && Sy == 0 && Sz == 0) continue;
+                    double R[3];
+                    const double r2 = bond(Xi, pos + 3 * (a0 + j), C, Sx, Sy, Sz, R);
+                    if (r2 < rc2) {
+                        if (FILL) {
+                            keys[o0 + n] = ((unsigned long long)(unsigned)j << 32) |
+                                           ((unsigned long long)(Sx + SHIFT_BIAS) << 20) |
+                                           ((unsigned long long)(Sy + SHIFT_BIAS) << 10) |
+                                           (unsigned long long)(Sz + SHIFT_BIAS);
+                            Rtmp[3 * (o0 + n)] = R[0]; Rtmp[3 * (o0 + n) + 1] = R[1]; Rtmp[3 * (o0 + n) + 2] = R[2];
+                        }
+                        ++n;
+                    }
+                }
+            }
+        }
+    }
+    if (!FILL) counts[s] = n;
+}
+
+// thread per pair: rank within the site by key -> canonical order
+__global__ void nl_sort_kernel(int64_t npairs, int64_t nsites, const int64_t* __restrict__ site_off,
+                               const int32_t* __restrict__ site_cfg, const int64_t* __restrict__ atom_off,
+                               const unsigned long long* __restrict__ keys, const double* __restrict__ Rtmp,
+                               int32_t* __restrict__ pi, int32_t* __restrict__ pj, int32_t* __restrict__ pS,
+                               double* __restrict__ pR, unsigned long long* __restrict__ keys_sorted) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    // site of pair p: binary search in site_off
+    int64_t lo = 0, hi = nsites;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (site_off[mid] <= p) lo = mid; else hi = mid; }
+    const int64_t s = lo, o0 = site_off[s], o1 = site_off[s + 1];
+    const unsigned long long k = keys[p];
+    int rank = 0;
+    for (int64_t q = o0; q < o1; ++q) rank += (keys[q] < k);
+    const int64_t dst = o0 + rank;
+    keys_sorted[dst] = k;
+    pi[dst] = (int32_t)(s - atom_off[site_cfg[s]]);
+    pj[dst] = (int32_t)(k >> 32);
+    pS[3 * dst] = (int)((k >> 20) & 1023) - SHIFT_BIAS;
+    pS[3 * dst + 1] = (int)((k >> 10) & 1023) - SHIFT_BIAS;
+    pS[3 * dst + 2] = (int)(k & 1023) - SHIFT_BIAS;
+    pR[3 * dst] = Rtmp[3 * p]; pR[3 * dst + 1] = Rtmp[3 * p + 1]; pR[3 * dst + 2] = Rtmp[3 * p + 2];
+}
+
+// thread per pair (i,j,S): locate (j,i,-S) in site j's sorted list
+__global__ void nl_reverse_kernel(int64_t npairs, const int64_t* __restrict__ site_off,
+                                  const int32_t* __restrict__ site_cfg_of_pair_site,
+                                  const int64_t* __restrict__ atom_off, int64_t nsites,
+                                  const int32_t* __restrict__ pi, const int32_t* __restrict__ pj,
+                                  const int32_t* __restrict__ pS, const unsigned long long* __restrict__ keys_sorted,
+                                  int32_t* __restrict__ prev) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs) return;
+    int64_t lo = 0, hi = nsites;
+    while (hi - lo > 1) { int64_t mid = (lo + hi) >> 1; if (site_off[mid] <= p) lo = mid; else hi = mid; }
+    const int64_t s = lo;
+    const int64_t a0 = atom_off[site_cfg_of_pair_site[s]];
+    const int64_t sj = a0 + pj[p];
+    const unsigned long long want = ((unsigned long long)(unsigned)pi[p] << 32) |
+                                    ((unsigned long long)(-pS[3 * p] + SHIFT_BIAS) << 20) |
+                                    ((unsigned long long)(-pS[3 * p + 1] + SHIFT_BIAS) << 10) |
+                                    (unsigned long long)(-pS[3 * p + 2] + SHIFT_BIAS);
+    int64_t l = site_off[sj], h = site_off[sj + 1];
+    int32_t found = -1;
+    while (l < h) {
+        int64_t mid = (l + h) >> 1;
+        unsigned long long km = keys_sorted[mid];
+        if (km == want) { found = (int32_t)mid; break; }
+        if (km < want) l = mid + 1; else h = mid;
+    }
+    prev[p] = found;
+}
+
+}  // namespace
+
+int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighList& nl) {
+    const int64_t ncfg = ch.ncfg, nsites = ch.natoms;
+    nl.nsites = nsites;
+    nl.rcut = rcut;
+    nl.npairs = 0;
+    nl.maxpairs_cfg = 0;
+    nl.h_cfg_pair_off.assign(ncfg + 1, 0);
+    if (nsites == 0) {
+        IPF_CUDA(ctx, nl.site_off.alloc(1));
+        IPF_CUDA(ctx, cudaMemsetAsync(nl.site_off.p, 0, sizeof(int64_t), ctx->stream));
+        return IPF_OK;
+    }
+    cudaStream_t st = ctx->stream;
+    // site -> config map
+    std::vector<int32_t> h_site_cfg(nsites);
+    for (int64_t c = 0; c < ncfg; ++c)
+        for (int64_t s = ch.h_atom_off[c]; s < ch.h_atom_off[c + 1]; ++s) h_site_cfg[s] = (int32_t)c;
+    DevBuf<int32_t> site_cfg, cell_start, cell_atoms, atom_cell, atom_wrap;
+    DevBuf<GridInfo> grid;
+    DevBuf<int64_t> counts;
+    IPF_CUDA(ctx, site_cfg.alloc(nsites));
+    IPF_CUDA(ctx, cell_start.alloc((size_t)ncfg * (NCELL_MAX + 1)));
+    IPF_CUDA(ctx, cell_atoms.alloc(nsites));
+    IPF_CUDA(ctx, atom_cell.alloc(nsites));
+    IPF_CUDA(ctx, atom_wrap.alloc(3 * nsites));
+    IPF_CUDA(ctx, grid.alloc(ncfg));
+    IPF_CUDA(ctx, counts.alloc(nsites + 1));
+    IPF_CUDA(ctx, nl.site_off.alloc(nsites + 1));
+    IPF_CUDA(ctx, cudaMemcpyAsync(site_cfg.p, h_site_cfg.data(), sizeof(int32_t) * nsites,
+                                  cudaMemcpyHostToDevice, st));
+    nl_bin_kernel<<<(unsigned)ncfg, 128, 0, st>>>(ch.atom_off.p, ch.pos.p, ch.cell.p, ch.pbc.p, rcut,
+                                                  grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p);
+    ctx->launches++;
+    const double rc2 = rcut * rcut;
+    const unsigned nb_sites = (unsigned)((nsites + 127) / 128);
+    IPF_CUDA(ctx, cudaMemsetAsync(counts.p + nsites, 0, sizeof(int64_t), st));
+    nl_pairs_kernel<false><<<nb_sites, 128, 0, st>>>(nsites, site_cfg.p, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
+                                                     grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
+                                                     counts.p, nullptr, nullptr, nullptr);
+    ctx->launches++;
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st);
+    void* tmp = nullptr;
+    IPF_CHECK(ipf_scratch(ctx, 0, tmp_bytes, &tmp));
+    IPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st));
+    ctx->launches++;
+    // per-config pair offsets to the host (also gives the total)
+    std::vector<int64_t> h_site_off(nsites + 1);
+    IPF_CUDA(ctx, cudaMemcpyAsync(h_site_off.data(), nl.site_off.p, sizeof(int64_t) * (nsites + 1),
+                                  cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t npairs = h_site_off[nsites];
+    nl.npairs = npairs;
+    for (int64_t c = 0; c <= ncfg; ++c) nl.h_cfg_pair_off[c] = h_site_off[ch.h_atom_off[c]];
+    int64_t mx = 0;
+    for (int64_t c = 0; c < ncfg; ++c) mx = std::max<int64_t>(mx, nl.h_cfg_pair_off[c + 1] - nl.h_cfg_pair_off[c]);
+    nl.maxpairs_cfg = (int32_t)mx;
+    IPF_CUDA(ctx, nl.pi.alloc(npairs));
+    IPF_CUDA(ctx, nl.pj.alloc(npairs));
+    IPF_CUDA(ctx, nl.pS.alloc(3 * npairs));
+    IPF_CUDA(ctx, nl.pR.alloc(3 * npairs));
+    IPF_CUDA(ctx, nl.prev.alloc(npairs));
+    if (npairs == 0) return IPF_OK;
+    DevBuf<unsigned long long> keys, keys_sorted;
+    DevBuf<double> Rtmp;
+    IPF_CUDA(ctx, keys.alloc(npairs));
+    IPF_CUDA(ctx, keys_sorted.alloc(npairs));
+    IPF_CUDA(ctx, Rtmp.alloc(3 * npairs));
+    nl_pairs_kernel<true><<<nb_sites, 128, 0, st>>>(nsites, site_cfg.p, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
+                                                    grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
+                                                    nullptr, nl.site_off.p, keys.p, Rtmp.p);
+    const unsigned nb_pairs = (unsigned)((npairs + 255) / 256);
+    nl_sort_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nsites, nl.site_off.p, site_cfg.p, ch.atom_off.p, keys.p,
+                                             Rtmp.p, nl.pi.p, nl.pj.p, nl.pS.p, nl.pR.p, keys_sorted.p);
+    nl_reverse_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nl.site_off.p, site_cfg.p, ch.atom_off.p, nsites,
+                                                nl.pi.p, nl.pj.p, nl.pS.p, keys_sorted.p, nl.prev.p);
+    ctx->launches += 3;
+    IPF_CUDA(ctx, cudaGetLastError());
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));   // temporaries are freed on return
+    return IPF_OK;
+}

@@ -1,0 +1,74 @@
+"""K2/K3 parity: LsqDB assembly through the C-ABI against the CPU oracle."""
+import numpy as np
+import pytest
+
+import ipfitting_jl_b200 as ipf
+from ipfitting_jl_b200 import synth
+from ipfitting_jl_b200.lsq_db import LsqDB
+import ipf_oracle as O
+from util import PSI_RTOL, psi_errors, rows_for, si_desc
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(basis, configs, ctx):
+    db = LsqDB("", basis, configs, ctx=ctx)
+    rows = rows_for(configs)
+    ref = O.assemble(db.basis, configs, rows["E"], rows["F"], rows["V"], db.nrows)
+    Psi = db.Psi
+    assert Psi.shape == ref.shape
+    assert np.isfinite(Psi).all()
+    err = psi_errors(Psi, ref, configs)
+    assert err <= PSI_RTOL, f"max relative error {err:.3e}"
+    return db, ref
+
+
+def test_2b_deg14(ctx):
+    configs = synth.rattled_configs("Si", 2, 6, seed=1, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(2, si_desc(), 14)
+    db, ref = _check(B, configs, ctx)
+    assert db.Psi.shape == (6 * 199, 14)
+
+
+def test_3b(ctx):
+    configs = synth.rattled_configs("Si", 2, 3, seed=2, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(2, si_desc(), 6) + ipf.nbpolys(3, si_desc(2.0), 6)
+    _check(B, configs, ctx)
+
+
+def test_4b(ctx):
+    configs = synth.rattled_configs("Si", 1, 3, seed=3, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(3, si_desc(2.0), 4) + ipf.nbpolys(4, si_desc(1.8), 4)
+    _check(B, configs, ctx)
+
+
+def test_5b(ctx):
+    configs = synth.rattled_configs("Si", 1, 2, seed=4, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(5, si_desc(1.3, 0.5), 3)
+    _check(B, configs, ctx)
+
+
+def test_missing_observations_and_key_order(ctx):
+    """A config may hold only E (`test/test_lsq_db.jl:17-18`); key order is free (`src/obsiter.jl:43`)."""
+    base = synth.rattled_configs("Si", 1, 4, seed=5, calc=synth.StillingerWeber())
+    cfgs = [ipf.Dat(base[0].at, "a", E=base[0].D["E"]),
+            ipf.Dat(base[1].at, "b", E=base[1].D["E"], F=base[1].D["F"], V=base[1].D["V"], okey_order=("V", "F", "E")),
+            ipf.Dat(base[2].at, "c", F=base[2].D["F"]),
+            ipf.Dat(base[3].at, "d", V=base[3].D["V"], E=base[3].D["E"], okey_order=("V", "E"))]
+    B = ipf.nbpolys(2, si_desc(), 5) + ipf.nbpolys(3, si_desc(2.0), 3)
+    db, _ = _check(B, cfgs, ctx)
+    assert cfgs[1].rows["V"][0] < cfgs[1].rows["F"][0] < cfgs[1].rows["E"][0]
+
+
+def test_mixed_sizes(ctx):
+    a = synth.rattled_configs("Si", 1, 2, seed=6, calc=synth.StillingerWeber())
+    b = synth.rattled_configs("Si", 2, 2, seed=7, calc=synth.StillingerWeber())
+    c = synth.rattled_configs("W", 2, 2, seed=8, calc=synth.PairPotential(ipf.rnn("W")), vacancies=2)
+    B = ipf.nbpolys(2, si_desc(), 8) + ipf.nbpolys(3, si_desc(2.0), 4)
+    _check(B, [a[0], b[0], c[0], a[1], c[1], b[1]], ctx)
+
+
+def test_empty(ctx):
+    B = ipf.nbpolys(2, si_desc(), 3)
+    db = LsqDB("", B, [], ctx=ctx)
+    assert db.Psi.shape == (0, 3)
