@@ -54,7 +54,7 @@ extern "C" {
 typedef struct ipf_ctx ipf_ctx;
 typedef struct ipf_basis ipf_basis;
 typedef struct ipf_matrix ipf_matrix;
-typedef struct ipf_solve ipf_solve;
+typedef struct ipf_solver ipf_solver;
 
 /* One run of basis functions sharing body-order and descriptor.
  * Monomial m belongs to local basis function mono_b[m] (non-decreasing) and has
@@ -124,6 +124,54 @@ int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg,
                      const int64_t* atom_off, const double* pos, const double* cell,
                      const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
                      const int64_t* rowF, const int64_t* rowV, ipf_matrix* Psi);
+
+/* ---- solve (K4-K7) -----------------------------------------------------
+ * Weighted, column-scaled least squares on the device-resident matrix:
+ *     minimise | diag(W[I]) (Psi[I, J] diag(Dinv) c' - Y[I]) |,   c = Dinv .* c'
+ *   Y, W [nrows of Psi]: observations (Vref already subtracted) and row weights
+ *       from collect_observations (src/lsq.jl:74-109); checked for NaN (:261-262).
+ *   Irows [nIrows] 0-based row selection or NULL = all (the host builds it as
+ *       (W != 0) & (Icfg in Itrain), src/lsq.jl:270-283);  Icols likewise (Ibasis).
+ *   Dinv [nIcols] diagonal of pinv(P) (src/lsq.jl:450-458) or NULL = identity.
+ * Psi is never modified (the reference copies too, src/lsq.jl:300).
+ *
+ * Staged form (multi-GPU: one ctx per GPU holding its own rows):
+ *     ipf_solve_begin
+ *     repeat { ipf_solve_gram  -> device pointer to the local (n+1)x(n+1) Gram of [A | y]
+ *              [host: all-reduce(sum) that buffer across ranks]
+ *              ipf_solve_factor -> done? }
+ *     ipf_solve_finish -> c, R, local residual sums
+ * ipf_solve is the single-GPU one-shot.  rel_rms = |A c' - y| / |y| on the
+ * weighted, scaled system (src/lsq.jl:473). */
+int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
+                        const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,
+                        const double* Dinv, ipf_solver** S);
+int32_t ipf_solve_shape(const ipf_solver* S, int64_t* M, int64_t* n);
+/* the weighted system itself (get_lsq_system, src/lsq.jl:245-311): Aw [M x n] column-major, yw [M] */
+int32_t ipf_solve_system_to_host(ipf_ctx* ctx, const ipf_solver* S, double* Aw, int64_t ld, double* yw);
+int32_t ipf_solve_gram(ipf_ctx* ctx, ipf_solver* S, void** G_dev, int64_t* n1);
+int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done);
+/* c [n]; R_out [n*n] column-major upper factor of the scaled system, or NULL;
+ * ssr, ssy: LOCAL sums |y - A c'|^2 and |y|^2 (sum across ranks before the ratio) */
+int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, double* ssr, double* ssy);
+int32_t ipf_solve_info(const ipf_solver* S, int32_t* npasses, double* defect, double* shift,
+                       double* gram_ms, double* trsm_ms);
+int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S);
+int32_t ipf_solve(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
+                  const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,
+                  const double* Dinv, double* c, double* R_out, double* rel_rms);
+
+/* yhat [nrows] = Psi * c  (c has one entry per column of Psi).  The fit values
+ * add_fits! stores (src/lsqerrors.jl:62-77) for a potential that is linear in
+ * the basis, without re-evaluating it (README.md:114-116). */
+int32_t ipf_predict(ipf_ctx* ctx, const ipf_matrix* Psi, const double* c, double* yhat);
+
+/* Error table sums (src/lsqerrors.jl:225-266): for every row r with group[r] = g >= 0
+ *   sse[g] += (werr[r] (Yraw[r] - (Psi c)[r] - Yoff[r]))^2,  ssy[g] += (werr[r] Yraw[r])^2, cnt[g] += 1
+ * Yoff = prediction of Vref (may be NULL); werr = err_weighthook (src/datatypes.jl:30,67). */
+int32_t ipf_residual_stats(ipf_ctx* ctx, const ipf_matrix* Psi, const double* c, const double* Yraw,
+                           const double* Yoff, const double* werr, const int32_t* group,
+                           int32_t ngroups, double* sse, double* ssy, int64_t* cnt);
 
 #ifdef __cplusplus
 }

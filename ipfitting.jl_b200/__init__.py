@@ -7,3 +7,8 @@ from .datatypes import vec_obs, devec_obs, weighthook, err_weighthook
 from .obsiter import observations
 from .basis import (CosCut, BondAngleDesc, NBPoly, NBodyBasis, nbpolys, bodyorder, degree,
                     as_basis, rnn, invariant_orbits)
+from .potentials import OneBody, NBodyIP, SumIP
+from .lsq_db import LsqDB, matrows, filter_basis, filter_configs, dbpath
+from .lsq import lsqfit, get_lsq_system, collect_observations
+from .lsqerrors import add_fits, rmse, mae
+from . import synth, parallel

@@ -62,6 +62,17 @@ SIGNATURES = {
     "ipf_matrix_device_ptr": (_vp, [_vp]),
     "ipf_neighbours": (C.c_int32, [_vp, C.c_int32, _dp, _dp, _bp, C.c_double, C.c_int64, _lp, _ip, _ip, _ip, _dp]),
     "ipf_assemble": (C.c_int32, [_vp, _vp, C.c_int64, _lp, _dp, _dp, _bp, _ip, _lp, _lp, _lp, _vp]),
+    "ipf_solve_begin": (C.c_int32, [_vp, _vp, _dp, _dp, _lp, C.c_int64, _lp, C.c_int64, _dp, C.POINTER(_vp)]),
+    "ipf_solve_shape": (C.c_int32, [_vp, _lp, _lp]),
+    "ipf_solve_system_to_host": (C.c_int32, [_vp, _vp, _dp, C.c_int64, _dp]),
+    "ipf_solve_gram": (C.c_int32, [_vp, _vp, C.POINTER(_vp), _lp]),
+    "ipf_solve_factor": (C.c_int32, [_vp, _vp, _ip]),
+    "ipf_solve_finish": (C.c_int32, [_vp, _vp, _dp, _dp, _dp, _dp]),
+    "ipf_solve_info": (C.c_int32, [_vp, _ip, _dp, _dp, _dp, _dp]),
+    "ipf_solve_destroy": (C.c_int32, [_vp, _vp]),
+    "ipf_solve": (C.c_int32, [_vp, _vp, _dp, _dp, _lp, C.c_int64, _lp, C.c_int64, _dp, _dp, _dp, _dp]),
+    "ipf_predict": (C.c_int32, [_vp, _vp, _dp, _dp]),
+    "ipf_residual_stats": (C.c_int32, [_vp, _vp, _dp, _dp, _dp, _dp, _ip, C.c_int32, _dp, _dp, _lp]),
 }
 
 

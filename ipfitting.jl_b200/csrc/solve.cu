@@ -1,0 +1,656 @@
+// solve.cu -- K4/K6/K7: the weighted, column-scaled least-squares solve.
+//
+// Replaces, in the reference,
+//   Y = W.*Y ; lmul!(Diagonal(W), Psi)                    src/lsq.jl:306-307  (K4, row/col selection :270-283)
+//   Psi <- Psi * pinv(P)                                  src/lsq.jl:450-458
+//   qr!(Psi); c = qr \ Y; rel_rms = |Q R c - Y| / |Y|     src/lsq.jl:466-473
+//   c = D_inv * c                                         src/lsq.jl:593
+//   rmse/relrmse per (configtype, okey)                   src/lsqerrors.jl:225-266
+//
+// Algorithm: row-sharded CholeskyQR with re-orthogonalisation.  Each pass forms
+// the Gram matrix of [A | y] on the FP64 tensor cores (gram.cu), the host sums the
+// per-GPU Gram blocks (one all-reduce; nothing to do on one GPU), every rank
+// factors the same n x n matrix G (+ shift) = L L^T and applies A <- A L^-T.
+// Passes repeat until |A^T A - I|_F <= 0.1; the last pass solves the (by then
+// perfectly conditioned) normal equations instead of touching A again:
+//     R = L_p^T ... L_1^T,   c = R^-1 (L_p^-1 z_p),   z_p = A_p^T y.
+// For cond(A) < ~1e7 this is CholeskyQR2 (2 Gram + 1 triangular pass); a failed
+// Cholesky triggers a diagonal shift (shifted CholeskyQR3) and one more pass.
+#include <cmath>
+
+#include "ipf_common.cuh"
+
+int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, int n1, double* G, double* kernel_ms);
+
+struct ipf_solver {
+    int64_t M = 0, Mpad = 0;        // local rows (selected, weight != 0), padded to 16
+    int n = 0, n1 = 0, ncp = 0;     // columns, n+1, padded to 128
+    double* A = nullptr;            // Mpad x ncp  (column n = weighted y, columns > n zero)
+    double* yorig = nullptr;        // [Mpad] weighted y (kept; column n of A is never modified either)
+    double* G = nullptr;            // n1 x n1 Gram of [A | y]
+    double* L = nullptr;            // n x n  lower Cholesky factor of the current pass
+    double* Rtot = nullptr;         // n x n  upper, product of the passes
+    double* Rtmp = nullptr;         // n x n
+    double* vec = nullptr;          // [n] work vector
+    double* dinv = nullptr;         // [n] or null
+    int* flag = nullptr;            // device status word
+    double* red = nullptr;          // reduction scratch
+    int pass = 0;
+    int state = 0;                  // 0: need gram, 1: need factor, 2: done
+    double defect = -1.0, shift = 0.0, gram_ms = 0.0, trsm_ms = 0.0;
+};
+
+namespace {
+
+constexpr int K4_COLS = 8;
+
+// ---- K4: gather rows/cols, apply row weights and column scaling -------------
+__global__ void k4_build_kernel(const double* __restrict__ Psi, int64_t ldp, const double* __restrict__ Y,
+                                const double* __restrict__ W, const int64_t* __restrict__ Irows, int64_t M,
+                                int64_t Mpad, const int64_t* __restrict__ Icols, int n,
+                                const double* __restrict__ dinv, double* __restrict__ A, int* __restrict__ flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= Mpad) return;
+    const int c0 = blockIdx.y * K4_COLS;
+    if (r >= M) {
+        for (int c = c0; c < min(n + 1, c0 + K4_COLS); ++c) A[(int64_t)c * Mpad + r] = 0.0;
+        return;
+    }
+    const int64_t src = Irows ? Irows[r] : r;
+    const double w = W[src];
+    bool bad = false;
+    for (int c = c0; c < min(n + 1, c0 + K4_COLS); ++c) {
+        double v;
+        if (c == n) {
+            v = w * Y[src];
+        } else {
+            const int64_t sc = Icols ? Icols[c] : c;
+            const double p = Psi[sc * ldp + src];
+            bad |= isnan(p);
+            v = w * p;
+            if (dinv) v *= dinv[c];
+        }
+        A[(int64_t)c * Mpad + r] = v;
+    }
+    if (bad) atomicOr(flag, 1);
+}
+
+// ---- K6: small dense kernels on the n x n factor (single CTA) ---------------
+// lower Cholesky, column-major, in place on L (copy of G[0:n,0:n] + shift I)
+__global__ void chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
+    extern __shared__ double s_col[];
+    __shared__ double s_d;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    for (int j = 0; j < n; ++j) {
+        if (tid == 0) s_d = L[(size_t)j * n + j];
+        __syncthreads();
+        const double d = s_d;
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (tid == 0) { flag[1] = 1; flag[2] = j; }
+            return;
+        }
+        const double ljj = sqrt(d);
+        for (int k = j + tid; k < n; k += blockDim.x) {
+            const double v = (k == j) ? ljj : L[(size_t)j * n + k] / ljj;
+            L[(size_t)j * n + k] = v;
+            s_col[k] = v;
+        }
+        __syncthreads();
+        for (int i = j + 1 + warp; i < n; i += nwarp) {
+            const double lij = s_col[i];
+            double* col = L + (size_t)i * n;
+            for (int k = i + lane; k < n; k += 32) col[k] -= s_col[k] * lij;
+        }
+        __syncthreads();
+    }
+    // zero the strict upper triangle
+    for (int64_t e = tid; e < (int64_t)n * n; e += blockDim.x) {
+        const int r = (int)(e % n), c = (int)(e / n);
+        if (r < c) L[e] = 0.0;
+    }
+}
+
+__global__ void copy_shift_kernel(const double* __restrict__ G, int n1, double* __restrict__ L, int n, double shift) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * n) return;
+    const int r = (int)(e % n), c = (int)(e / n);
+    L[e] = G[(size_t)c * n1 + r] + (r == c ? shift : 0.0);
+}
+
+// |G[0:n,0:n] - I|_F^2 and max diagonal; out[0] = frob^2, out[1] = maxdiag (single CTA, deterministic)
+__global__ void defect_kernel(const double* __restrict__ G, int n1, int n, double* __restrict__ out) {
+    __shared__ double s_a[32], s_b[32];
+    double fro = 0.0, md = 0.0;
+    for (int64_t e = threadIdx.x; e < (int64_t)n * n; e += blockDim.x) {
+        const int r = (int)(e % n), c = (int)(e / n);
+        const double g = G[(size_t)c * n1 + r];
+        const double d = g - (r == c ? 1.0 : 0.0);
+        fro += d * d;
+        if (r == c) md = fmax(md, fabs(g));
+    }
+    fro = warp_sum(fro);
+    for (int o = 16; o > 0; o >>= 1) md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = fro; s_b[threadIdx.x >> 5] = md; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double f = 0.0, m = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { f += s_a[w]; m = fmax(m, s_b[w]); }
+        out[0] = f; out[1] = m;
+    }
+}
+
+// Rnew = L^T * Rold (both n x n column-major; L lower, Rold upper) ; first pass Rold = null -> Rnew = L^T
+__global__ void rprod_kernel(const double* __restrict__ L, const double* __restrict__ Rold, double* __restrict__ Rnew, int n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * n) return;
+    const int i = (int)(e % n), j = (int)(e / n);
+    double s = 0.0;
+    if (i <= j) {
+        if (!Rold) s = L[(size_t)i * n + j];
+        else {
+            const double* a = L + (size_t)i * n;      // L[m][i], m >= i
+            const double* b = Rold + (size_t)j * n;   // Rold[m][j], m <= j
+            for (int m = i; m <= j; ++m) s += a[m] * b[m];
+        }
+    }
+    Rnew[e] = s;
+}
+
+// mode 0: solve L w = b (lower, forward);  mode 1: solve R x = b (upper, backward).  x overwrites b.
+__global__ void trsv_kernel(const double* __restrict__ T, int n, double* __restrict__ b, int mode) {
+    extern __shared__ double s_x[];
+    const int tid = threadIdx.x;
+    for (int k = tid; k < n; k += blockDim.x) s_x[k] = b[k];
+    __syncthreads();
+    if (mode == 0) {
+        for (int j = 0; j < n; ++j) {
+            const double xj = s_x[j] / T[(size_t)j * n + j];
+            __syncthreads();
+            if (tid == 0) s_x[j] = xj;
+            for (int k = j + 1 + tid; k < n; k += blockDim.x) s_x[k] -= T[(size_t)j * n + k] * xj;
+            __syncthreads();
+        }
+    } else {
+        for (int j = n - 1; j >= 0; --j) {
+            const double xj = s_x[j] / T[(size_t)j * n + j];
+            __syncthreads();
+            if (tid == 0) s_x[j] = xj;
+            for (int k = tid; k < j; k += blockDim.x) s_x[k] -= T[(size_t)j * n + k] * xj;
+            __syncthreads();
+        }
+    }
+    for (int k = tid; k < n; k += blockDim.x) b[k] = s_x[k];
+}
+
+// ---- triangular pass on the big matrix: A <- A L^-T, one thread per row -----
+constexpr int TB = 32;      // column block
+constexpr int TM = 64;      // panel depth staged in shared memory
+constexpr int TRSM_THREADS = 128;
+
+__global__ void __launch_bounds__(TRSM_THREADS)
+trsm_rows_kernel(double* __restrict__ A, int64_t ld, int64_t M, const double* __restrict__ L, int n) {
+    __shared__ __align__(16) double sL[TM * TB];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = r < M;
+    for (int J0 = 0; J0 < n; J0 += TB) {
+        const int nb = min(TB, n - J0);
+        double acc[TB];
+#pragma unroll
+        for (int t = 0; t < TB; ++t) acc[t] = (live && t < nb) ? A[(int64_t)(J0 + t) * ld + r] : 0.0;
+        // acc -= X[r, 0:J0] * L[J0:J0+nb, 0:J0]^T
+        for (int m0 = 0; m0 < J0; m0 += TM) {
+            const int mm = min(TM, J0 - m0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < mm * TB; e += blockDim.x) {
+                const int m = e / TB, t = e % TB;
+                sL[e] = (t < nb) ? L[(size_t)(m0 + m) * n + J0 + t] : 0.0;
+            }
+            __syncthreads();
+            if (live) {
+                for (int m = 0; m < mm; ++m) {
+                    const double xm = A[(int64_t)(m0 + m) * ld + r];
+                    const double2* row = reinterpret_cast<const double2*>(sL + m * TB);
+#pragma unroll
+                    for (int t = 0; t < TB / 2; ++t) {
+                        const double2 l2 = row[t];
+                        acc[2 * t] -= xm * l2.x;
+                        acc[2 * t + 1] -= xm * l2.y;
+                    }
+                }
+            }
+        }
+        // diagonal block: x_t = (acc_t - sum_{u<t} x_u L[J0+t][J0+u]) / L[J0+t][J0+t]
+        __syncthreads();
+        for (int e = threadIdx.x; e < TB * TB; e += blockDim.x) {
+            const int u = e / TB, t = e % TB;     // sL[u][t] = L[J0+t][J0+u]
+            sL[e] = (t < nb && u < nb) ? L[(size_t)(J0 + u) * n + J0 + t] : (t == u ? 1.0 : 0.0);
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int t = 0; t < TB; ++t) {
+                const double xt = acc[t] / sL[t * TB + t];
+                acc[t] = xt;
+#pragma unroll
+                for (int t2 = t + 1; t2 < TB; ++t2) acc[t2] -= xt * sL[t * TB + t2];
+            }
+#pragma unroll
+            for (int t = 0; t < TB; ++t)
+                if (t < nb) A[(int64_t)(J0 + t) * ld + r] = acc[t];
+        }
+    }
+}
+
+// ---- residual r = y - A c (current A, coefficients in the current basis) -----
+__global__ void residual_kernel(const double* __restrict__ A, int64_t ld, int64_t M, int n,
+                                const double* __restrict__ c, double* __restrict__ partial) {
+    extern __shared__ double s_c[];
+    __shared__ double s_r[32], s_y[32];
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s_c[k] = c[k];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double rr = 0.0, yy = 0.0;
+    if (r < M) {
+        const double y = A[(int64_t)n * ld + r];
+        double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+        int k = 0;
+        for (; k + 3 < n; k += 4) {
+            p0 += A[(int64_t)k * ld + r] * s_c[k];
+            p1 += A[(int64_t)(k + 1) * ld + r] * s_c[k + 1];
+            p2 += A[(int64_t)(k + 2) * ld + r] * s_c[k + 2];
+            p3 += A[(int64_t)(k + 3) * ld + r] * s_c[k + 3];
+        }
+        for (; k < n; ++k) p0 += A[(int64_t)k * ld + r] * s_c[k];
+        const double res = y - ((p0 + p1) + (p2 + p3));
+        rr = res * res;
+        yy = y * y;
+    }
+    rr = warp_sum(rr); yy = warp_sum(yy);
+    if ((threadIdx.x & 31) == 0) { s_r[threadIdx.x >> 5] = rr; s_y[threadIdx.x >> 5] = yy; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += s_r[w]; b += s_y[w]; }
+        partial[2 * blockIdx.x] = a; partial[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void sum_pairs_kernel(const double* __restrict__ partial, int64_t nblk, double* __restrict__ out) {
+    __shared__ double s_a[32], s_b[32];
+    double a = 0.0, b = 0.0;
+    for (int64_t k = threadIdx.x; k < nblk; k += blockDim.x) { a += partial[2 * k]; b += partial[2 * k + 1]; }
+    a = warp_sum(a); b = warp_sum(b);
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { x += s_a[w]; y += s_b[w]; }
+        out[0] = x; out[1] = y;
+    }
+}
+
+__global__ void scale_vec_kernel(double* __restrict__ c, const double* __restrict__ d, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) c[k] *= d[k];
+}
+
+// ---- prediction yhat = Psi c on the raw matrix -------------------------------
+__global__ void predict_kernel(const double* __restrict__ Psi, int64_t ld, int64_t nrows, int ncols,
+                               const double* __restrict__ c, double* __restrict__ yhat) {
+    extern __shared__ double s_c[];
+    for (int k = threadIdx.x; k < ncols; k += blockDim.x) s_c[k] = c[k];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nrows) return;
+    double p0 = 0.0, p1 = 0.0, p2 = 0.0, p3 = 0.0;
+    int k = 0;
+    for (; k + 3 < ncols; k += 4) {
+        p0 += Psi[(int64_t)k * ld + r] * s_c[k];
+        p1 += Psi[(int64_t)(k + 1) * ld + r] * s_c[k + 1];
+        p2 += Psi[(int64_t)(k + 2) * ld + r] * s_c[k + 2];
+        p3 += Psi[(int64_t)(k + 3) * ld + r] * s_c[k + 3];
+    }
+    for (; k < ncols; ++k) p0 += Psi[(int64_t)k * ld + r] * s_c[k];
+    yhat[r] = (p0 + p1) + (p2 + p3);
+}
+
+// per-group sums of (werr (y - yhat - yoff))^2 and (werr y)^2: one CTA per group, fixed order
+__global__ void group_stats_kernel(const double* __restrict__ yhat, const double* __restrict__ Y,
+                                   const double* __restrict__ Yoff, const double* __restrict__ werr,
+                                   const int32_t* __restrict__ group, int64_t nrows,
+                                   double* __restrict__ sse, double* __restrict__ ssy, int64_t* __restrict__ cnt) {
+    __shared__ double s_a[32], s_b[32];
+    __shared__ long long s_c[32];
+    const int g = blockIdx.x;
+    double a = 0.0, b = 0.0;
+    long long c = 0;
+    for (int64_t r = threadIdx.x; r < nrows; r += blockDim.x) {
+        if (group[r] != g) continue;
+        const double w = werr[r];
+        const double ex = w * Y[r];
+        const double fit = w * (yhat[r] + (Yoff ? Yoff[r] : 0.0));
+        const double d = ex - fit;
+        a += d * d; b += ex * ex; c += 1;
+    }
+    a = warp_sum(a); b = warp_sum(b);
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_b[threadIdx.x >> 5] = b; s_c[threadIdx.x >> 5] = c; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double x = 0.0, y = 0.0; long long z = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { x += s_a[w]; y += s_b[w]; z += s_c[w]; }
+        sse[g] = x; ssy[g] = y; cnt[g] = z;
+    }
+}
+
+template <class T>
+int upload(ipf_ctx* ctx, T** d, const T* h, size_t n) {
+    IPF_CUDA(ctx, cudaMalloc((void**)d, sizeof(T) * (n ? n : 1)));
+    if (n) IPF_CUDA(ctx, cudaMemcpyAsync(*d, h, sizeof(T) * n, cudaMemcpyHostToDevice, ctx->stream));
+    return IPF_OK;
+}
+
+void free_solve(ipf_solver* S) {
+    if (!S) return;
+    for (void* p : {(void*)S->A, (void*)S->yorig, (void*)S->G, (void*)S->L, (void*)S->Rtot, (void*)S->Rtmp,
+                    (void*)S->vec, (void*)S->dinv, (void*)S->flag, (void*)S->red})
+        if (p) cudaFree(p);
+    delete S;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
+                        const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,
+                        const double* Dinv, ipf_solver** out) {
+    if (!ctx || !Psi || !out || (!Y && Psi->nrows) || (!W && Psi->nrows))
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad arguments");
+    *out = nullptr;
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nrows = Psi->nrows;
+    // NaN checks in the reference's order (src/lsq.jl:261-262)
+    for (int64_t r = 0; r < nrows; ++r) if (std::isnan(Y[r])) return ipf_set_error(ctx, IPF_ENAN_Y, "NaN detected in observations vector");
+    for (int64_t r = 0; r < nrows; ++r) if (std::isnan(W[r])) return ipf_set_error(ctx, IPF_ENAN_W, "NaN detected in weights vector");
+    const int64_t M = Irows ? nIrows : nrows;
+    const int64_t n64 = Icols ? nIcols : Psi->ncols;
+    if (M < 0 || n64 <= 0 || n64 > 1 << 20) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad system size");
+    if (Irows) for (int64_t r = 0; r < M; ++r) if (Irows[r] < 0 || Irows[r] >= nrows) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: row index out of range");
+    if (Icols) for (int64_t c = 0; c < n64; ++c) if (Icols[c] < 0 || Icols[c] >= Psi->ncols) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: column index out of range");
+    ipf_solver* S = new ipf_solver();
+    S->M = M; S->n = (int)n64; S->n1 = S->n + 1;
+    S->Mpad = ((M + 15) / 16) * 16;
+    if (S->Mpad == 0) S->Mpad = 16;
+    S->ncp = ((S->n1 + 127) / 128) * 128;
+    cudaStream_t st = ctx->stream;
+    const size_t abytes = sizeof(double) * (size_t)S->Mpad * S->ncp;
+    int rc = IPF_OK;
+    double *dY = nullptr, *dW = nullptr;
+    int64_t *dIr = nullptr, *dIc = nullptr;
+    auto fail = [&](int code) {
+        for (void* p : {(void*)dY, (void*)dW, (void*)dIr, (void*)dIc}) if (p) cudaFree(p);
+        free_solve(S);
+        return code;
+    };
+    cudaError_t e = cudaMalloc((void**)&S->A, abytes);
+    if (e != cudaSuccess) return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %zu bytes for the weighted system: %s", abytes, cudaGetErrorString(e)));
+    const size_t nn = (size_t)S->n * S->n;
+    if ((e = cudaMalloc((void**)&S->G, sizeof(double) * (size_t)S->n1 * S->n1)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&S->L, sizeof(double) * nn)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&S->Rtot, sizeof(double) * nn)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&S->Rtmp, sizeof(double) * nn)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&S->vec, sizeof(double) * S->n1)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&S->flag, sizeof(int) * 4)) != cudaSuccess ||
+        (e = cudaMalloc((void**)&S->red, sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8))) != cudaSuccess)
+        return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %s", cudaGetErrorString(e)));
+    if ((rc = upload(ctx, &dY, Y, (size_t)nrows)) != IPF_OK) return fail(rc);
+    if ((rc = upload(ctx, &dW, W, (size_t)nrows)) != IPF_OK) return fail(rc);
+    if (Irows && (rc = upload(ctx, &dIr, Irows, (size_t)M)) != IPF_OK) return fail(rc);
+    if (Icols && (rc = upload(ctx, &dIc, Icols, (size_t)n64)) != IPF_OK) return fail(rc);
+    if (Dinv && (rc = upload(ctx, &S->dinv, Dinv, (size_t)n64)) != IPF_OK) return fail(rc);
+    cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st);
+    // zero columns n1..ncp (the Gram tiles read them)
+    if (S->ncp > S->n1) cudaMemsetAsync(S->A + (size_t)S->n1 * S->Mpad, 0, sizeof(double) * (size_t)(S->ncp - S->n1) * S->Mpad, st);
+    dim3 grid((unsigned)((S->Mpad + 255) / 256), (unsigned)((S->n1 + K4_COLS - 1) / K4_COLS));
+    k4_build_kernel<<<grid, 256, 0, st>>>(Psi->d, Psi->ld, dY, dW, dIr, M, S->Mpad, dIc, S->n, S->dinv, S->A, S->flag);
+    ctx->launches++;
+    int hflag[4] = {0, 0, 0, 0};
+    e = cudaMemcpyAsync(hflag, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ipf_set_error(ctx, IPF_ECUDA, "ipf_solve_begin: %s", cudaGetErrorString(e)));
+    for (void* p : {(void*)dY, (void*)dW, (void*)dIr, (void*)dIc}) if (p) cudaFree(p);
+    dY = dW = nullptr; dIr = dIc = nullptr;
+    if (hflag[0]) return fail(ipf_set_error(ctx, IPF_ENAN_PSI, "discovered NaNs in LSQ system matrix"));
+    *out = S;
+    return IPF_OK;
+}
+
+int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S) {
+    if (!S) return IPF_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    free_solve(S);
+    return IPF_OK;
+}
+
+int32_t ipf_solve_shape(const ipf_solver* S, int64_t* M, int64_t* n) {
+    if (!S) return IPF_EINVAL;
+    if (M) *M = S->M;
+    if (n) *n = S->n;
+    return IPF_OK;
+}
+
+int32_t ipf_solve_system_to_host(ipf_ctx* ctx, const ipf_solver* S, double* Aw, int64_t ld, double* yw) {
+    if (!ctx || !S || (S->M && (!Aw || ld < S->M))) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_system_to_host: bad arguments");
+    if (S->pass != 0) return ipf_set_error(ctx, IPF_ESTATE, "the weighted system has already been factored in place");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (S->M) {
+        IPF_CUDA(ctx, cudaMemcpy2DAsync(Aw, sizeof(double) * ld, S->A, sizeof(double) * S->Mpad, sizeof(double) * S->M, S->n, cudaMemcpyDeviceToHost, ctx->stream));
+        if (yw) IPF_CUDA(ctx, cudaMemcpyAsync(yw, S->A + (size_t)S->n * S->Mpad, sizeof(double) * S->M, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPF_OK;
+}
+
+int32_t ipf_solve_gram(ipf_ctx* ctx, ipf_solver* S, void** G_dev, int64_t* n1) {
+    if (!ctx || !S) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_gram: bad arguments");
+    if (S->state != 0) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_gram: called out of order");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    double ms = 0.0;
+    IPF_CHECK(ipf_gram(ctx, S->A, S->Mpad, S->Mpad, S->ncp, S->n1, S->G, &ms));
+    S->gram_ms += ms;
+    S->state = 1;
+    if (G_dev) *G_dev = S->G;
+    if (n1) *n1 = S->n1;
+    return IPF_OK;
+}
+
+int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
+    if (!ctx || !S || !done) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_factor: bad arguments");
+    if (S->state != 1) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_factor: called out of order");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = S->n, n1 = S->n1;
+    const size_t nn = (size_t)n * n;
+    const unsigned nblk = (unsigned)((nn + 255) / 256);
+    defect_kernel<<<1, 1024, 0, st>>>(S->G, n1, n, S->red);
+    ctx->launches++;
+    double h[2];
+    IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    if (!std::isfinite(h[0]) || !std::isfinite(h[1]))
+        return ipf_set_error(ctx, IPF_ESINGULAR, "ipf_solve_factor: non-finite Gram matrix");
+    const double defect = std::sqrt(h[0]), maxdiag = h[1];
+    const bool final_pass = S->pass >= 1 && defect <= 0.1;
+    if (S->pass >= 1) S->defect = defect;
+    if (!final_pass && S->pass >= 6)
+        return ipf_set_error(ctx, IPF_ESINGULAR, "CholeskyQR did not reach orthogonality in %d passes (defect %.3e)", S->pass, defect);
+    // Cholesky with escalating shift
+    double shift = 0.0;
+    for (int attempt = 0;; ++attempt) {
+        copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, shift);
+        IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
+        chol_lower_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->flag);
+        ctx->launches += 2;
+        int hf[4];
+        IPF_CUDA(ctx, cudaMemcpyAsync(hf, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+        IPF_CUDA(ctx, cudaStreamSynchronize(st));
+        IPF_CUDA(ctx, cudaGetLastError());
+        if (!hf[1]) break;
+        if (attempt >= 12)
+            return ipf_set_error(ctx, IPF_ESINGULAR, "Cholesky of the Gram matrix failed at column %d even with shift %.3e", hf[2], shift);
+        shift = (shift == 0.0) ? 1e-15 * (double)n * maxdiag : shift * 100.0;
+    }
+    S->shift = std::max(S->shift, shift);
+    // Rtot <- L^T Rtot
+    rprod_kernel<<<nblk, 256, 0, st>>>(S->L, S->pass == 0 ? nullptr : S->Rtot, S->Rtmp, n);
+    ctx->launches++;
+    std::swap(S->Rtot, S->Rtmp);
+    if (final_pass) {
+        // c = Rtot^-1 (L^-1 z),  z = G[0:n, n]
+        IPF_CUDA(ctx, cudaMemcpyAsync(S->vec, S->G + (size_t)n * n1, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+        trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->vec, 0);
+        // residual in the orthonormal basis needs c'' = L^-T (L^-1 z): compute it into G's scratch later;
+        // here keep w = L^-1 z in vec and the solution in vec[n..): not needed, finish computes both.
+        ctx->launches++;
+        S->state = 2;
+        *done = 1;
+    } else {
+        cudaEvent_t e0, e1;
+        IPF_CUDA(ctx, cudaEventCreate(&e0));
+        IPF_CUDA(ctx, cudaEventCreate(&e1));
+        IPF_CUDA(ctx, cudaEventRecord(e0, st));
+        trsm_rows_kernel<<<(unsigned)((S->Mpad + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, 0, st>>>(S->A, S->Mpad, S->M, S->L, n);
+        IPF_CUDA(ctx, cudaEventRecord(e1, st));
+        ctx->launches++;
+        IPF_CUDA(ctx, cudaStreamSynchronize(st));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        S->trsm_ms += ms;
+        S->pass++;
+        S->state = 0;
+        *done = 0;
+    }
+    IPF_CUDA(ctx, cudaGetLastError());
+    return IPF_OK;
+}
+
+// c[n] (already multiplied by Dinv), R_out n x n column-major (may be NULL),
+// local residual sums ssr = |y - A c|^2, ssy = |y|^2 of the weighted system.
+int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, double* ssr, double* ssy) {
+    if (!ctx || !S || !c) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_finish: bad arguments");
+    if (S->state != 2) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_finish: factorisation not complete");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = S->n;
+    // vec holds w = L^-1 z.  Coefficients in the current (orthonormalised) basis: cc = L^-T w.
+    // L^T is the upper factor: reuse trsv mode 1 on L^T stored as Rtmp = transpose(L).
+    // rprod with Rold = null writes L^T into Rtmp.
+    const size_t nn = (size_t)n * n;
+    const unsigned nblk = (unsigned)((nn + 255) / 256);
+    rprod_kernel<<<nblk, 256, 0, st>>>(S->L, nullptr, S->Rtmp, n);
+    double* cc = S->G;     // Gram storage is free now: [0..n) = cc, [n1..n1+n) = final c
+    IPF_CUDA(ctx, cudaMemcpyAsync(cc, S->vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtmp, n, cc, 1);
+    const int64_t nb = (S->Mpad + 255) / 256;
+    residual_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, n, cc, S->red + 8);
+    sum_pairs_kernel<<<1, 1024, 0, st>>>(S->red + 8, nb, S->red);
+    // solution in the original (scaled) basis: c = Rtot^-1 w
+    double* cf = S->G + S->n1;
+    IPF_CUDA(ctx, cudaMemcpyAsync(cf, S->vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtot, n, cf, 1);
+    if (S->dinv) scale_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(cf, S->dinv, n);
+    ctx->launches += 6;
+    double h[2];
+    IPF_CUDA(ctx, cudaMemcpyAsync(c, cf, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
+    if (R_out) IPF_CUDA(ctx, cudaMemcpyAsync(R_out, S->Rtot, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    IPF_CUDA(ctx, cudaGetLastError());
+    if (ssr) *ssr = h[0];
+    if (ssy) *ssy = h[1];
+    return IPF_OK;
+}
+
+int32_t ipf_solve_info(const ipf_solver* S, int32_t* npasses, double* defect, double* shift, double* gram_ms, double* trsm_ms) {
+    if (!S) return IPF_EINVAL;
+    if (npasses) *npasses = S->pass + 1;
+    if (defect) *defect = S->defect;
+    if (shift) *shift = S->shift;
+    if (gram_ms) *gram_ms = S->gram_ms;
+    if (trsm_ms) *trsm_ms = S->trsm_ms;
+    return IPF_OK;
+}
+
+// single-GPU one-shot
+int32_t ipf_solve(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W, const int64_t* Irows,
+                  int64_t nIrows, const int64_t* Icols, int64_t nIcols, const double* Dinv, double* c,
+                  double* R_out, double* rel_rms) {
+    ipf_solver* S = nullptr;
+    IPF_CHECK(ipf_solve_begin(ctx, Psi, Y, W, Irows, nIrows, Icols, nIcols, Dinv, &S));
+    int rc = IPF_OK;
+    int32_t done = 0;
+    while (!done && rc == IPF_OK) {
+        rc = ipf_solve_gram(ctx, S, nullptr, nullptr);
+        if (rc == IPF_OK) rc = ipf_solve_factor(ctx, S, &done);
+    }
+    double ssr = 0.0, ssy = 0.0;
+    if (rc == IPF_OK) rc = ipf_solve_finish(ctx, S, c, R_out, &ssr, &ssy);
+    if (rc == IPF_OK && rel_rms) *rel_rms = std::sqrt(ssr) / std::sqrt(ssy);
+    ipf_solve_destroy(ctx, S);
+    return rc;
+}
+
+int32_t ipf_predict(ipf_ctx* ctx, const ipf_matrix* Psi, const double* c, double* yhat) {
+    if (!ctx || !Psi || !c || (!yhat && Psi->nrows)) return ipf_set_error(ctx, IPF_EINVAL, "ipf_predict: bad arguments");
+    if (Psi->nrows == 0) return IPF_OK;
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf<double> dc, dy;
+    IPF_CUDA(ctx, dc.alloc(Psi->ncols));
+    IPF_CUDA(ctx, dy.alloc(Psi->nrows));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dc.p, c, sizeof(double) * Psi->ncols, cudaMemcpyHostToDevice, st));
+    predict_kernel<<<(unsigned)((Psi->nrows + 255) / 256), 256, sizeof(double) * Psi->ncols, st>>>(Psi->d, Psi->ld, Psi->nrows, (int)Psi->ncols, dc.p, dy.p);
+    ctx->launches++;
+    IPF_CUDA(ctx, cudaMemcpyAsync(yhat, dy.p, sizeof(double) * Psi->nrows, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    IPF_CUDA(ctx, cudaGetLastError());
+    return IPF_OK;
+}
+
+int32_t ipf_residual_stats(ipf_ctx* ctx, const ipf_matrix* Psi, const double* c, const double* Yraw,
+                           const double* Yoff, const double* werr, const int32_t* group, int32_t ngroups,
+                           double* sse, double* ssy, int64_t* cnt) {
+    if (!ctx || !Psi || !c || !Yraw || !werr || !group || ngroups <= 0 || !sse || !ssy || !cnt)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_residual_stats: bad arguments");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nrows = Psi->nrows;
+    DevBuf<double> dc, dy, dY, dO, dw, dsse, dssy;
+    DevBuf<int32_t> dg;
+    DevBuf<int64_t> dcnt;
+    IPF_CUDA(ctx, dc.alloc(Psi->ncols)); IPF_CUDA(ctx, dy.alloc(nrows)); IPF_CUDA(ctx, dY.alloc(nrows));
+    IPF_CUDA(ctx, dO.alloc(nrows)); IPF_CUDA(ctx, dw.alloc(nrows)); IPF_CUDA(ctx, dg.alloc(nrows));
+    IPF_CUDA(ctx, dsse.alloc(ngroups)); IPF_CUDA(ctx, dssy.alloc(ngroups)); IPF_CUDA(ctx, dcnt.alloc(ngroups));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dc.p, c, sizeof(double) * Psi->ncols, cudaMemcpyHostToDevice, st));
+    if (nrows) {
+        IPF_CUDA(ctx, cudaMemcpyAsync(dY.p, Yraw, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
+        if (Yoff) IPF_CUDA(ctx, cudaMemcpyAsync(dO.p, Yoff, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
+        IPF_CUDA(ctx, cudaMemcpyAsync(dw.p, werr, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
+        IPF_CUDA(ctx, cudaMemcpyAsync(dg.p, group, sizeof(int32_t) * nrows, cudaMemcpyHostToDevice, st));
+        predict_kernel<<<(unsigned)((nrows + 255) / 256), 256, sizeof(double) * Psi->ncols, st>>>(Psi->d, Psi->ld, nrows, (int)Psi->ncols, dc.p, dy.p);
+        ctx->launches++;
+    }
+    group_stats_kernel<<<ngroups, 1024, 0, st>>>(dy.p, dY.p, Yoff ? dO.p : nullptr, dw.p, dg.p, nrows, dsse.p, dssy.p, dcnt.p);
+    ctx->launches++;
+    IPF_CUDA(ctx, cudaMemcpyAsync(sse, dsse.p, sizeof(double) * ngroups, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(ssy, dssy.p, sizeof(double) * ngroups, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(cnt, dcnt.p, sizeof(int64_t) * ngroups, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    IPF_CUDA(ctx, cudaGetLastError());
+    return IPF_OK;
+}
+
+}  // extern "C"

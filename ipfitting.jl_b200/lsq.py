@@ -1,0 +1,285 @@
+"""`lsqfit` and friends: observations + weights -> weighted system -> solve -> IP, fitinfo.
+
+Mirrors `/root/reference/src/lsq.jl`:
+  collect_observations   :74-109     _get_weights :118-161     _fix_weights! :698-707
+  get_lsq_system         :245-311    lsqfit       :404-614     asm_fitinfo   :617-678
+The dense work (row weighting + column scaling `:306-307,450-458`, the QR solve
+`:466-473`, `c = D_inv*c` `:593`) runs on the GPU through the C-ABI
+(`ipf_solve_*`); everything here is the host-side dictionary logic of the reference.
+
+Only the `:qr` solver family is provided by the CUDA path (`:rrqr`,
+`:svd` are "next"; `:lsqr/:brr/:ard/:xgboost` wrap third-party python/Julia solvers
+and are out of scope).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+
+from . import _capi, parallel
+from .datatypes import weighthook
+from .lsq_db import LsqDB, matrows
+from .obsiter import observations
+from .potentials import NBodyIP, OneBody, SumIP, vref_observation
+from .prototypes import ENERGY, FORCES, VIRIAL
+
+_QR = ("qr", ":qr")
+
+
+def _fix_weights(weights: Optional[dict]) -> dict:
+    """`_fix_weights!` (`src/lsq.jl:698-707`)."""
+    weights = {} if weights is None else weights
+    if "ignore" not in weights:
+        weights = dict(weights)
+        weights["ignore"] = []
+    if "default" not in weights:
+        weights["default"] = {"E": 1.0, "F": 1.0, "V": 1.0}
+    return weights
+
+
+def _get_weights(weights: dict, wh: float, dat, obskey: str, o: np.ndarray) -> np.ndarray:
+    """`_get_weights` (`src/lsq.jl:118-161`)."""
+    w = 0.0
+    if "W" in dat.info:
+        # overrides everything, weighthook included (`:125-131`)
+        if obskey in dat.info["W"]:
+            w = dat.info["W"][obskey]
+    else:
+        ct = dat.configtype
+        cfgkey = ct if ct in weights else "default"
+        if obskey in weights[cfgkey]:
+            w = weights[cfgkey][obskey] * wh
+    wa = np.atleast_1d(np.asarray(w, dtype=np.float64))
+    if obskey in (ENERGY, VIRIAL):
+        if wa.size == 1:
+            return np.full(len(o), wa[0])
+        if wa.size == len(o):
+            return wa.copy()
+    elif obskey == FORCES:
+        if wa.size != 1:
+            raise ValueError("_get_weights: a vector weight is not allowed for \"F\"")
+        return np.full(len(o), wa[0])
+    raise ValueError("_get_weights: length(w) is neither 1 nor length(o)?!?!?")
+
+
+def collect_observations(db: LsqDB, weights: dict, Vref):
+    """`collect_observations(db, weights, Vref) -> Y, W, Icfg` (`src/lsq.jl:74-109`).
+    Icfg is 0-based here, -1 for rows that were skipped."""
+    nrows = db.nrows
+    Y = np.zeros(nrows)
+    W = np.zeros(nrows)
+    Icfg = np.full(nrows, -1, dtype=np.int64)
+    ignore = weights["ignore"]
+    for okey, dat, icfg in observations(db):
+        if dat.configtype in ignore or okey in ignore:
+            continue
+        irows = matrows(dat, okey)
+        obs = dat.D[okey]
+        if "Vref" in dat.info:
+            obs = obs - np.asarray(dat.info["Vref"][okey], dtype=np.float64)
+        elif Vref is not None:
+            obs = obs - vref_observation(Vref, okey, dat)
+        Y[irows] = obs
+        Icfg[irows] = icfg
+        W[irows] = _get_weights(weights, weighthook(okey, dat), dat, okey, obs)
+    return Y, W, Icfg
+
+
+def _select(db: LsqDB, Y, W, Icfg, Ibasis, Itrain):
+    """Row/column selection of `get_lsq_system` (`src/lsq.jl:270-283`)."""
+    if np.isnan(Y).any():
+        raise _capi.IPFError(-4, "NaN detected in observations vector")
+    if np.isnan(W).any():
+        raise _capi.IPFError(-5, "NaN detected in weights vector")
+    keep = W != 0
+    if Itrain is not None:
+        keep &= np.isin(Icfg, np.asarray(list(Itrain), dtype=np.int64))
+    Irows = np.nonzero(keep)[0].astype(np.int64)
+    Icols = None if Ibasis is None else np.asarray(list(Ibasis), dtype=np.int64)
+    return Irows, Icols
+
+
+class _Solver:
+    """RAII wrapper of the staged `ipf_solve_*` calls."""
+
+    def __init__(self, ctx: _capi.Context, Psi_dev: _capi.DeviceMatrix, Y, W, Irows, Icols, Dinv):
+        self.ctx = ctx
+        Y = np.ascontiguousarray(Y, dtype=np.float64)
+        W = np.ascontiguousarray(W, dtype=np.float64)
+        h = C.c_void_p()
+        ir = None if Irows is None else np.ascontiguousarray(Irows, dtype=np.int64)
+        ic = None if Icols is None else np.ascontiguousarray(Icols, dtype=np.int64)
+        dv = None if Dinv is None else np.ascontiguousarray(Dinv, dtype=np.float64)
+        ctx.check(ctx.lib.ipf_solve_begin(
+            ctx.h, Psi_dev.h, _capi.ptr(Y, C.c_double), _capi.ptr(W, C.c_double),
+            None if ir is None else _capi.ptr(ir, C.c_int64), 0 if ir is None else len(ir),
+            None if ic is None else _capi.ptr(ic, C.c_int64), 0 if ic is None else len(ic),
+            None if dv is None else _capi.ptr(dv, C.c_double), C.byref(h)))
+        self.h = h
+        M, n = C.c_int64(), C.c_int64()
+        ctx.lib.ipf_solve_shape(h, C.byref(M), C.byref(n))
+        self.M, self.n = M.value, n.value
+
+    def system_to_host(self):
+        A = np.empty((self.M, self.n), order="F")
+        y = np.empty(self.M)
+        self.ctx.check(self.ctx.lib.ipf_solve_system_to_host(
+            self.ctx.h, self.h, _capi.ptr(A, C.c_double), max(1, self.M), _capi.ptr(y, C.c_double)))
+        return A, y
+
+    def gram(self):
+        g, n1 = C.c_void_p(), C.c_int64()
+        self.ctx.check(self.ctx.lib.ipf_solve_gram(self.ctx.h, self.h, C.byref(g), C.byref(n1)))
+        return g.value, n1.value
+
+    def factor(self) -> bool:
+        done = C.c_int32()
+        self.ctx.check(self.ctx.lib.ipf_solve_factor(self.ctx.h, self.h, C.byref(done)))
+        return bool(done.value)
+
+    def finish(self, want_R=True):
+        c = np.empty(self.n)
+        R = np.empty((self.n, self.n), order="F") if want_R else None
+        ssr, ssy = C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.ipf_solve_finish(
+            self.ctx.h, self.h, _capi.ptr(c, C.c_double), None if R is None else _capi.ptr(R, C.c_double),
+            C.byref(ssr), C.byref(ssy)))
+        return c, R, ssr.value, ssy.value
+
+    def info(self) -> dict:
+        npass, defect, shift, gms, tms = C.c_int32(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
+        self.ctx.lib.ipf_solve_info(self.h, C.byref(npass), C.byref(defect), C.byref(shift), C.byref(gms), C.byref(tms))
+        return {"passes": npass.value, "orth_defect": defect.value, "shift": shift.value,
+                "gram_ms": gms.value, "trsm_ms": tms.value}
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.ipf_solve_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None):
+    """Weighted LSQ solve of the device-resident system.  `comm`: a
+    `parallel.Communicator` (rows are sharded over its ranks) or None."""
+    S = _Solver(ctx, Psi_dev, Y, W, Irows, Icols, Dinv)
+    try:
+        while True:
+            gptr, n1 = S.gram()
+            if comm is not None and comm.world_size > 1:
+                comm.allreduce_device_f64(gptr, n1 * n1, ctx.device)
+            if S.factor():
+                break
+        c, R, ssr, ssy = S.finish(want_R)
+        if comm is not None and comm.world_size > 1:
+            ssr, ssy = comm.allreduce_scalars([ssr, ssy])
+        info = S.info()
+    finally:
+        S.close()
+    info["rel_rms"] = math.sqrt(ssr) / math.sqrt(ssy) if ssy > 0 else float("nan")
+    return c, R, info
+
+
+def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=None, Vref="default",
+                   weights=None, regularisers=()):
+    """`get_lsq_system(db; ...) -> Psi_W, Y_W` on the host (`src/lsq.jl:245-311`); default
+    `Vref = OneBody(E0)` as there."""
+    if regularisers:
+        raise NotImplementedError("regularisers are not part of the CUDA path yet (SURVEY.md §8f N4)")
+    if isinstance(Vref, str) and Vref == "default":
+        Vref = OneBody(E0 if E0 is not None else 0.0)
+    weights = _fix_weights(weights)
+    Y, W, Icfg = collect_observations(db, weights, Vref)
+    Irows, Icols = _select(db, Y, W, Icfg, Ibasis, Itrain)
+    S = _Solver(db._context(), db.Psi_dev, Y, W, Irows, Icols, None)
+    try:
+        return S.system_to_host()
+    finally:
+        S.close()
+
+
+def _diag_of(P, n) -> Optional[np.ndarray]:
+    if P is None:
+        return None
+    P = np.asarray(P, dtype=np.float64)
+    if P.ndim == 2:
+        if not np.allclose(P, np.diag(np.diag(P))):
+            raise NotImplementedError("only diagonal column preconditioners P are supported")
+        P = np.diag(P)
+    if P.shape != (n,):
+        raise ValueError("solver[\"P\"] has the wrong size")
+    # pinv of a diagonal matrix (`src/lsq.jl:457`)
+    return np.where(P != 0, 1.0 / np.where(P != 0, P, 1.0), 0.0)
+
+
+def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=None, Itrain=None, E0=0.0,
+           Vref=None, weights=None, sigmas=None, regularisers=(), deldb=False, error_table=False,
+           saveqr: Optional[dict] = None, comm: "parallel.Communicator" = None):
+    """`lsqfit(db; kwargs...) -> IP, fitinfo` (`src/lsq.jl:404-614`)."""
+    solver = {"solver": "qr"} if solver is None else solver
+    if weights is not None and sigmas is not None:
+        raise ValueError("cannot specify both weights and sigmas")
+    if sigmas is not None:
+        # inverted in place in the caller's dict, as the reference does (`:424-429`)
+        weights = sigmas
+        for _cfg, cw in weights.items():
+            if isinstance(cw, dict):
+                for k in cw:
+                    cw[k] = 1.0 / cw[k]
+    if regularisers:
+        raise NotImplementedError("regularisers are not part of the CUDA path yet (SURVEY.md §8f N4)")
+    weights = _fix_weights(weights)
+    name = str(solver.get("solver", "qr")).lstrip(":")
+    if name != "qr":
+        raise ValueError("unknown `solver` in `lsqfit`" if name not in ("svd", "rrqr", "lsqr", "brr", "ard", "xgboost")
+                         else f"solver :{name} is not provided by the CUDA path (only :qr)")
+    ctx = db._context()
+    Y, W, Icfg = collect_observations(db, weights, Vref)
+    Irows, Icols = _select(db, Y, W, Icfg, Ibasis, Itrain)
+    n = len(db.basis) if Icols is None else len(Icols)
+    Dinv = _diag_of(solver.get("P"), n)
+    if "P" in solver:
+        del solver["P"]          # `src/lsq.jl:460-462`
+    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm)
+    kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
+    if isinstance(saveqr, dict):
+        saveqr["R"] = R
+        saveqr["Y"] = (W * Y)[Irows]
+    if deldb:
+        db.delete()
+    # combine(db.basis, c) uses the FULL basis (`src/lsq.jl:603`): scatter a subset fit
+    cfull = np.zeros(len(db.basis))
+    if Icols is None:
+        cfull[:] = c
+    else:
+        cfull[Icols] = c
+    IP = NBodyIP(db.basis, cfull)
+    if Vref is not None:
+        IP = SumIP(Vref, IP)
+    infodict = asm_fitinfo(db, IP, c, Icols, weights, Vref, E0, regularisers, verbose, error_table,
+                           cfull=cfull, comm=comm)
+    infodict["cond_R"] = kappa
+    infodict["rel_rms"] = info["rel_rms"]
+    infodict["solve_info"] = info
+    infodict.update(solver)
+    return IP, infodict
+
+
+def asm_fitinfo(db, IP, c, Icols, weights, Vref, E0, regularisers, verbose, error_table, *, cfull, comm=None):
+    """`asm_fitinfo` (`src/lsq.jl:617-678`)."""
+    Jbasis = list(range(len(db.basis))) if Icols is None else [int(k) for k in Icols]
+    infodict = {"E0": E0, "Ibasis": Jbasis, "c": np.array(c), "dbpath": db.dbpath, "weights": weights,
+                "regularisers": list(regularisers), "errors": {}, "IPFitting_version": "na"}
+    if error_table:
+        from .lsqerrors import db_errors
+        rm, rel = db_errors(db, cfull, Vref, comm=comm)
+        infodict["errors"] = {"rmse": rm, "relrmse": rel}
+    return infodict

@@ -1,0 +1,152 @@
+"""K4-K7 parity: get_lsq_system / lsqfit / error table through the C-ABI against the
+numpy+LAPACK restatement of the reference (oracle/lsq_oracle.py) on the oracle's own Psi."""
+import numpy as np
+import pytest
+
+import ipfitting_jl_b200 as ipf
+from ipfitting_jl_b200 import _capi, synth
+from ipfitting_jl_b200.lsq import solve_device
+from ipfitting_jl_b200.lsq_db import LsqDB
+import ipf_oracle as O
+import lsq_oracle as LO
+from util import rows_for, si_desc
+
+pytestmark = pytest.mark.gpu
+
+C_RTOL = 1e-8        # north_star: coefficients and per-configtype RMSEs agree to 1e-8
+
+
+@pytest.fixture(scope="module")
+def fitcase(ctx):
+    sw = synth.StillingerWeber()
+    cfgs = synth.rattled_configs("Si", 2, 12, seed=21, calc=sw, configtype="bulk")
+    more = synth.rattled_configs("Si", 1, 10, seed=22, calc=sw, configtype="small")
+    configs = cfgs + more
+    # a weakly collinear basis so that coefficient parity at 1e-8 is meaningful (cond ~ 1e4)
+    B = ipf.nbpolys(2, si_desc(2.0), 4) + ipf.nbpolys(3, si_desc(1.7), 2)
+    db = LsqDB("", B, configs, ctx=ctx)
+    r = rows_for(configs)
+    ref = O.assemble(db.basis, configs, r["E"], r["F"], r["V"], db.nrows)
+    return db, ref
+
+
+def test_get_lsq_system_matches_hand_assembly(fitcase):
+    """`test/test_lsq.jl:31-59`: the system equals w * vec_obs(evalb(B, at)) assembled by hand."""
+    db, ref = fitcase
+    w = {"default": {"E": 1.345, "F": 2.987}}
+    A, Y = ipf.get_lsq_system(db, Vref=ipf.OneBody(0.0), weights=w)
+    rowsel = []
+    Aman, Yman = [], []
+    for d in db.configs:
+        nat = len(d.at)
+        for okey, wt in (("E", 1.345 / np.sqrt(nat)), ("F", 2.987)):
+            f, n = d.rows[okey]
+            rowsel.append((f, okey))
+            Aman.append(wt * ref[f:f + n, :]); Yman.append(wt * d.D[okey])
+    order = np.argsort([f for f, _ in rowsel], kind="stable")
+    Aman = np.vstack([Aman[k] for k in order]); Yman = np.concatenate([Yman[k] for k in order])
+    assert A.shape == Aman.shape                 # V rows dropped: no "V" weight => w = 0 (Q1)
+    assert np.allclose(Y, Yman, rtol=1e-13, atol=0)
+    scale = np.abs(Aman).max(axis=0)
+    assert (np.abs(A - Aman).max(axis=0) <= 1e-10 * scale).all()
+    A2, Y2 = LO.get_lsq_system(ref, db.configs, weights=w, E0=0.0)
+    assert np.allclose(Y, Y2, rtol=1e-13, atol=0) and A.shape == A2.shape
+
+
+@pytest.mark.parametrize("weights", [None,
+                                     {"default": {"E": 100.0, "F": 1.0, "V": 0.5}},
+                                     {"default": {"E": 30.0, "F": 1.0, "V": 0.3}, "small": {"E": 10.0, "F": 2.0}},
+                                     {"default": {"E": 10.0, "F": 1.0, "V": 1.0}, "ignore": ["small"]}])
+def test_lsqfit_matches_reference_qr(fitcase, weights):
+    db, ref = fitcase
+    E0 = -4.0
+    IP, info = ipf.lsqfit(db, weights=None if weights is None else dict(weights), E0=E0, Vref=ipf.OneBody(E0),
+                          error_table=True)
+    c_ref, kappa, rel_rms, R = LO.lsqfit_qr(ref, db.configs, weights, E0=E0)
+    c = info["c"]
+    assert kappa < 1e7
+    assert np.linalg.norm(c - c_ref) <= C_RTOL * np.linalg.norm(c_ref)
+    assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
+    assert abs(info["cond_R"] - kappa) <= 1e-6 * kappa
+    err_ref, rel_ref = LO.rmse_table(ref, db.configs, c_ref, E0=E0)
+    for ct in err_ref:
+        for okey in err_ref[ct]:
+            assert abs(info["errors"]["rmse"][ct][okey] - err_ref[ct][okey]) <= C_RTOL * err_ref[ct][okey]
+            assert abs(info["errors"]["relrmse"][ct][okey] - rel_ref[ct][okey]) <= C_RTOL * rel_ref[ct][okey]
+
+
+def test_subset_fit_and_column_scaling(fitcase):
+    db, ref = fitcase
+    Ib = ipf.filter_basis(db, lambda b: ipf.bodyorder(b) < 3)
+    Itrain = list(range(0, len(db.configs), 2))
+    P = np.linspace(0.5, 3.0, len(Ib))
+    IP, info = ipf.lsqfit(db, Ibasis=Ib, Itrain=Itrain, solver={"solver": "qr", "P": P.copy()},
+                          weights={"default": {"E": 50.0, "F": 1.0, "V": 1.0}})
+    c_ref, kappa, rel_rms, _ = LO.lsqfit_qr(ref, db.configs, {"default": {"E": 50.0, "F": 1.0, "V": 1.0}},
+                                            E0=None, Ibasis=Ib, Itrain=Itrain, P=P)
+    assert np.linalg.norm(info["c"] - c_ref) <= C_RTOL * np.linalg.norm(c_ref)
+    assert info["Ibasis"] == [int(k) for k in Ib]
+    assert len(IP.c) == len(db.basis) and np.all(IP.c[len(Ib):] == 0)     # Q8: scattered into the full basis
+    assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
+
+
+def test_ill_conditioned_system_needs_reorthogonalisation(ctx):
+    """cond ~ 1e11: plain normal equations are useless; the shifted/iterated CholeskyQR
+    must reproduce the Householder solution to the accuracy the conditioning allows."""
+    rng = np.random.default_rng(5)
+    M, n = 6000, 40
+    U, _ = np.linalg.qr(rng.standard_normal((M, n)))
+    V, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    s = np.logspace(0, -11, n)
+    A = np.asfortranarray((U * s) @ V.T)
+    x = rng.standard_normal(n)
+    y = A @ x + 1e-6 * rng.standard_normal(M)
+    Pm = _capi.DeviceMatrix(ctx, M, n)
+    Pm.from_host(A)
+    c, R, info = solve_device(ctx, Pm, y, np.ones(M))
+    import scipy.linalg as sla
+    Q, Rr = sla.qr(A, mode="economic")
+    c_ref = sla.solve_triangular(Rr, Q.T @ y)
+    kappa = np.linalg.cond(Rr)
+    assert info["passes"] >= 3
+    # both are backward stable: compare residuals and the well-determined part of c
+    r, r_ref = np.linalg.norm(A @ c - y), np.linalg.norm(A @ c_ref - y)
+    assert abs(r - r_ref) <= 1e-8 * r_ref
+    assert np.linalg.norm(A @ (c - c_ref)) <= 1e-9 * np.linalg.norm(y)
+    assert abs(np.linalg.cond(R) - kappa) <= 1e-3 * kappa
+    Pm.close()
+
+
+def test_nan_checks(fitcase):
+    db, _ = fitcase
+    bad = db.configs[0].D["E"].copy()
+    db.configs[0].D["E"][0] = np.nan
+    try:
+        with pytest.raises(_capi.IPFError, match="NaN detected in observations vector"):
+            ipf.lsqfit(db)
+    finally:
+        db.configs[0].D["E"][:] = bad
+    ctx = db._context()
+    M = _capi.DeviceMatrix(ctx, 8, 2)
+    A = np.ones((8, 2), order="F"); A[3, 1] = np.nan
+    M.from_host(A)
+    with pytest.raises(_capi.IPFError, match="discovered NaNs in LSQ system matrix"):
+        solve_device(ctx, M, np.ones(8), np.ones(8))
+    with pytest.raises(_capi.IPFError, match="NaN detected in weights vector"):
+        w = np.ones(8); w[2] = np.nan
+        M.from_host(np.ones((8, 2), order="F"))
+        solve_device(ctx, M, np.ones(8), w)
+
+
+def test_add_fits_equals_error_table(fitcase):
+    """`test/test_errors.jl:54-71`: add_fits! + rmse(configs) == fitinfo["errors"]."""
+    db, _ = fitcase
+    E0 = -4.0
+    IP, info = ipf.lsqfit(db, E0=E0, Vref=ipf.OneBody(E0), error_table=True,
+                          weights={"default": {"E": 30.0, "F": 1.0, "V": 0.3}})
+    ipf.add_fits(IP, db.configs, fitkey="IP", db=db)
+    rm, rel = ipf.rmse(db.configs, fitkey="IP")
+    for ct in rm:
+        for okey in rm[ct]:
+            assert abs(rm[ct][okey] - info["errors"]["rmse"][ct][okey]) <= 1e-9 * rm[ct][okey]
+            assert abs(rel[ct][okey] - info["errors"]["relrmse"][ct][okey]) <= 1e-9 * rel[ct][okey]
