@@ -55,6 +55,7 @@ typedef struct ipf_ctx ipf_ctx;
 typedef struct ipf_basis ipf_basis;
 typedef struct ipf_matrix ipf_matrix;
 typedef struct ipf_solver ipf_solver;
+typedef struct ipf_configs ipf_configs;
 
 /* One run of basis functions sharing body-order and descriptor.
  * Monomial m belongs to local basis function mono_b[m] (non-decreasing) and has
@@ -81,6 +82,12 @@ const char* ipf_last_error(ipf_ctx* ctx);
 int64_t ipf_launch_count(ipf_ctx* ctx);
 /* the CUDA stream all work of this ctx is issued on (a cudaStream_t) */
 void* ipf_stream(ipf_ctx* ctx);
+/* per-kernel device timing (CUDA events on the ctx stream), used by bench.py for the
+ * roofline numbers.  Names: "neighbour_list", "pair_record", "site_deriv_2b|3b|4b|5b",
+ * "k4_build", "gram", "cholesky", "trsm", "residual". */
+int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on);
+int32_t ipf_profile_reset(ipf_ctx* ctx);
+int32_t ipf_profile_get(ipf_ctx* ctx, const char* name, double* ms, int64_t* count);
 
 /* ---- basis ------------------------------------------------------------ */
 int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* blocks,
@@ -125,6 +132,16 @@ int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg,
                      const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
                      const int64_t* rowF, const int64_t* rowV, ipf_matrix* Psi);
 
+/* The same in two steps, with the configurations kept resident on the device
+ * (repeated assembly, benchmarking with inputs already in HBM). */
+int32_t ipf_configs_create(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
+                           const double* cell, const uint8_t* pbc, const int32_t* Z,
+                           const int64_t* rowE, const int64_t* rowF, const int64_t* rowV,
+                           ipf_configs** cfgs);
+int32_t ipf_configs_destroy(ipf_ctx* ctx, ipf_configs* cfgs);
+int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_configs* cfgs,
+                             ipf_matrix* Psi);
+
 /* ---- solve (K4-K7) -----------------------------------------------------
  * Weighted, column-scaled least squares on the device-resident matrix:
  *     minimise | diag(W[I]) (Psi[I, J] diag(Dinv) c' - Y[I]) |,   c = Dinv .* c'
@@ -146,6 +163,10 @@ int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg,
 int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
                         const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,
                         const double* Dinv, ipf_solver** S);
+/* as ipf_solve_begin, every vector argument being a DEVICE pointer */
+int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* dY, const double* dW,
+                            const int64_t* dIrows, int64_t nIrows, const int64_t* dIcols,
+                            int64_t nIcols, const double* dDinv, ipf_solver** S);
 int32_t ipf_solve_shape(const ipf_solver* S, int64_t* M, int64_t* n);
 /* the weighted system itself (get_lsq_system, src/lsq.jl:245-311): Aw [M x n] column-major, yw [M] */
 int32_t ipf_solve_system_to_host(ipf_ctx* ctx, const ipf_solver* S, double* Aw, int64_t ld, double* yw);

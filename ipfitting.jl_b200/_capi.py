@@ -49,6 +49,9 @@ SIGNATURES = {
     "ipf_last_error": (C.c_char_p, [_vp]),
     "ipf_launch_count": (C.c_int64, [_vp]),
     "ipf_stream": (_vp, [_vp]),
+    "ipf_profile_enable": (C.c_int32, [_vp, C.c_int32]),
+    "ipf_profile_reset": (C.c_int32, [_vp]),
+    "ipf_profile_get": (C.c_int32, [_vp, C.c_char_p, _dp, _lp]),
     "ipf_basis_create": (C.c_int32, [_vp, C.c_int32, C.POINTER(BlockSpec), C.POINTER(_vp)]),
     "ipf_basis_destroy": (C.c_int32, [_vp, _vp]),
     "ipf_basis_length": (C.c_int64, [_vp]),
@@ -62,6 +65,10 @@ SIGNATURES = {
     "ipf_matrix_device_ptr": (_vp, [_vp]),
     "ipf_neighbours": (C.c_int32, [_vp, C.c_int32, _dp, _dp, _bp, C.c_double, C.c_int64, _lp, _ip, _ip, _ip, _dp]),
     "ipf_assemble": (C.c_int32, [_vp, _vp, C.c_int64, _lp, _dp, _dp, _bp, _ip, _lp, _lp, _lp, _vp]),
+    "ipf_configs_create": (C.c_int32, [_vp, C.c_int64, _lp, _dp, _dp, _bp, _ip, _lp, _lp, _lp, C.POINTER(_vp)]),
+    "ipf_configs_destroy": (C.c_int32, [_vp, _vp]),
+    "ipf_assemble_configs": (C.c_int32, [_vp, _vp, _vp, _vp]),
+    "ipf_solve_begin_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.POINTER(_vp)]),
     "ipf_solve_begin": (C.c_int32, [_vp, _vp, _dp, _dp, _lp, C.c_int64, _lp, C.c_int64, _dp, C.POINTER(_vp)]),
     "ipf_solve_shape": (C.c_int32, [_vp, _lp, _lp]),
     "ipf_solve_system_to_host": (C.c_int32, [_vp, _vp, _dp, C.c_int64, _dp]),
@@ -122,6 +129,21 @@ class Context:
         if rc != IPF_OK:
             msg = self.lib.ipf_last_error(self.h).decode()
             raise IPFError(rc, _REF_MESSAGES.get(rc, msg) if rc in _REF_MESSAGES else msg)
+
+    def profile(self, on: bool = True):
+        self.lib.ipf_profile_enable(self.h, 1 if on else 0)
+
+    def profile_reset(self):
+        self.lib.ipf_profile_reset(self.h)
+
+    def profile_get(self, name: str):
+        ms, cnt = C.c_double(), C.c_int64()
+        self.lib.ipf_profile_get(self.h, name.encode(), C.byref(ms), C.byref(cnt))
+        return ms.value, cnt.value
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.ipf_stream(self.h) or 0)
 
     @property
     def launches(self) -> int:

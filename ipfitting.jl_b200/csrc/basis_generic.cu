@@ -292,6 +292,7 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * REC * (size_t)(npairs + 1), &rec));
     IPF_CHECK(ipf_scratch(ctx, 2, sizeof(double) * (size_t)(blk.maxdeg + 1) * (size_t)(npairs + 1), &xpow));
     if (npairs > 0) {
+        ProfScope prof_(ctx, "pair_record");
         pair_record_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(
             npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, (double*)rec, (double*)xpow);
         ctx->launches++;
@@ -329,12 +330,30 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = (const double*)rec; A.xpow = (const double*)xpow;
     A.npairs = npairs; A.rowE = ch.rowE.p; A.rowF = ch.rowF.p; A.rowV = ch.rowV.p;
     A.Psi = Psi->d; A.ld = Psi->ld; A.col0 = blk.col0; A.scratch = (double*)scr; A.counter = (int*)cnt;
+    if (ctx->profiling) {
+        // algorithmic work counter: unordered clusters sum_i C(n_i, N-1) (roofline numerator)
+        static const char* cnames[6] = {"", "", "count:clusters_2b", "count:clusters_3b", "count:clusters_4b", "count:clusters_5b"};
+        double tot = 0.0;
+        const int nx = blk.N - 1;
+        for (int64_t s = 0; s < nl.nsites; ++s) {
+            const double n = (double)(nl.h_site_off[s + 1] - nl.h_site_off[s]);
+            double c = 1.0;
+            for (int k = 0; k < nx; ++k) c *= (n - k) / (double)(k + 1);
+            if (n >= nx) tot += c;
+        }
+        ctx->prof[cnames[blk.N]].ms += tot;
+        ctx->prof["count:pairs"].ms += (double)nl.npairs;
+    }
+    static const char* names[6] = {"", "", "site_deriv_2b", "site_deriv_3b", "site_deriv_4b", "site_deriv_5b"};
+    {
+    ProfScope prof_(ctx, names[blk.N >= 2 && blk.N <= 5 ? blk.N : 0]);
     switch (blk.N) {
         case 2: site_deriv_generic_kernel<1><<<grid, GEN_THREADS, 0, st>>>(A); break;
         case 3: site_deriv_generic_kernel<2><<<grid, GEN_THREADS, 0, st>>>(A); break;
         case 4: site_deriv_generic_kernel<3><<<grid, GEN_THREADS, 0, st>>>(A); break;
         case 5: site_deriv_generic_kernel<4><<<grid, GEN_THREADS, 0, st>>>(A); break;
         default: return ipf_set_error(ctx, IPF_EINVAL, "body-order %d not supported", blk.N);
+    }
     }
     ctx->launches++;
     IPF_CUDA(ctx, cudaGetLastError());

@@ -70,6 +70,42 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
     return IPF_OK;
 }
 
+int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on) {
+    if (!ctx) return IPF_EINVAL;
+    ctx->profiling = on != 0;
+    return IPF_OK;
+}
+
+int32_t ipf_profile_reset(ipf_ctx* ctx) {
+    if (!ctx) return IPF_EINVAL;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& kv : ctx->prof) {
+        for (auto& ev : kv.second.pending) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    }
+    ctx->prof.clear();
+    return IPF_OK;
+}
+
+int32_t ipf_profile_get(ipf_ctx* ctx, const char* name, double* ms, int64_t* count) {
+    if (!ctx || !name) return IPF_EINVAL;
+    auto it = ctx->prof.find(name);
+    if (ms) *ms = 0.0;
+    if (count) *count = 0;
+    if (it == ctx->prof.end()) return IPF_OK;
+    cudaStreamSynchronize(ctx->stream);
+    ProfEntry& e = it->second;
+    for (auto& ev : e.pending) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev.first, ev.second) == cudaSuccess) e.ms += t;
+        cudaEventDestroy(ev.first);
+        cudaEventDestroy(ev.second);
+    }
+    e.pending.clear();
+    if (ms) *ms = e.ms;
+    if (count) *count = e.count;
+    return IPF_OK;
+}
+
 const char* ipf_last_error(ipf_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 int64_t ipf_launch_count(ipf_ctx* ctx) { return ctx ? ctx->launches : 0; }
 void* ipf_stream(ipf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -281,51 +317,96 @@ int32_t ipf_neighbours(ipf_ctx* ctx, int32_t nat, const double* pos, const doubl
     return IPF_OK;
 }
 
-int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg, const int64_t* atom_off,
-                     const double* pos, const double* cell, const uint8_t* pbc, const int32_t* Z,
-                     const int64_t* rowE, const int64_t* rowF, const int64_t* rowV, ipf_matrix* Psi) {
+// Device-resident configuration set: the chunks ipf_assemble works through.
+struct ipf_configs {
+    std::vector<ChunkDev*> chunks;
+    int64_t ncfg = 0, natoms = 0, max_row = 0;
+    ~ipf_configs() { for (auto* c : chunks) delete c; }
+};
+
+int32_t ipf_configs_create(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
+                           const double* cell, const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
+                           const int64_t* rowF, const int64_t* rowV, ipf_configs** out) {
     (void)Z;
-    if (!ctx || !basis || ncfg < 0 || !atom_off || !cell || !pbc || !rowE || !rowF || !rowV || !Psi)
-        return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: bad arguments");
-    if (Psi->ncols != basis->ncols)
-        return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: Psi has %lld columns, basis has %lld",
-                             (long long)Psi->ncols, (long long)basis->ncols);
-    if (ncfg == 0) return IPF_OK;
-    if (!pos && atom_off[ncfg] > 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: pos is NULL");
+    if (!ctx || !out || ncfg < 0 || !atom_off || (ncfg && (!cell || !pbc || !rowE || !rowF || !rowV)))
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_configs_create: bad arguments");
+    *out = nullptr;
+    if (ncfg && !pos && atom_off[ncfg] > 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_configs_create: pos is NULL");
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
-    IPF_CHECK(validate_configs(ctx, ncfg, atom_off, pos, cell));
-    // row blocks must lie inside the matrix
+    if (ncfg) IPF_CHECK(validate_configs(ctx, ncfg, atom_off, pos, cell));
+    ipf_configs* cf = new (std::nothrow) ipf_configs();
+    if (!cf) return IPF_ENOMEM;
+    cf->ncfg = ncfg;
+    cf->natoms = ncfg ? atom_off[ncfg] : 0;
     for (int64_t c = 0; c < ncfg; ++c) {
         const int64_t nat = atom_off[c + 1] - atom_off[c];
         const int64_t r[3] = {rowE[c], rowF[c], rowV[c]};
         const int64_t len[3] = {1, 3 * nat, 6};
-        for (int k = 0; k < 3; ++k)
-            if (r[k] < 0 || (r[k] > 0 && r[k] - 1 + len[k] > Psi->nrows))
-                return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: config %lld: row block out of range", (long long)c);
+        for (int k = 0; k < 3; ++k) {
+            if (r[k] < 0) { delete cf; return ipf_set_error(ctx, IPF_EINVAL, "config %lld: negative row", (long long)c); }
+            if (r[k] > 0) cf->max_row = std::max(cf->max_row, r[k] - 1 + len[k]);
+        }
     }
-    // chunks of configurations: bounded scratch, one neighbour list per distinct cutoff
+    // chunks of configurations: bounded scratch per launch
     const int64_t max_atoms_chunk = 1 << 16;
     int64_t c0 = 0;
     while (c0 < ncfg) {
         int64_t c1 = c0 + 1;
         while (c1 < ncfg && atom_off[c1 + 1] - atom_off[c0] <= max_atoms_chunk) ++c1;
-        ChunkDev ch;
-        IPF_CHECK(upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, ch));
+        ChunkDev* ch = new (std::nothrow) ChunkDev();
+        if (!ch) { delete cf; return IPF_ENOMEM; }
+        cf->chunks.push_back(ch);
+        int rc = upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, *ch);
+        if (rc != IPF_OK) { delete cf; return rc; }
+        c0 = c1;
+    }
+    *out = cf;
+    return IPF_OK;
+}
+
+int32_t ipf_configs_destroy(ipf_ctx* ctx, ipf_configs* cf) {
+    if (!cf) return IPF_OK;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    delete cf;
+    return IPF_OK;
+}
+
+int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_configs* cf, ipf_matrix* Psi) {
+    if (!ctx || !basis || !cf || !Psi) return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble_configs: bad arguments");
+    if (Psi->ncols != basis->ncols)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: Psi has %lld columns, basis has %lld",
+                             (long long)Psi->ncols, (long long)basis->ncols);
+    if (cf->max_row > Psi->nrows)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: row block out of range (%lld > %lld rows)",
+                             (long long)cf->max_row, (long long)Psi->nrows);
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (const ChunkDev* ch : cf->chunks) {
+        // one neighbour list per distinct cutoff
         std::vector<double> done_rcut;
         for (size_t k = 0; k < basis->blocks.size(); ++k) {
             const double rc = basis->blocks[k].rc2;
             if (std::find(done_rcut.begin(), done_rcut.end(), rc) != done_rcut.end()) continue;
             done_rcut.push_back(rc);
             NeighList nl;
-            IPF_CHECK(ipf_build_neighbours(ctx, ch, rc, nl));
+            IPF_CHECK(ipf_build_neighbours(ctx, *ch, rc, nl));
             for (size_t k2 = k; k2 < basis->blocks.size(); ++k2)
                 if (basis->blocks[k2].rc2 == rc)
-                    IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], ch, nl, Psi));
+                    IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
         }
-        c0 = c1;
     }
     IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IPF_OK;
+}
+
+int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg, const int64_t* atom_off,
+                     const double* pos, const double* cell, const uint8_t* pbc, const int32_t* Z,
+                     const int64_t* rowE, const int64_t* rowF, const int64_t* rowV, ipf_matrix* Psi) {
+    if (!ctx || !basis || !Psi) return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: bad arguments");
+    ipf_configs* cf = nullptr;
+    IPF_CHECK(ipf_configs_create(ctx, ncfg, atom_off, pos, cell, pbc, Z, rowE, rowF, rowV, &cf));
+    const int rc = ipf_assemble_configs(ctx, basis, cf, Psi);
+    ipf_configs_destroy(ctx, cf);
+    return rc;
 }
 
 }  // extern "C"

@@ -180,8 +180,11 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
         IPF_CUDA(ctx, cudaEventCreate(&e1));
         IPF_CUDA(ctx, cudaEventRecord(e0, st));
     }
-    gram_kernel<<<dim3(T, nchunk), GRAM_THREADS, GRAM_SMEM, st>>>(A, ld, Mpad, nt, nchunk, chunk_rows,
-                                                                  (const int2*)d_tiles, (double*)part);
+    {
+        ProfScope prof_(ctx, "gram");
+        gram_kernel<<<dim3(T, nchunk), GRAM_THREADS, GRAM_SMEM, st>>>(A, ld, Mpad, nt, nchunk, chunk_rows,
+                                                                      (const int2*)d_tiles, (double*)part);
+    }
     if (kernel_ms) IPF_CUDA(ctx, cudaEventRecord(e1, st));
     gram_reduce_kernel<<<T, 256, 0, st>>>((const double*)part, T, nchunk, (const int2*)d_tiles, G, n1);
     ctx->launches += 2;

@@ -3,12 +3,23 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/ipf_b200.h"
 
+// per-kernel device timing (CUDA events on the ctx stream), off by default
+struct ProfEntry {
+    double ms = 0.0;
+    int64_t count = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
 struct ipf_ctx {
+    bool profiling = false;
+    std::map<std::string, ProfEntry> prof;
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -55,6 +66,26 @@ int ipf_set_error(ipf_ctx* ctx, int code, const char* fmt, ...);
         if (rc__ != IPF_OK) return rc__; \
     } while (0)
 
+// RAII timing scope: records an event pair around the launches issued inside it
+struct ProfScope {
+    ipf_ctx* ctx;
+    ProfEntry* e = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ProfScope(ipf_ctx* c, const char* name) : ctx(c) {
+        if (!c->profiling) return;
+        e = &c->prof[name];
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, c->stream);
+    }
+    ~ProfScope() {
+        if (!e) return;
+        cudaEventRecord(e1, ctx->stream);
+        e->pending.emplace_back(e0, e1);
+        e->count++;
+    }
+};
+
 // grow-only scratch slot
 int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out);
 
@@ -86,6 +117,7 @@ struct NeighList {
     DevBuf<double> pR;            // [npairs*3] bond vector R_ij = X_j + S C - X_i
     DevBuf<int32_t> prev;         // [npairs] chunk-global index of the reverse pair (j,i,-S)
     std::vector<int64_t> h_cfg_pair_off;   // [ncfg+1] host copy of per-config pair offsets
+    std::vector<int64_t> h_site_off;       // [nsites+1] host copy of site_off
 };
 
 // Config chunk resident on the device

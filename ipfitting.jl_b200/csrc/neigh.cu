@@ -236,6 +236,7 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
         return IPF_OK;
     }
     cudaStream_t st = ctx->stream;
+    ProfScope prof_(ctx, "neighbour_list");
     // site -> config map
     std::vector<int32_t> h_site_cfg(nsites);
     for (int64_t c = 0; c < ncfg; ++c)
@@ -270,7 +271,8 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     IPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st));
     ctx->launches++;
     // per-config pair offsets to the host (also gives the total)
-    std::vector<int64_t> h_site_off(nsites + 1);
+    std::vector<int64_t>& h_site_off = nl.h_site_off;
+    h_site_off.assign(nsites + 1, 0);
     IPF_CUDA(ctx, cudaMemcpyAsync(h_site_off.data(), nl.site_off.p, sizeof(int64_t) * (nsites + 1),
                                   cudaMemcpyDeviceToHost, st));
     IPF_CUDA(ctx, cudaStreamSynchronize(st));

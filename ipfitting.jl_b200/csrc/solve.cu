@@ -362,22 +362,28 @@ void free_solve(ipf_solver* S) {
 
 extern "C" {
 
-int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
-                        const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,
-                        const double* Dinv, ipf_solver** out) {
-    if (!ctx || !Psi || !out || (!Y && Psi->nrows) || (!W && Psi->nrows))
+// bit 1: NaN in Y, bit 2: NaN in W (all rows, as the reference checks before the row selection)
+__global__ void nan_check_kernel(const double* __restrict__ Y, const double* __restrict__ W, int64_t n, int* flag) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    int f = 0;
+    if (isnan(Y[r])) f |= 2;
+    if (isnan(W[r])) f |= 4;
+    if (f) atomicOr(flag, f);
+}
+
+// All vector arguments are DEVICE pointers here.
+int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* dY, const double* dW,
+                            const int64_t* dIrows, int64_t nIrows, const int64_t* dIcols, int64_t nIcols,
+                            const double* dDinv, ipf_solver** out) {
+    if (!ctx || !Psi || !out || (!dY && Psi->nrows) || (!dW && Psi->nrows))
         return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad arguments");
     *out = nullptr;
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
     const int64_t nrows = Psi->nrows;
-    // NaN checks in the reference's order (src/lsq.jl:261-262)
-    for (int64_t r = 0; r < nrows; ++r) if (std::isnan(Y[r])) return ipf_set_error(ctx, IPF_ENAN_Y, "NaN detected in observations vector");
-    for (int64_t r = 0; r < nrows; ++r) if (std::isnan(W[r])) return ipf_set_error(ctx, IPF_ENAN_W, "NaN detected in weights vector");
-    const int64_t M = Irows ? nIrows : nrows;
-    const int64_t n64 = Icols ? nIcols : Psi->ncols;
+    const int64_t M = dIrows ? nIrows : nrows;
+    const int64_t n64 = dIcols ? nIcols : Psi->ncols;
     if (M < 0 || n64 <= 0 || n64 > 1 << 20) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad system size");
-    if (Irows) for (int64_t r = 0; r < M; ++r) if (Irows[r] < 0 || Irows[r] >= nrows) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: row index out of range");
-    if (Icols) for (int64_t c = 0; c < n64; ++c) if (Icols[c] < 0 || Icols[c] >= Psi->ncols) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: column index out of range");
     ipf_solver* S = new ipf_solver();
     S->M = M; S->n = (int)n64; S->n1 = S->n + 1;
     S->Mpad = ((M + 15) / 16) * 16;
@@ -385,14 +391,7 @@ int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, co
     S->ncp = ((S->n1 + 127) / 128) * 128;
     cudaStream_t st = ctx->stream;
     const size_t abytes = sizeof(double) * (size_t)S->Mpad * S->ncp;
-    int rc = IPF_OK;
-    double *dY = nullptr, *dW = nullptr;
-    int64_t *dIr = nullptr, *dIc = nullptr;
-    auto fail = [&](int code) {
-        for (void* p : {(void*)dY, (void*)dW, (void*)dIr, (void*)dIc}) if (p) cudaFree(p);
-        free_solve(S);
-        return code;
-    };
+    auto fail = [&](int code) { free_solve(S); return code; };
     cudaError_t e = cudaMalloc((void**)&S->A, abytes);
     if (e != cudaSuccess) return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %zu bytes for the weighted system: %s", abytes, cudaGetErrorString(e)));
     const size_t nn = (size_t)S->n * S->n;
@@ -404,27 +403,59 @@ int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, co
         (e = cudaMalloc((void**)&S->flag, sizeof(int) * 4)) != cudaSuccess ||
         (e = cudaMalloc((void**)&S->red, sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8))) != cudaSuccess)
         return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %s", cudaGetErrorString(e)));
-    if ((rc = upload(ctx, &dY, Y, (size_t)nrows)) != IPF_OK) return fail(rc);
-    if ((rc = upload(ctx, &dW, W, (size_t)nrows)) != IPF_OK) return fail(rc);
-    if (Irows && (rc = upload(ctx, &dIr, Irows, (size_t)M)) != IPF_OK) return fail(rc);
-    if (Icols && (rc = upload(ctx, &dIc, Icols, (size_t)n64)) != IPF_OK) return fail(rc);
-    if (Dinv && (rc = upload(ctx, &S->dinv, Dinv, (size_t)n64)) != IPF_OK) return fail(rc);
+    if (dDinv) {
+        if ((e = cudaMalloc((void**)&S->dinv, sizeof(double) * n64)) != cudaSuccess ||
+            (e = cudaMemcpyAsync(S->dinv, dDinv, sizeof(double) * n64, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+            return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %s", cudaGetErrorString(e)));
+    }
     cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st);
+    if (nrows) nan_check_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(dY, dW, nrows, S->flag);
     // zero columns n1..ncp (the Gram tiles read them)
     if (S->ncp > S->n1) cudaMemsetAsync(S->A + (size_t)S->n1 * S->Mpad, 0, sizeof(double) * (size_t)(S->ncp - S->n1) * S->Mpad, st);
     dim3 grid((unsigned)((S->Mpad + 255) / 256), (unsigned)((S->n1 + K4_COLS - 1) / K4_COLS));
-    k4_build_kernel<<<grid, 256, 0, st>>>(Psi->d, Psi->ld, dY, dW, dIr, M, S->Mpad, dIc, S->n, S->dinv, S->A, S->flag);
-    ctx->launches++;
+    { ProfScope prof_(ctx, "k4_build");
+    k4_build_kernel<<<grid, 256, 0, st>>>(Psi->d, Psi->ld, dY, dW, dIrows, M, S->Mpad, dIcols, S->n, S->dinv, S->A, S->flag); }
+    ctx->launches += 2;
     int hflag[4] = {0, 0, 0, 0};
     e = cudaMemcpyAsync(hflag, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) return fail(ipf_set_error(ctx, IPF_ECUDA, "ipf_solve_begin: %s", cudaGetErrorString(e)));
-    for (void* p : {(void*)dY, (void*)dW, (void*)dIr, (void*)dIc}) if (p) cudaFree(p);
-    dY = dW = nullptr; dIr = dIc = nullptr;
-    if (hflag[0]) return fail(ipf_set_error(ctx, IPF_ENAN_PSI, "discovered NaNs in LSQ system matrix"));
+    // the reference's order of checks (src/lsq.jl:261-262, 285-292)
+    if (hflag[0] & 2) return fail(ipf_set_error(ctx, IPF_ENAN_Y, "NaN detected in observations vector"));
+    if (hflag[0] & 4) return fail(ipf_set_error(ctx, IPF_ENAN_W, "NaN detected in weights vector"));
+    if (hflag[0] & 1) return fail(ipf_set_error(ctx, IPF_ENAN_PSI, "discovered NaNs in LSQ system matrix"));
     *out = S;
     return IPF_OK;
+}
+
+int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
+                        const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,
+                        const double* Dinv, ipf_solver** out) {
+    if (!ctx || !Psi || !out || (!Y && Psi->nrows) || (!W && Psi->nrows))
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad arguments");
+    *out = nullptr;
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int64_t nrows = Psi->nrows;
+    const int64_t M = Irows ? nIrows : nrows;
+    const int64_t n64 = Icols ? nIcols : Psi->ncols;
+    if (M < 0 || n64 <= 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad system size");
+    if (Irows) for (int64_t r = 0; r < M; ++r) if (Irows[r] < 0 || Irows[r] >= nrows) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: row index out of range");
+    if (Icols) for (int64_t c = 0; c < n64; ++c) if (Icols[c] < 0 || Icols[c] >= Psi->ncols) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: column index out of range");
+    DevBuf<double> dY, dW, dD;
+    DevBuf<int64_t> dIr, dIc;
+    cudaStream_t st = ctx->stream;
+    IPF_CUDA(ctx, dY.alloc(nrows)); IPF_CUDA(ctx, dW.alloc(nrows));
+    if (nrows) {
+        IPF_CUDA(ctx, cudaMemcpyAsync(dY.p, Y, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
+        IPF_CUDA(ctx, cudaMemcpyAsync(dW.p, W, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
+    }
+    if (Irows) { IPF_CUDA(ctx, dIr.alloc(M)); if (M) IPF_CUDA(ctx, cudaMemcpyAsync(dIr.p, Irows, sizeof(int64_t) * M, cudaMemcpyHostToDevice, st)); }
+    if (Icols) { IPF_CUDA(ctx, dIc.alloc(n64)); IPF_CUDA(ctx, cudaMemcpyAsync(dIc.p, Icols, sizeof(int64_t) * n64, cudaMemcpyHostToDevice, st)); }
+    if (Dinv) { IPF_CUDA(ctx, dD.alloc(n64)); IPF_CUDA(ctx, cudaMemcpyAsync(dD.p, Dinv, sizeof(double) * n64, cudaMemcpyHostToDevice, st)); }
+    // (ipf_solve_begin_dev synchronises the stream before returning, so the temporaries may be freed)
+    return ipf_solve_begin_dev(ctx, Psi, dY.p, dW.p, Irows ? dIr.p : nullptr, M, Icols ? dIc.p : nullptr, n64,
+                               Dinv ? dD.p : nullptr, out);
 }
 
 int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S) {
@@ -491,7 +522,8 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     for (int attempt = 0;; ++attempt) {
         copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, shift);
         IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
-        chol_lower_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->flag);
+        { ProfScope prof_(ctx, "cholesky");
+        chol_lower_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->flag); }
         ctx->launches += 2;
         int hf[4];
         IPF_CUDA(ctx, cudaMemcpyAsync(hf, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
@@ -521,7 +553,8 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         IPF_CUDA(ctx, cudaEventCreate(&e0));
         IPF_CUDA(ctx, cudaEventCreate(&e1));
         IPF_CUDA(ctx, cudaEventRecord(e0, st));
-        trsm_rows_kernel<<<(unsigned)((S->Mpad + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, 0, st>>>(S->A, S->Mpad, S->M, S->L, n);
+        { ProfScope prof_(ctx, "trsm");
+        trsm_rows_kernel<<<(unsigned)((S->Mpad + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, 0, st>>>(S->A, S->Mpad, S->M, S->L, n); }
         IPF_CUDA(ctx, cudaEventRecord(e1, st));
         ctx->launches++;
         IPF_CUDA(ctx, cudaStreamSynchronize(st));
@@ -555,7 +588,8 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     IPF_CUDA(ctx, cudaMemcpyAsync(cc, S->vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
     trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtmp, n, cc, 1);
     const int64_t nb = (S->Mpad + 255) / 256;
-    residual_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, n, cc, S->red + 8);
+    { ProfScope prof_(ctx, "residual");
+    residual_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, n, cc, S->red + 8); }
     sum_pairs_kernel<<<1, 1024, 0, st>>>(S->red + 8, nb, S->red);
     // solution in the original (scaled) basis: c = Rtot^-1 w
     double* cf = S->G + S->n1;

@@ -85,7 +85,7 @@ def _pairs(at: Atoms, rcut: float):
             continue
         h = 1.0 / np.linalg.norm(Ci[:, a])
         s = at.X @ Ci[:, a]
-        n = int(math.floor(rcut / h + (s.max() - s.min()))) + 1
+        n = int(math.floor(rcut / h + (s.max() - s.min())))
         rng_.append(np.arange(-n, n + 1))
     S = np.array([[i, j, k] for i in rng_[0] for j in rng_[1] for k in rng_[2]], dtype=np.float64)
     sh = S @ C                                                # [ns,3]
