@@ -256,9 +256,11 @@ def run_ours(args):
         barrier()
     ms_dev = e0.elapsed_time(e1)
     launches = ctx.launches - l0
-    prof = {k: ctx.profile_get(k) for k in ("neighbour_list", "pair_record", "site_deriv_2b", "site_deriv_3b",
+    prof = {k: ctx.profile_get(k) for k in ("neighbour_list", "pair_record", "site_deriv_2b", "site_deriv_3b", "gather_3b",
                                              "k4_build", "gram", "cholesky", "trsm", "residual")}
     clusters3 = ctx.profile_get("count:clusters_3b")[0]
+    ordered3 = ctx.profile_get("count:ordered_pairs_3b")[0]
+    pairs3 = ctx.profile_get("count:pairs_3b")[0]
     ctx.profile(False)
     if comm is not None:
         t = torch.tensor([ms_dev], device="cuda", dtype=torch.float64)
@@ -292,28 +294,48 @@ def run_ours(args):
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel (3B basis evaluation: FP64 FMA pipe)
+    # ---- rooflines: the three heavy kernels, the slowest one is reported as `roofline`
     blk3 = [b for b in basis.blocks if b.N == 3][0]
-    flops3 = clusters3 * cluster_flops(blk3)
-    ms3, n3 = prof["site_deriv_3b"]
+    D = blk3.maxdeg
     peaks = {}
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk):
         peaks = json.load(open(pk))
-    fp64_peak = 33.9      # TFLOP/s, DFMA chains measured on this pool (profiles/r01_fp64_peaks.jsonl)
-    ach = flops3 / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
-    roofline = {"kernel": "site_deriv_generic_kernel<2> (3-body basis + derivatives)", "bound": "fp64",
-                "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                "traffic": None, "launches": n3, "avg_launch_ms": ms3 / max(1, n3),
-                "algorithmic_flops_per_launch": flops3 / max(1, n3),
-                "peak_source": "own DFMA-chain microbenchmark tools/peaks.cu (MEASURED_PEAKS.json has no FP64 entry); "
-                               "DMMA m8n8k4 peak 37.1 TFLOP/s, HBM %.0f GB/s (driver-measured)" % peaks.get("hbm_gbs", 6553.9)}
+    hbm_peak = float(peaks.get("hbm_gbs", 6553.9))
+    fp64_peak, dmma_peak = 33.9, 37.1      # TFLOP/s, tools/peaks.cu on this pool (profiles/r01_fp64_peaks.jsonl)
+    # (a) moments kernel: FP64 operations of the factorised algorithm (FMA = 2, MUL = ADD = 1), DESIGN.md §kernels
+    f_k = 5 + D + 9 * (D * (D + 1) // 2) + 2 * (D + 1)          # per ordered neighbour pair (j, k)
+    n_single = int(np.sum(np.bincount(blk3.mono_b) == 1)); n_double = blk3.nb - n_single
+    f_comb = 33 * n_double + 25 * n_single                      # per own leg: combine moments into all functions
+    flops3 = ordered3 * f_k + pairs3 * f_comb
+    ms3, n3 = prof["site_deriv_3b"]
+    ach3 = flops3 / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
+    naive3 = clusters3 * cluster_flops(blk3) / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
+    r_mom = {"kernel": "moments3b_kernel (3-body basis values + derivatives per ordered pair)", "bound": "fp64",
+             "achieved": ach3, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach3 / fp64_peak, "traffic": None,
+             "launches": n3, "avg_launch_ms": ms3 / max(1, n3), "algorithmic_flops_per_launch": flops3 / max(1, n3),
+             "naive_algorithm_equivalent_tflops": naive3, "total_ms": ms3}
+    # (b) gather kernel: HBM bytes = own + reverse scratch entry (32 B each) per (pair, function) + the rows written
+    msg, ng = prof["gather_3b"]
+    bytes_g = pairs3 * blk3.nb * 64.0 + float(nrows) * blk3.nb * 8.0 * args.steps
+    achg = bytes_g / (msg * 1e-3) * 1e-9 if msg > 0 else 0.0
+    r_gat = {"kernel": "gather3b_kernel (scratch -> E/F/V rows)", "bound": "hbm", "achieved": achg, "peak": hbm_peak,
+             "unit": "GB/s", "frac": achg / hbm_peak, "traffic": None, "launches": ng, "avg_launch_ms": msg / max(1, ng),
+             "algorithmic_bytes_per_launch": bytes_g / max(1, ng), "total_ms": msg}
+    # (c) Gram kernel: algorithmic flops M n (n+1) (symmetric half) on the FP64 tensor pipe
     gram_ms, gram_n = prof["gram"]
     M = len(Irows)
-    gram_flops = float(M) * ncols * (ncols + 1) * gram_n     # algorithmic, symmetric half
+    gram_flops = float(M) * ncols * (ncols + 1) * gram_n
+    achd = gram_flops / (gram_ms * 1e-3) * 1e-12 if gram_ms > 0 else 0.0
+    r_gram = {"kernel": "gram_kernel (DMMA m8n8k4 f64, upper-triangular tiles)", "bound": "tensor", "achieved": achd,
+              "peak": dmma_peak, "unit": "TFLOP/s", "frac": achd / dmma_peak, "traffic": None, "launches": gram_n,
+              "avg_launch_ms": gram_ms / max(1, gram_n), "algorithmic_flops_per_launch": gram_flops / max(1, gram_n),
+              "total_ms": gram_ms}
+    cands = sorted([r_mom, r_gat, r_gram], key=lambda r: -r["total_ms"])
+    roofline = cands[0]
+    roofline["peak_source"] = ("HBM: MEASURED_PEAKS.json (driver); FP64 FMA 33.9 and DMMA 37.1 TFLOP/s: own microbenchmark "
+                               "tools/peaks.cu (MEASURED_PEAKS.json has no FP64 entry), cuBLAS DGEMM 8192^3 = 35.5")
     kernels = {k: {"ms": v[0], "launches": v[1]} for k, v in prof.items()}
-    kernels["gram"]["tflops_algorithmic"] = gram_flops / (gram_ms * 1e-3) * 1e-12 if gram_ms > 0 else 0.0
-    kernels["gram"]["frac_of_dmma_peak_37.1"] = kernels["gram"]["tflops_algorithmic"] / 37.1
 
     # ---- CPU baseline (restated reference path) on a bounded sample, rank 0, N = 1 only
     cpu = None
@@ -338,7 +360,8 @@ def run_ours(args):
             "solve_ms": (ms_dev - 1e3 * t_asm) / args.steps,
             "e2e": {"value": e2e_val, "unit": "entries/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline, "kernels": kernels,
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
+            "roofline_other": cands[1:], "kernels": kernels,
             "cpu_baseline": cpu, "fit": {"rel_rms": math.sqrt(ssr / ssy) if comm is None else rel_e2e,
                                          "coeff_diff_dev_vs_e2e": float(np.linalg.norm(c_dev - c_e2e) / np.linalg.norm(c_e2e))}}
     print(json.dumps(line), flush=True)

@@ -85,6 +85,8 @@ void* ipf_stream(ipf_ctx* ctx);
 /* per-kernel device timing (CUDA events on the ctx stream), used by bench.py for the
  * roofline numbers.  Names: "neighbour_list", "pair_record", "site_deriv_2b|3b|4b|5b",
  * "k4_build", "gram", "cholesky", "trsm", "residual". */
+/* on = 1: use only the table-driven kernels (the specialised 3-body path is then bypassed) */
+int32_t ipf_set_force_generic(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_reset(ipf_ctx* ctx);
 int32_t ipf_profile_get(ipf_ctx* ctx, const char* name, double* ms, int64_t* count);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ipf_last_error": (C.c_char_p, [_vp]),
     "ipf_launch_count": (C.c_int64, [_vp]),
     "ipf_stream": (_vp, [_vp]),
+    "ipf_set_force_generic": (C.c_int32, [_vp, C.c_int32]),
     "ipf_profile_enable": (C.c_int32, [_vp, C.c_int32]),
     "ipf_profile_reset": (C.c_int32, [_vp]),
     "ipf_profile_get": (C.c_int32, [_vp, C.c_char_p, _dp, _lp]),
@@ -129,6 +130,9 @@ class Context:
         if rc != IPF_OK:
             msg = self.lib.ipf_last_error(self.h).decode()
             raise IPFError(rc, _REF_MESSAGES.get(rc, msg) if rc in _REF_MESSAGES else msg)
+
+    def force_generic(self, on: bool = True):
+        self.lib.ipf_set_force_generic(self.h, 1 if on else 0)
 
     def profile(self, on: bool = True):
         self.lib.ipf_profile_enable(self.h, 1 if on else 0)

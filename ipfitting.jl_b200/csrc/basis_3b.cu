@@ -1,0 +1,423 @@
+// basis_3b.cu -- K3 fast path: canonical 3-body bond-angle basis nbpolys(3, desc, D).
+//
+// Same own-leg decomposition as basis_generic.cu (one thread per ordered pair
+// p = (i, j)), but the sum over the second leg k is factorised.  Every monomial
+//     x_j^a x_k^b w_jk^c            (orbit partner: x_j^b x_k^a w_jk^c)
+// is (thread constant) x (function of k only), so per own leg only the MOMENTS
+//     Z_c[e] = sum_k fc_k x_k^e w_jk^c                 (scalar,  e + c <= D)
+//     U_c[e] = sum_k fc_k x_k^e w_jk^(c-1) Rhat_k      (vector,  c >= 1)
+// are accumulated in the k loop (5 FP64 instructions per (e, c) and k instead of
+// ~7 per basis function and k), and the basis functions (a <= b, c) follow from
+//     S0 = x^a Z_c[b] + x^b Z_c[a]        S1 = a x^(a-1) Z_c[b] + b x^(b-1) Z_c[a]
+//     T  = c (x^a U_c[b] + x^b U_c[a]) - c S0 Rhat_j                 (x = x_j; a = b: one term)
+//     g_p = (fc_j' S0 + fc_j x_j' S1) Rhat_j + fc_j/r_j T,     e_p = fc_j S0 / 2.
+// The (e, c) plane is cut into units of consecutive c (register budget); a CTA
+// runs one unit for 128 consecutive pairs.  (g_p, e_p) go to the HBM scratch
+// S[pair][scol][4] (scol = unit-major column order, so a thread writes its unit's
+// functions contiguously); gather3b_kernel sums them in a fixed order into the
+// E / F / V rows (deterministic, no atomics) with fully coalesced 1 KB reads per
+// (pair, 32 columns), own and reverse pair alike.
+#include "ipf_common.cuh"
+
+int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec, const double** xpow);
+
+namespace {
+
+constexpr int REC = 8;
+constexpr int A_THREADS = 128;
+constexpr int MAXD = 14;
+
+struct Fast3Args {
+    int64_t p0, np;                // batch pair range [p0, p0 + np)
+    int64_t npairs;                // pairs in the chunk (stride of the xpow table)
+    const double* rec;
+    const double* xpow;
+    const int64_t* site_off;
+    const int64_t* atom_off;
+    const int32_t* psite;          // chunk-global site of every pair
+    int nb;
+    double* S;                     // [np][nb][4], scol order
+};
+
+// number of basis functions with w-exponent c (degree-D basis): pairs a <= b, a + b <= D - c, minus the constant
+__host__ __device__ constexpr int nfun_c(int D, int c) {
+    int n = 0;
+    for (int a = 0; a <= (D - c) / 2; ++a) n += (D - c - a) - a + 1;
+    return n - (c == 0 ? 1 : 0);
+}
+__host__ __device__ constexpr int scol_base(int D, int C0) {
+    int n = 0;
+    for (int c = 0; c < C0; ++c) n += nfun_c(D, c);
+    return n;
+}
+
+__host__ __device__ constexpr int cmidx(int c, int a, int b) { return (c * (MAXD + 1) + a) * (MAXD + 1) + b; }
+
+__device__ __forceinline__ double4 ld4(const double* p) {
+    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
+    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
+    return make_double4(a.x, a.y, b.x, b.y);
+}
+
+template <int E>
+__device__ __forceinline__ double ipow_c(double w) {
+    if constexpr (E <= 0) return 1.0;
+    else if constexpr (E == 1) return w;
+    else {
+        const double h = ipow_c<E / 2>(w);
+        if constexpr (E % 2 == 0) return h * h;
+        else return h * h * w;
+    }
+}
+
+// one unit = exponents c in [C0, C1] of w
+template <int D, int C0, int C1>
+__device__ __forceinline__ void unit3b(const Fast3Args& A) {
+    const int64_t pl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pl >= A.np) return;
+    const int64_t p = A.p0 + pl;
+    constexpr int NC = C1 - C0 + 1;
+    constexpr int EMAX = D - C0;            // largest x-exponent in this unit
+    double Z[NC][EMAX + 1];
+    double U[NC][EMAX + 1][3];
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci)
+#pragma unroll
+        for (int e = 0; e <= EMAX; ++e) { Z[ci][e] = 0.0; U[ci][e][0] = U[ci][e][1] = U[ci][e][2] = 0.0; }
+
+    const double4 o0v = ld4(A.rec + REC * p);
+    const double4 o1v = ld4(A.rec + REC * p + 4);
+    const double Rj0 = o0v.x, Rj1 = o0v.y, Rj2 = o0v.z, rinvj = o0v.w;
+    const double dxj = o1v.y, fcj = o1v.z, dfcj = o1v.w;
+    const int64_t s = A.psite[p];
+    const int64_t k0 = A.site_off[s], k1 = A.site_off[s + 1];
+
+    for (int64_t k = k0; k < k1; ++k) {
+        if (k == p) continue;
+        const double4 a0 = ld4(A.rec + REC * k);
+        const double4 a1 = ld4(A.rec + REC * k + 4);
+        const double w = Rj0 * a0.x + Rj1 * a0.y + Rj2 * a0.z;
+        const double fck = a1.z;
+        // wl[ci] = fck w^(c-1), c = C0 + ci  (unused for c = 0)
+        double wl[NC];
+        if constexpr (C0 >= 1) {
+            wl[0] = fck * ipow_c<(C0 >= 1 ? C0 - 1 : 0)>(w);
+#pragma unroll
+            for (int ci = 1; ci < NC; ++ci) wl[ci] = wl[ci - 1] * w;
+        } else {
+            wl[0] = 0.0;
+            if constexpr (NC > 1) {
+                wl[1] = fck;
+#pragma unroll
+                for (int ci = 2; ci < NC; ++ci) wl[ci] = wl[ci - 1] * w;
+            }
+        }
+#pragma unroll
+        for (int e = 0; e <= EMAX; ++e) {
+            const double xe = __ldg(A.xpow + (int64_t)e * A.npairs + k);
+#pragma unroll
+            for (int ci = 0; ci < NC; ++ci) {
+                const int c = C0 + ci;
+                if (e <= D - c) {
+                    if (c == 0) {
+                        Z[ci][e] = fma(xe, fck, Z[ci][e]);
+                    } else {
+                        const double t = xe * wl[ci];          // fck x^e w^(c-1)
+                        U[ci][e][0] = fma(t, a0.x, U[ci][e][0]);
+                        U[ci][e][1] = fma(t, a0.y, U[ci][e][1]);
+                        U[ci][e][2] = fma(t, a0.z, U[ci][e][2]);
+                        Z[ci][e] = fma(t, w, Z[ci][e]);
+                    }
+                }
+            }
+        }
+    }
+    // ---- combine into basis functions
+    double X[EMAX + 1], dX[EMAX + 1];
+#pragma unroll
+    for (int e = 0; e <= EMAX; ++e) X[e] = __ldg(A.xpow + (int64_t)e * A.npairs + p);
+    dX[0] = 0.0;
+#pragma unroll
+    for (int e = 1; e <= EMAX; ++e) dX[e] = (double)e * X[e - 1];
+    const double tang = fcj * rinvj;
+    const double fdx = fcj * dxj;
+    double4* Sp = reinterpret_cast<double4*>(A.S) + pl * A.nb;
+    int sc = scol_base(D, C0);
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci) {
+        const int c = C0 + ci;
+#pragma unroll
+        for (int a = 0; a <= (D - c) / 2; ++a) {
+#pragma unroll
+            for (int b = a; b <= D - c - a; ++b) {
+                if (a + b + c == 0) continue;
+                double S0, S1, T0, T1, T2;
+                if (a == b) {
+                    S0 = X[a] * Z[ci][a];
+                    S1 = dX[a] * Z[ci][a];
+                    T0 = X[a] * U[ci][a][0]; T1 = X[a] * U[ci][a][1]; T2 = X[a] * U[ci][a][2];
+                } else {
+                    S0 = fma(X[a], Z[ci][b], X[b] * Z[ci][a]);
+                    S1 = fma(dX[a], Z[ci][b], dX[b] * Z[ci][a]);
+                    T0 = fma(X[a], U[ci][b][0], X[b] * U[ci][a][0]);
+                    T1 = fma(X[a], U[ci][b][1], X[b] * U[ci][a][1]);
+                    T2 = fma(X[a], U[ci][b][2], X[b] * U[ci][a][2]);
+                }
+                const double cc = (double)c;
+                const double radial = fma(dfcj, S0, fdx * S1) - tang * cc * S0;   // coefficient of Rhat_j
+                const double tc = tang * cc;
+                double4 g;
+                g.x = fma(radial, Rj0, tc * T0);
+                g.y = fma(radial, Rj1, tc * T1);
+                g.z = fma(radial, Rj2, tc * T2);
+                g.w = 0.5 * fcj * S0;
+                Sp[sc] = g;
+                ++sc;
+            }
+        }
+    }
+}
+
+// unit tables: consecutive c packed while the accumulators fit (<= 56 doubles)
+template <int D>
+struct UnitTable {
+    int n = 0;
+    int c0[MAXD + 1] = {}, c1[MAXD + 1] = {};
+    constexpr UnitTable() {
+        int c = 0;
+        while (c <= D) {
+            int acc = 0, e = c;
+            while (e <= D) {
+                const int add = (e == 0 ? 1 : 4) * (D - e + 1);
+                if (acc > 0 && acc + add > 56) break;
+                acc += add;
+                ++e;
+            }
+            c0[n] = c; c1[n] = e - 1; ++n;
+            c = e;
+        }
+    }
+};
+
+template <int D, int U>
+__device__ __forceinline__ void dispatch_unit(const Fast3Args& A, int unit) {
+    constexpr UnitTable<D> T{};
+    if constexpr (U < T.n) {
+        if (unit == U) unit3b<D, T.c0[U], T.c1[U]>(A);
+        else dispatch_unit<D, U + 1>(A, unit);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(A_THREADS) moments3b_kernel(Fast3Args A) {
+    dispatch_unit<D, 0>(A, blockIdx.y);
+}
+
+template <int D>
+int num_units() {
+    constexpr UnitTable<D> T{};
+    return T.n;
+}
+
+// ---- gather: S -> E / F / V rows ---------------------------------------------
+struct Gather3Args {
+    int64_t p0;               // first pair of the batch
+    int64_t c0;               // first config (chunk-local) of the batch
+    int nb;
+    const double* S;
+    const int16_t* scol2col;  // [nb] scratch column -> local basis column
+    const int64_t* atom_off;
+    const int64_t* site_off;
+    const int32_t* prev;
+    const double* pR;
+    const int64_t* rowE;
+    const int64_t* rowF;
+    const int64_t* rowV;
+    double* Psi;
+    int64_t ld, col0;
+};
+
+constexpr int G_THREADS = 256;
+constexpr int G_WARPS = G_THREADS / 32;
+constexpr int G_ACH = 64;         // atoms per shared-memory tile
+constexpr int G_LDT = 3 * G_ACH + 1;
+
+// CTA = (config, 32 scratch columns); lanes = columns, warps split the atoms.
+__global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
+    extern __shared__ double g_smem[];
+    double* Fs = g_smem;                                            // [32][G_LDT]
+    double (*part)[7][32] = reinterpret_cast<double (*)[7][32]>(g_smem + 32 * G_LDT);   // [G_WARPS][7][32]
+    const int c = (int)(A.c0 + blockIdx.x);
+    const int sc = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = sc < A.nb;
+    const int64_t a0 = A.atom_off[c];
+    const int nat = (int)(A.atom_off[c + 1] - a0);
+    const int64_t rE = A.rowE[c], rF = A.rowF[c], rV = A.rowV[c];
+    const double4* S4 = reinterpret_cast<const double4*>(A.S) + (live ? sc : 0);
+    double e = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
+    for (int ab = 0; ab < nat; ab += G_ACH) {
+        const int na = min(G_ACH, nat - ab);
+        for (int al = warp; al < na; al += G_WARPS) {
+            const int64_t s = a0 + ab + al;
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            const int64_t q0 = A.site_off[s], q1 = A.site_off[s + 1];
+#pragma unroll 4
+            for (int64_t p = q0; p < q1; ++p) {
+                const double4 g = S4[(p - A.p0) * A.nb];
+                const double4 h = S4[((int64_t)A.prev[p] - A.p0) * A.nb];
+                const double r0 = A.pR[3 * p], r1 = A.pR[3 * p + 1], r2 = A.pR[3 * p + 2];
+                f0 += g.x - h.x; f1 += g.y - h.y; f2 += g.z - h.z;
+                e += g.w;
+                v0 -= g.x * r0; v1 -= g.y * r1; v2 -= g.z * r2;      // xx, yy, zz
+                v3 -= g.z * r1; v4 -= g.z * r0; v5 -= g.y * r0;      // zy, zx, yx
+            }
+            Fs[lane * G_LDT + 3 * al] = f0;
+            Fs[lane * G_LDT + 3 * al + 1] = f1;
+            Fs[lane * G_LDT + 3 * al + 2] = f2;
+        }
+        __syncthreads();
+        if (rF) {
+            const int nrow = 3 * na;
+            for (int cl = 0; cl < 32; ++cl) {
+                const int scl = blockIdx.y * 32 + cl;
+                if (scl >= A.nb) break;
+                double* colp = A.Psi + (size_t)(A.col0 + A.scol2col[scl]) * A.ld + (rF - 1) + 3 * ab;
+                for (int r = threadIdx.x; r < nrow; r += G_THREADS) colp[r] = Fs[cl * G_LDT + r];
+            }
+        }
+        __syncthreads();
+    }
+    part[warp][0][lane] = e; part[warp][1][lane] = v0; part[warp][2][lane] = v1; part[warp][3][lane] = v2;
+    part[warp][4][lane] = v3; part[warp][5][lane] = v4; part[warp][6][lane] = v5;
+    __syncthreads();
+    if (warp == 0 && live) {
+        double* colp = A.Psi + (size_t)(A.col0 + A.scol2col[sc]) * A.ld;
+#pragma unroll
+        for (int comp = 0; comp < 7; ++comp) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < G_WARPS; ++w) t += part[w][comp][lane];
+            if (comp == 0) { if (rE) colp[rE - 1] = t; }
+            else if (rV) colp[rV - 1 + comp - 1] = t;
+        }
+    }
+}
+
+template <int D>
+int launch_moments(ipf_ctx* ctx, const Fast3Args& A) {
+    dim3 grid((unsigned)((A.np + A_THREADS - 1) / A_THREADS), (unsigned)num_units<D>());
+    moments3b_kernel<D><<<grid, A_THREADS, 0, ctx->stream>>>(A);
+    return IPF_OK;
+}
+
+}  // namespace
+
+// Returns IPF_OK and sets *handled when the block is the canonical nbpolys(3, desc, D) basis
+// with a supported D; otherwise *handled = false and nothing is done.
+int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                          ipf_matrix* Psi, bool* handled) {
+    *handled = false;
+    if (blk.N != 3 || blk.maxdeg > MAXD) return IPF_OK;
+    // ---- canonical check + column map
+    int D = 0;
+    for (int m = 0; m < blk.nmono; ++m) {
+        const uint8_t* e = &blk.h_mono_exp[(size_t)m * IPF_MAX_VARS];
+        D = std::max(D, (int)e[0] + e[1] + e[2]);
+    }
+    if (D < 2 || D > MAXD) return IPF_OK;
+    std::vector<int16_t> colmap((MAXD + 1) * (MAXD + 1) * (MAXD + 1), -1);
+    int expect = 0;
+    for (int deg = 1; deg <= D; ++deg)
+        for (int a = 0; a <= deg; ++a)
+            for (int b = a; a + b <= deg; ++b) {
+                const int c = deg - a - b;
+                // orbit sorted: (a,b,c) then (b,a,c) when a < b
+                if (expect >= blk.nb) return IPF_OK;
+                const int m0 = blk.h_mono_start[expect], m1 = blk.h_mono_start[expect + 1];
+                const int want = (a == b) ? 1 : 2;
+                if (m1 - m0 != want) return IPF_OK;
+                const uint8_t* e0 = &blk.h_mono_exp[(size_t)m0 * IPF_MAX_VARS];
+                if (e0[0] != a || e0[1] != b || e0[2] != c) return IPF_OK;
+                if (want == 2) {
+                    const uint8_t* e1 = e0 + IPF_MAX_VARS;
+                    if (e1[0] != b || e1[1] != a || e1[2] != c) return IPF_OK;
+                }
+                colmap[cmidx(c, a, b)] = (int16_t)expect;
+                ++expect;
+            }
+    if (expect != blk.nb) return IPF_OK;
+    if (ch.ncfg == 0 || nl.npairs == 0) { *handled = true; return IPF_OK; }
+
+    cudaStream_t st = ctx->stream;
+    const double *rec = nullptr, *xpow = nullptr;
+    IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &xpow));
+    // scratch column order = the order unit3b emits the functions: c ascending, then a, then b
+    std::vector<int16_t> h_s2c;
+    for (int c = 0; c <= D; ++c)
+        for (int a = 0; a <= (D - c) / 2; ++a)
+            for (int b = a; b <= D - c - a; ++b)
+                if (a + b + c > 0) h_s2c.push_back(colmap[cmidx(c, a, b)]);
+    if ((int)h_s2c.size() != blk.nb) return ipf_set_error(ctx, IPF_EINVAL, "internal: 3-body column count mismatch");
+    ABuf<int16_t> s2c;
+    IPF_CHECK(s2c.alloc(ctx, h_s2c.size()));
+    IPF_CUDA(ctx, cudaMemcpyAsync(s2c.p, h_s2c.data(), sizeof(int16_t) * h_s2c.size(), cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_s2c is a local
+
+    // batches of whole configurations; S (32 B per pair and function) lives in HBM
+    const size_t s_budget = (size_t)4 << 30;
+    const int64_t max_pairs_batch = std::max<int64_t>(nl.maxpairs_cfg, (int64_t)(s_budget / (32 * (size_t)blk.nb)));
+    void* Sbuf = nullptr;
+    IPF_CHECK(ipf_scratch(ctx, 3, (size_t)32 * blk.nb * (size_t)std::min<int64_t>(max_pairs_batch, nl.npairs), &Sbuf));
+    if (ctx->profiling && !nl.h_site_off.empty()) {
+        double tot = 0.0;
+        for (int64_t s = 0; s < nl.nsites; ++s) {
+            const double n = (double)(nl.h_site_off[s + 1] - nl.h_site_off[s]);
+            tot += 0.5 * n * (n - 1.0);
+        }
+        ctx->prof["count:clusters_3b"].ms += tot;
+        ctx->prof["count:ordered_pairs_3b"].ms += 2.0 * tot;
+        ctx->prof["count:pairs_3b"].ms += (double)nl.npairs;
+    }
+    int64_t c0 = 0;
+    while (c0 < ch.ncfg) {
+        int64_t c1 = c0 + 1;
+        while (c1 < ch.ncfg && nl.h_cfg_pair_off[c1 + 1] - nl.h_cfg_pair_off[c0] <= max_pairs_batch) ++c1;
+        Fast3Args A;
+        A.p0 = nl.h_cfg_pair_off[c0]; A.np = nl.h_cfg_pair_off[c1] - A.p0; A.npairs = nl.npairs;
+        A.rec = rec; A.xpow = xpow; A.site_off = nl.site_off.p; A.atom_off = ch.atom_off.p;
+        A.psite = nl.psite.p; A.nb = blk.nb; A.S = (double*)Sbuf;
+        if (A.np > 0) {
+            ProfScope prof_(ctx, "site_deriv_3b");
+            switch (D) {
+#define IPF_CASE(DD) case DD: launch_moments<DD>(ctx, A); break;
+                IPF_CASE(2) IPF_CASE(3) IPF_CASE(4) IPF_CASE(5) IPF_CASE(6) IPF_CASE(7) IPF_CASE(8)
+                IPF_CASE(9) IPF_CASE(10) IPF_CASE(11) IPF_CASE(12) IPF_CASE(13) IPF_CASE(14)
+#undef IPF_CASE
+                default: return ipf_set_error(ctx, IPF_EINVAL, "3-body degree %d not instantiated", D);
+            }
+            ctx->launches++;
+        }
+        Gather3Args G;
+        G.p0 = A.p0; G.c0 = c0; G.nb = blk.nb; G.S = (const double*)Sbuf; G.scol2col = s2c.p;
+        G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
+        G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;
+        G.Psi = Psi->d; G.ld = Psi->ld; G.col0 = blk.col0;
+        {
+            ProfScope prof_(ctx, "gather_3b");
+            dim3 grid((unsigned)(c1 - c0), (unsigned)((blk.nb + 31) / 32));
+            constexpr size_t g_bytes = sizeof(double) * (32 * G_LDT + G_WARPS * 7 * 32);
+            static bool attr_set = false;
+            if (!attr_set) {
+                IPF_CUDA(ctx, cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes));
+                attr_set = true;
+            }
+            gather3b_kernel<<<grid, G_THREADS, g_bytes, st>>>(G);
+            ctx->launches++;
+        }
+        c0 = c1;
+    }
+    IPF_CUDA(ctx, cudaGetLastError());
+    *handled = true;
+    return IPF_OK;
+}

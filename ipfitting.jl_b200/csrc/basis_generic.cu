@@ -282,21 +282,32 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
 
 }  // namespace
 
+// pair records (8 doubles) + power table xpow[e][pair] of one descriptor, in ctx scratch slots 1 and 2
+int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec_out, const double** xpow_out) {
+    const int64_t npairs = nl.npairs;
+    void *rec = nullptr, *xpow = nullptr;
+    IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * REC * (size_t)(npairs + 1), &rec));
+    IPF_CHECK(ipf_scratch(ctx, 2, sizeof(double) * (size_t)(blk.maxdeg + 1) * (size_t)(npairs + 1), &xpow));
+    if (npairs > 0) {
+        ProfScope prof_(ctx, "pair_record");
+        pair_record_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, ctx->stream>>>(
+            npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, (double*)rec, (double*)xpow);
+        ctx->launches++;
+    }
+    *rec_out = (const double*)rec;
+    *xpow_out = (const double*)xpow;
+    return IPF_OK;
+}
+
 int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
                                ipf_matrix* Psi) {
     cudaStream_t st = ctx->stream;
     if (ch.ncfg == 0 || blk.nb == 0) return IPF_OK;
     const int64_t npairs = nl.npairs;
     // pair records + power table for this descriptor
-    void *rec = nullptr, *xpow = nullptr, *scr = nullptr, *cpo = nullptr, *cnt = nullptr;
-    IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * REC * (size_t)(npairs + 1), &rec));
-    IPF_CHECK(ipf_scratch(ctx, 2, sizeof(double) * (size_t)(blk.maxdeg + 1) * (size_t)(npairs + 1), &xpow));
-    if (npairs > 0) {
-        ProfScope prof_(ctx, "pair_record");
-        pair_record_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, st>>>(
-            npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, (double*)rec, (double*)xpow);
-        ctx->launches++;
-    }
+    const double *rec = nullptr, *xpow = nullptr;
+    void *scr = nullptr, *cnt = nullptr;
+    IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &xpow));
     // unit size: bounded by the shared-memory monomial table and by 64 functions
     int unit = 64;
     {
@@ -317,17 +328,14 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     const int grid = (int)std::min<int64_t>((int64_t)ch.ncfg * nunits, 2LL * ctx->sm_count);
     const int maxpairs = std::max(1, nl.maxpairs_cfg);
     IPF_CHECK(ipf_scratch(ctx, 3, sizeof(double) * 4 * (size_t)grid * unit * maxpairs, &scr));
-    IPF_CHECK(ipf_scratch(ctx, 4, sizeof(int64_t) * (size_t)(ch.ncfg + 1), &cpo));
     IPF_CHECK(ipf_scratch(ctx, 5, 256, &cnt));
-    IPF_CUDA(ctx, cudaMemcpyAsync(cpo, nl.h_cfg_pair_off.data(), sizeof(int64_t) * (ch.ncfg + 1),
-                                  cudaMemcpyHostToDevice, st));
     IPF_CUDA(ctx, cudaMemsetAsync(cnt, 0, sizeof(int), st));
     GenArgs A;
     A.nb = blk.nb; A.unit = unit; A.nunits = nunits; A.maxpairs = maxpairs;
     A.nitems = (int64_t)ch.ncfg * nunits; A.ncfg = ch.ncfg;
     A.mono_start = blk.mono_start; A.mono_exp = blk.mono_exp;
-    A.atom_off = ch.atom_off.p; A.cfg_pair_off = (const int64_t*)cpo; A.site_off = nl.site_off.p;
-    A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = (const double*)rec; A.xpow = (const double*)xpow;
+    A.atom_off = ch.atom_off.p; A.cfg_pair_off = nl.cfg_pair_off.p; A.site_off = nl.site_off.p;
+    A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = rec; A.xpow = xpow;
     A.npairs = npairs; A.rowE = ch.rowE.p; A.rowF = ch.rowF.p; A.rowV = ch.rowV.p;
     A.Psi = Psi->d; A.ld = Psi->ld; A.col0 = blk.col0; A.scratch = (double*)scr; A.counter = (int*)cnt;
     if (ctx->profiling) {
@@ -357,7 +365,5 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     }
     ctx->launches++;
     IPF_CUDA(ctx, cudaGetLastError());
-    // the host copy of cfg_pair_off must outlive the async copy
-    IPF_CUDA(ctx, cudaStreamSynchronize(st));
     return IPF_OK;
 }

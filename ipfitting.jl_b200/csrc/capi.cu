@@ -34,6 +34,43 @@ int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out) {
     return IPF_OK;
 }
 
+int ipf_arena_alloc(ipf_ctx* ctx, size_t bytes, void** out) {
+    Arena& a = ctx->arena;
+    bytes = (bytes + 255) & ~(size_t)255;
+    a.need += bytes;
+    if (a.off + bytes <= a.cap) {
+        *out = a.base + a.off;
+        a.off += bytes;
+        return IPF_OK;
+    }
+    void* p = nullptr;
+    IPF_CUDA(ctx, cudaMalloc(&p, bytes));
+    a.spill.push_back(p);
+    *out = p;
+    return IPF_OK;
+}
+
+int ipf_arena_reset(ipf_ctx* ctx) {
+    Arena& a = ctx->arena;
+    if (!a.spill.empty() || a.need > a.cap) {
+        IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->stream2) IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
+        for (void* p : a.spill) cudaFree(p);
+        a.spill.clear();
+        if (a.need > a.cap) {
+            if (a.base) cudaFree(a.base);
+            a.base = nullptr;
+            a.cap = 0;
+            const size_t want = a.need + a.need / 8 + (1 << 20);
+            IPF_CUDA(ctx, cudaMalloc((void**)&a.base, want));
+            a.cap = want;
+        }
+    }
+    a.off = 0;
+    a.need = 0;
+    return IPF_OK;
+}
+
 extern "C" {
 
 int32_t ipf_init(int32_t device, ipf_ctx** out) {
@@ -44,6 +81,7 @@ int32_t ipf_init(int32_t device, ipf_ctx** out) {
     ctx->device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         int sm = 0;
         e = cudaDeviceGetAttribute(&sm, cudaDevAttrMultiProcessorCount, device);
@@ -63,10 +101,21 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
     if (!ctx) return IPF_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
     for (int k = 0; k < 8; ++k)
         if (ctx->scratch[k]) cudaFree(ctx->scratch[k]);
+    for (void* p : ctx->arena.spill) cudaFree(p);
+    if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;
+    return IPF_OK;
+}
+
+// 1: always use the table-driven kernels (tests compare the two paths)
+int32_t ipf_set_force_generic(ipf_ctx* ctx, int32_t on) {
+    if (!ctx) return IPF_EINVAL;
+    ctx->force_generic = on != 0;
     return IPF_OK;
 }
 
@@ -264,6 +313,11 @@ static int upload_chunk(ipf_ctx* ctx, int64_t c0, int64_t c1, const int64_t* ato
     IPF_CUDA(ctx, ch.rowE.alloc(ncfg));
     IPF_CUDA(ctx, ch.rowF.alloc(ncfg));
     IPF_CUDA(ctx, ch.rowV.alloc(ncfg));
+    IPF_CUDA(ctx, ch.site_cfg.alloc(natoms));
+    std::vector<int32_t> h_site_cfg((size_t)natoms);
+    for (int64_t c = 0; c < ncfg; ++c)
+        for (int64_t s = ch.h_atom_off[c]; s < ch.h_atom_off[c + 1]; ++s) h_site_cfg[s] = (int32_t)c;
+    if (natoms) IPF_CUDA(ctx, cudaMemcpyAsync(ch.site_cfg.p, h_site_cfg.data(), sizeof(int32_t) * natoms, cudaMemcpyHostToDevice, st));
     IPF_CUDA(ctx, cudaMemcpyAsync(ch.atom_off.p, ch.h_atom_off.data(), sizeof(int64_t) * (ncfg + 1), cudaMemcpyHostToDevice, st));
     if (natoms) IPF_CUDA(ctx, cudaMemcpyAsync(ch.pos.p, pos + 3 * a0, sizeof(double) * 3 * natoms, cudaMemcpyHostToDevice, st));
     IPF_CUDA(ctx, cudaMemcpyAsync(ch.cell.p, cell + 9 * c0, sizeof(double) * 9 * ncfg, cudaMemcpyHostToDevice, st));
@@ -305,6 +359,7 @@ int32_t ipf_neighbours(ipf_ctx* ctx, int32_t nat, const double* pos, const doubl
     ChunkDev ch;
     IPF_CHECK(upload_chunk(ctx, 0, 1, off, pos, cell, pbc, nullptr, nullptr, nullptr, ch));
     NeighList nl;
+    IPF_CHECK(ipf_arena_reset(ctx));
     IPF_CHECK(ipf_build_neighbours(ctx, ch, rcut, nl));
     *n = nl.npairs;
     const int64_t m = std::min<int64_t>(cap, nl.npairs);
@@ -388,10 +443,14 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
             if (std::find(done_rcut.begin(), done_rcut.end(), rc) != done_rcut.end()) continue;
             done_rcut.push_back(rc);
             NeighList nl;
+            IPF_CHECK(ipf_arena_reset(ctx));
             IPF_CHECK(ipf_build_neighbours(ctx, *ch, rc, nl));
             for (size_t k2 = k; k2 < basis->blocks.size(); ++k2)
-                if (basis->blocks[k2].rc2 == rc)
-                    IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
+                if (basis->blocks[k2].rc2 == rc) {
+                    bool handled = false;
+                    if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_3b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
+                    if (!handled) IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
+                }
         }
     }
     IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

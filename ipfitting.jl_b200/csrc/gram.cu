@@ -130,7 +130,9 @@ __global__ void gram_reduce_kernel(const double* __restrict__ part, int ntiles, 
                                    const int2* __restrict__ tiles, double* __restrict__ G, int n1) {
     const int tile = blockIdx.x;
     const int ti = tiles[tile].x, tj = tiles[tile].y;
-    for (int e = threadIdx.x; e < BT * BT; e += blockDim.x) {
+    // blockIdx.y selects a band of BT / gridDim.y rows of the tile
+    const int band = BT * BT / gridDim.y;
+    for (int e = blockIdx.y * band + threadIdx.x; e < (blockIdx.y + 1) * band; e += blockDim.x) {
         const int i = e / BT, j = e % BT;
         const int gi = ti * BT + i, gj = tj * BT + j;
         if (gi >= n1 || gj >= n1) continue;
@@ -186,7 +188,7 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
                                                                       (const int2*)d_tiles, (double*)part);
     }
     if (kernel_ms) IPF_CUDA(ctx, cudaEventRecord(e1, st));
-    gram_reduce_kernel<<<T, 256, 0, st>>>((const double*)part, T, nchunk, (const int2*)d_tiles, G, n1);
+    gram_reduce_kernel<<<dim3(T, 32), 256, 0, st>>>((const double*)part, T, nchunk, (const int2*)d_tiles, G, n1);
     ctx->launches += 2;
     IPF_CUDA(ctx, cudaGetLastError());
     IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_tiles must outlive the copy

@@ -17,8 +17,18 @@ struct ProfEntry {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+// bump allocator for per-chunk device temporaries: no cudaMalloc/cudaFree in steady state
+struct Arena {
+    char* base = nullptr;
+    size_t cap = 0, off = 0, need = 0;
+    std::vector<void*> spill;       // overflow allocations of the current cycle
+};
+
 struct ipf_ctx {
+    Arena arena;
+    cudaStream_t stream2 = nullptr;     // second stream: gather of batch n overlaps the moments of batch n+1
     bool profiling = false;
+    bool force_generic = false;
     std::map<std::string, ProfEntry> prof;
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -88,6 +98,20 @@ struct ProfScope {
 
 // grow-only scratch slot
 int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out);
+// arena: alloc is stream-ordered-safe on ctx->stream; reset recycles everything handed out so far
+int ipf_arena_alloc(ipf_ctx* ctx, size_t bytes, void** out);
+int ipf_arena_reset(ipf_ctx* ctx);
+
+template <class T>
+struct ABuf {          // arena-backed array (never freed individually)
+    T* p = nullptr;
+    int alloc(ipf_ctx* ctx, size_t count) {
+        void* q = nullptr;
+        int rc = ipf_arena_alloc(ctx, sizeof(T) * (count ? count : 1), &q);
+        p = (T*)q;
+        return rc;
+    }
+};
 
 template <class T>
 struct DevBuf {
@@ -104,20 +128,22 @@ struct DevBuf {
     }
 };
 
-// ---- neighbour list of a chunk of configurations (device resident) -------
+// ---- neighbour list of a chunk of configurations (device resident, arena backed) -------
 struct NeighList {
     int64_t nsites = 0;       // atoms in the chunk
     int64_t npairs = 0;
     int32_t maxpairs_cfg = 0; // max pairs of one config
     double rcut = 0;
-    DevBuf<int64_t> site_off;     // [nsites+1] pair offsets (chunk-global)
-    DevBuf<int32_t> pi;           // [npairs] centre atom, local index in its config
-    DevBuf<int32_t> pj;           // [npairs] neighbour atom, local index in its config
-    DevBuf<int32_t> pS;           // [npairs*3] image shift
-    DevBuf<double> pR;            // [npairs*3] bond vector R_ij = X_j + S C - X_i
-    DevBuf<int32_t> prev;         // [npairs] chunk-global index of the reverse pair (j,i,-S)
-    std::vector<int64_t> h_cfg_pair_off;   // [ncfg+1] host copy of per-config pair offsets
-    std::vector<int64_t> h_site_off;       // [nsites+1] host copy of site_off
+    ABuf<int64_t> site_off;       // [nsites+1] pair offsets (chunk-global)
+    ABuf<int32_t> pi;             // [npairs] centre atom, local index in its config
+    ABuf<int32_t> pj;             // [npairs] neighbour atom, local index in its config
+    ABuf<int32_t> psite;          // [npairs] centre atom, chunk-global site index
+    ABuf<int32_t> pS;             // [npairs*3] image shift
+    ABuf<double> pR;              // [npairs*3] bond vector R_ij = X_j + S C - X_i
+    ABuf<int32_t> prev;           // [npairs] chunk-global index of the reverse pair (j,i,-S)
+    ABuf<int64_t> cfg_pair_off;   // [ncfg+1] device copy of the per-config pair offsets
+    std::vector<int64_t> h_cfg_pair_off;   // [ncfg+1] host copy
+    std::vector<int64_t> h_site_off;       // [nsites+1] host copy (only filled while profiling)
 };
 
 // Config chunk resident on the device
@@ -128,12 +154,15 @@ struct ChunkDev {
     DevBuf<double> cell;        // [9*ncfg]
     DevBuf<uint8_t> pbc;        // [3*ncfg]
     DevBuf<int64_t> rowE, rowF, rowV;   // [ncfg] 1-based, 0 = absent
+    DevBuf<int32_t> site_cfg;           // [natoms] config of every atom
     std::vector<int64_t> h_atom_off;
 };
 
 int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighList& nl);
 int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
                                const NeighList& nl, ipf_matrix* Psi);
+int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                          ipf_matrix* Psi, bool* handled);
 
 // ---- device helpers ---------------------------------------------------------
 __device__ __forceinline__ double warp_sum(double v) {

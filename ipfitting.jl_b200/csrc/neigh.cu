@@ -167,12 +167,19 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
     if (!FILL) counts[s] = n;
 }
 
+__global__ void cfg_offsets_kernel(int64_t ncfg, const int64_t* __restrict__ atom_off,
+                                   const int64_t* __restrict__ site_off, int64_t* __restrict__ out) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c <= ncfg) out[c] = site_off[atom_off[c]];
+}
+
 // thread per pair: rank within the site by key -> canonical order
 __global__ void nl_sort_kernel(int64_t npairs, int64_t nsites, const int64_t* __restrict__ site_off,
                                const int32_t* __restrict__ site_cfg, const int64_t* __restrict__ atom_off,
                                const unsigned long long* __restrict__ keys, const double* __restrict__ Rtmp,
-                               int32_t* __restrict__ pi, int32_t* __restrict__ pj, int32_t* __restrict__ pS,
-                               double* __restrict__ pR, unsigned long long* __restrict__ keys_sorted) {
+                               int32_t* __restrict__ pi, int32_t* __restrict__ pj, int32_t* __restrict__ psite,
+                               int32_t* __restrict__ pS, double* __restrict__ pR,
+                               unsigned long long* __restrict__ keys_sorted) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     // site of pair p: binary search in site_off
@@ -186,6 +193,7 @@ __global__ void nl_sort_kernel(int64_t npairs, int64_t nsites, const int64_t* __
     keys_sorted[dst] = k;
     pi[dst] = (int32_t)(s - atom_off[site_cfg[s]]);
     pj[dst] = (int32_t)(k >> 32);
+    psite[dst] = (int32_t)s;
     pS[3 * dst] = (int)((k >> 20) & 1023) - SHIFT_BIAS;
     pS[3 * dst + 1] = (int)((k >> 10) & 1023) - SHIFT_BIAS;
     pS[3 * dst + 2] = (int)(k & 1023) - SHIFT_BIAS;
@@ -230,79 +238,79 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     nl.npairs = 0;
     nl.maxpairs_cfg = 0;
     nl.h_cfg_pair_off.assign(ncfg + 1, 0);
+    nl.h_site_off.clear();
+    cudaStream_t st = ctx->stream;
+    IPF_CHECK(nl.site_off.alloc(ctx, nsites + 1));
+    IPF_CHECK(nl.cfg_pair_off.alloc(ctx, ncfg + 1));
     if (nsites == 0) {
-        IPF_CUDA(ctx, nl.site_off.alloc(1));
-        IPF_CUDA(ctx, cudaMemsetAsync(nl.site_off.p, 0, sizeof(int64_t), ctx->stream));
+        IPF_CUDA(ctx, cudaMemsetAsync(nl.site_off.p, 0, sizeof(int64_t), st));
+        IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p, 0, sizeof(int64_t) * (ncfg + 1), st));
         return IPF_OK;
     }
-    cudaStream_t st = ctx->stream;
     ProfScope prof_(ctx, "neighbour_list");
-    // site -> config map
-    std::vector<int32_t> h_site_cfg(nsites);
-    for (int64_t c = 0; c < ncfg; ++c)
-        for (int64_t s = ch.h_atom_off[c]; s < ch.h_atom_off[c + 1]; ++s) h_site_cfg[s] = (int32_t)c;
-    DevBuf<int32_t> site_cfg, cell_start, cell_atoms, atom_cell, atom_wrap;
-    DevBuf<GridInfo> grid;
-    DevBuf<int64_t> counts;
-    IPF_CUDA(ctx, site_cfg.alloc(nsites));
-    IPF_CUDA(ctx, cell_start.alloc((size_t)ncfg * (NCELL_MAX + 1)));
-    IPF_CUDA(ctx, cell_atoms.alloc(nsites));
-    IPF_CUDA(ctx, atom_cell.alloc(nsites));
-    IPF_CUDA(ctx, atom_wrap.alloc(3 * nsites));
-    IPF_CUDA(ctx, grid.alloc(ncfg));
-    IPF_CUDA(ctx, counts.alloc(nsites + 1));
-    IPF_CUDA(ctx, nl.site_off.alloc(nsites + 1));
-    IPF_CUDA(ctx, cudaMemcpyAsync(site_cfg.p, h_site_cfg.data(), sizeof(int32_t) * nsites,
-                                  cudaMemcpyHostToDevice, st));
+    ABuf<int32_t> cell_start, cell_atoms, atom_cell, atom_wrap;
+    ABuf<GridInfo> grid;
+    ABuf<int64_t> counts;
+    IPF_CHECK(cell_start.alloc(ctx, (size_t)ncfg * (NCELL_MAX + 1)));
+    IPF_CHECK(cell_atoms.alloc(ctx, nsites));
+    IPF_CHECK(atom_cell.alloc(ctx, nsites));
+    IPF_CHECK(atom_wrap.alloc(ctx, 3 * nsites));
+    IPF_CHECK(grid.alloc(ctx, ncfg));
+    IPF_CHECK(counts.alloc(ctx, nsites + 1));
+    const int32_t* site_cfg = ch.site_cfg.p;
     nl_bin_kernel<<<(unsigned)ncfg, 128, 0, st>>>(ch.atom_off.p, ch.pos.p, ch.cell.p, ch.pbc.p, rcut,
                                                   grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p);
     ctx->launches++;
     const double rc2 = rcut * rcut;
     const unsigned nb_sites = (unsigned)((nsites + 127) / 128);
     IPF_CUDA(ctx, cudaMemsetAsync(counts.p + nsites, 0, sizeof(int64_t), st));
-    nl_pairs_kernel<false><<<nb_sites, 128, 0, st>>>(nsites, site_cfg.p, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
+    nl_pairs_kernel<false><<<nb_sites, 128, 0, st>>>(nsites, site_cfg, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
                                                      grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
                                                      counts.p, nullptr, nullptr, nullptr);
     ctx->launches++;
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st);
     void* tmp = nullptr;
-    IPF_CHECK(ipf_scratch(ctx, 0, tmp_bytes, &tmp));
+    IPF_CHECK(ipf_arena_alloc(ctx, tmp_bytes, &tmp));
     IPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st));
     ctx->launches++;
-    // per-config pair offsets to the host (also gives the total)
-    std::vector<int64_t>& h_site_off = nl.h_site_off;
-    h_site_off.assign(nsites + 1, 0);
-    IPF_CUDA(ctx, cudaMemcpyAsync(h_site_off.data(), nl.site_off.p, sizeof(int64_t) * (nsites + 1),
+    // per-config pair offsets (ncfg+1 values) to the host; gives the total too
+    cfg_offsets_kernel<<<(unsigned)((ncfg + 256) / 256), 256, 0, st>>>(ncfg, ch.atom_off.p, nl.site_off.p, nl.cfg_pair_off.p);
+    ctx->launches++;
+    IPF_CUDA(ctx, cudaMemcpyAsync(nl.h_cfg_pair_off.data(), nl.cfg_pair_off.p, sizeof(int64_t) * (ncfg + 1),
                                   cudaMemcpyDeviceToHost, st));
+    if (ctx->profiling) {
+        nl.h_site_off.assign(nsites + 1, 0);
+        IPF_CUDA(ctx, cudaMemcpyAsync(nl.h_site_off.data(), nl.site_off.p, sizeof(int64_t) * (nsites + 1),
+                                      cudaMemcpyDeviceToHost, st));
+    }
     IPF_CUDA(ctx, cudaStreamSynchronize(st));
-    const int64_t npairs = h_site_off[nsites];
+    const int64_t npairs = nl.h_cfg_pair_off[ncfg];
     nl.npairs = npairs;
-    for (int64_t c = 0; c <= ncfg; ++c) nl.h_cfg_pair_off[c] = h_site_off[ch.h_atom_off[c]];
     int64_t mx = 0;
     for (int64_t c = 0; c < ncfg; ++c) mx = std::max<int64_t>(mx, nl.h_cfg_pair_off[c + 1] - nl.h_cfg_pair_off[c]);
     nl.maxpairs_cfg = (int32_t)mx;
-    IPF_CUDA(ctx, nl.pi.alloc(npairs));
-    IPF_CUDA(ctx, nl.pj.alloc(npairs));
-    IPF_CUDA(ctx, nl.pS.alloc(3 * npairs));
-    IPF_CUDA(ctx, nl.pR.alloc(3 * npairs));
-    IPF_CUDA(ctx, nl.prev.alloc(npairs));
+    IPF_CHECK(nl.pi.alloc(ctx, npairs));
+    IPF_CHECK(nl.pj.alloc(ctx, npairs));
+    IPF_CHECK(nl.psite.alloc(ctx, npairs));
+    IPF_CHECK(nl.pS.alloc(ctx, 3 * npairs));
+    IPF_CHECK(nl.pR.alloc(ctx, 3 * npairs));
+    IPF_CHECK(nl.prev.alloc(ctx, npairs));
     if (npairs == 0) return IPF_OK;
-    DevBuf<unsigned long long> keys, keys_sorted;
-    DevBuf<double> Rtmp;
-    IPF_CUDA(ctx, keys.alloc(npairs));
-    IPF_CUDA(ctx, keys_sorted.alloc(npairs));
-    IPF_CUDA(ctx, Rtmp.alloc(3 * npairs));
-    nl_pairs_kernel<true><<<nb_sites, 128, 0, st>>>(nsites, site_cfg.p, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
+    ABuf<unsigned long long> keys, keys_sorted;
+    ABuf<double> Rtmp;
+    IPF_CHECK(keys.alloc(ctx, npairs));
+    IPF_CHECK(keys_sorted.alloc(ctx, npairs));
+    IPF_CHECK(Rtmp.alloc(ctx, 3 * npairs));
+    nl_pairs_kernel<true><<<nb_sites, 128, 0, st>>>(nsites, site_cfg, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
                                                     grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
                                                     nullptr, nl.site_off.p, keys.p, Rtmp.p);
     const unsigned nb_pairs = (unsigned)((npairs + 255) / 256);
-    nl_sort_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nsites, nl.site_off.p, site_cfg.p, ch.atom_off.p, keys.p,
-                                             Rtmp.p, nl.pi.p, nl.pj.p, nl.pS.p, nl.pR.p, keys_sorted.p);
-    nl_reverse_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nl.site_off.p, site_cfg.p, ch.atom_off.p, nsites,
+    nl_sort_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nsites, nl.site_off.p, site_cfg, ch.atom_off.p, keys.p,
+                                             Rtmp.p, nl.pi.p, nl.pj.p, nl.psite.p, nl.pS.p, nl.pR.p, keys_sorted.p);
+    nl_reverse_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nl.site_off.p, site_cfg, ch.atom_off.p, nsites,
                                                 nl.pi.p, nl.pj.p, nl.pS.p, keys_sorted.p, nl.prev.p);
     ctx->launches += 3;
     IPF_CUDA(ctx, cudaGetLastError());
-    IPF_CUDA(ctx, cudaStreamSynchronize(st));   // temporaries are freed on return
     return IPF_OK;
 }

@@ -72,3 +72,38 @@ def test_empty(ctx):
     B = ipf.nbpolys(2, si_desc(), 3)
     db = LsqDB("", B, [], ctx=ctx)
     assert db.Psi.shape == (0, 3)
+
+
+@pytest.mark.parametrize("D", [2, 3, 5, 8, 11, 14])
+def test_3b_specialised_path(ctx, D):
+    """Canonical nbpolys(3, desc, D) goes through the moment-factorised kernels (basis_3b.cu)."""
+    configs = (synth.rattled_configs("Si", 1, 2, seed=30 + D, calc=synth.StillingerWeber())
+               + synth.rattled_configs("Si", 2, 1, seed=40 + D, calc=synth.StillingerWeber()))
+    B = ipf.nbpolys(3, si_desc(2.5 if D <= 11 else 2.0), D)
+    ctx.profile(True); ctx.profile_reset()
+    _check(B, configs, ctx)
+    assert ctx.profile_get("gather_3b")[1] > 0, "specialised 3-body path was not taken"
+    ctx.profile(False)
+
+
+def test_3b_specialised_equals_table_driven(ctx):
+    configs = synth.rattled_configs("Si", 2, 3, seed=50, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(2, si_desc(), 4) + ipf.nbpolys(3, si_desc(), 7)
+    fast = LsqDB("", B, configs, ctx=ctx).Psi
+    ctx.force_generic(True)
+    try:
+        slow = LsqDB("", B, configs, ctx=ctx).Psi
+    finally:
+        ctx.force_generic(False)
+    scale = np.abs(slow).max(axis=0)
+    assert (np.abs(fast - slow).max(axis=0) <= 1e-12 * scale).all()
+
+
+def test_non_canonical_3b_uses_table_driven_path(ctx):
+    """A subset / reordering of the 3-body functions is not the canonical basis: generic kernels."""
+    configs = synth.rattled_configs("Si", 1, 2, seed=51, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(3, si_desc(2.0), 5)[::2]
+    ctx.profile(True); ctx.profile_reset()
+    _check(B, configs, ctx)
+    assert ctx.profile_get("gather_3b")[1] == 0
+    ctx.profile(False)
