@@ -19,7 +19,7 @@
 // (pair, 32 columns), own and reverse pair alike.
 #include "ipf_common.cuh"
 
-int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec, const double** xpow);
+int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec, int* rs);
 
 namespace {
 
@@ -29,9 +29,7 @@ constexpr int MAXD = 14;
 
 struct Fast3Args {
     int64_t p0, np;                // batch pair range [p0, p0 + np)
-    int64_t npairs;                // pairs in the chunk (stride of the xpow table)
-    const double* rec;
-    const double* xpow;
+    const double* rec;             // pair records, stride RS<D> doubles: head (8) + x^0..x^D
     const int64_t* site_off;
     const int64_t* atom_off;
     const int32_t* psite;          // chunk-global site of every pair
@@ -70,34 +68,38 @@ __device__ __forceinline__ double ipow_c(double w) {
     }
 }
 
-// one unit = exponents c in [C0, C1] of w
-template <int D, int C0, int C1>
-__device__ __forceinline__ void unit3b(const Fast3Args& A) {
-    const int64_t pl = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pl >= A.np) return;
-    const int64_t p = A.p0 + pl;
-    constexpr int NC = C1 - C0 + 1;
-    constexpr int EMAX = D - C0;            // largest x-exponent in this unit
-    double Z[NC][EMAX + 1];
-    double U[NC][EMAX + 1][3];
-#pragma unroll
-    for (int ci = 0; ci < NC; ++ci)
-#pragma unroll
-        for (int e = 0; e <= EMAX; ++e) { Z[ci][e] = 0.0; U[ci][e][0] = U[ci][e][1] = U[ci][e][2] = 0.0; }
+template <int D>
+struct RecStride { static constexpr int value = (REC + D + 2) & ~1; };
 
-    const double4 o0v = ld4(A.rec + REC * p);
-    const double4 o1v = ld4(A.rec + REC * p + 4);
-    const double Rj0 = o0v.x, Rj1 = o0v.y, Rj2 = o0v.z, rinvj = o0v.w;
-    const double dxj = o1v.y, fcj = o1v.z, dfcj = o1v.w;
-    const int64_t s = A.psite[p];
-    const int64_t k0 = A.site_off[s], k1 = A.site_off[s + 1];
+constexpr int A_MAXREC = 288;              // pair records staged in shared memory per CTA
+constexpr int A_OUTG = 8;                  // functions per staged output group
+constexpr int A_OUTLD = 4 * A_OUTG + 2;    // doubles per staged row (+2: conflict-free 16-byte columns)
 
-    for (int64_t k = k0; k < k1; ++k) {
-        if (k == p) continue;
-        const double4 a0 = ld4(A.rec + REC * k);
-        const double4 a1 = ld4(A.rec + REC * k + 4);
-        const double w = Rj0 * a0.x + Rj1 * a0.y + Rj2 * a0.z;
-        const double fck = a1.z;
+template <int D>
+__host__ __device__ constexpr size_t moments_smem_bytes() {
+    constexpr size_t a = sizeof(double) * (size_t)A_MAXREC * RecStride<D>::value;
+    constexpr size_t b = sizeof(double) * (size_t)A_THREADS * A_OUTLD;
+    return a > b ? a : b;
+}
+
+// moment accumulation over the neighbours of the thread's centre atom; RK points at the record of
+// the first neighbour (shared or global memory: the caller instantiates one copy per address space)
+template <int D, int C0, int C1, int NC, int EMAX>
+__device__ __forceinline__ void moment_loop(const double* __restrict__ rk, int n, int jself, double Rj0, double Rj1,
+                                            double Rj2, double (&Z)[NC][EMAX + 1], double (&U)[NC][EMAX + 1][3]) {
+    constexpr int RS = RecStride<D>::value;
+    for (int kk = 0; kk < n; ++kk, rk += RS) {
+        const double2 r01 = *reinterpret_cast<const double2*>(rk);
+        const double2 r23 = *reinterpret_cast<const double2*>(rk + 2);
+        const double2 a1 = *reinterpret_cast<const double2*>(rk + 6);      // fc, dfc
+        double xe[EMAX + 2];
+#pragma unroll
+        for (int e = 0; e <= EMAX; e += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(rk + REC + e);
+            xe[e] = v.x; xe[e + 1] = v.y;
+        }
+        const double w = Rj0 * r01.x + Rj1 * r01.y + Rj2 * r23.x;
+        const double fck = (kk == jself) ? 0.0 : a1.x;      // the own leg is not its own partner
         // wl[ci] = fck w^(c-1), c = C0 + ci  (unused for c = 0)
         double wl[NC];
         if constexpr (C0 >= 1) {
@@ -114,38 +116,108 @@ __device__ __forceinline__ void unit3b(const Fast3Args& A) {
         }
 #pragma unroll
         for (int e = 0; e <= EMAX; ++e) {
-            const double xe = __ldg(A.xpow + (int64_t)e * A.npairs + k);
 #pragma unroll
             for (int ci = 0; ci < NC; ++ci) {
                 const int c = C0 + ci;
                 if (e <= D - c) {
                     if (c == 0) {
-                        Z[ci][e] = fma(xe, fck, Z[ci][e]);
+                        Z[ci][e] = fma(xe[e], fck, Z[ci][e]);
                     } else {
-                        const double t = xe * wl[ci];          // fck x^e w^(c-1)
-                        U[ci][e][0] = fma(t, a0.x, U[ci][e][0]);
-                        U[ci][e][1] = fma(t, a0.y, U[ci][e][1]);
-                        U[ci][e][2] = fma(t, a0.z, U[ci][e][2]);
+                        const double t = xe[e] * wl[ci];          // fck x^e w^(c-1)
+                        U[ci][e][0] = fma(t, r01.x, U[ci][e][0]);
+                        U[ci][e][1] = fma(t, r01.y, U[ci][e][1]);
+                        U[ci][e][2] = fma(t, r23.x, U[ci][e][2]);
                         Z[ci][e] = fma(t, w, Z[ci][e]);
                     }
                 }
             }
         }
     }
-    // ---- combine into basis functions
+}
+
+// coalesced write-out of NG staged functions of all rows of the CTA: S[(pl0+row)*nb + sc0 .. +NG)
+template <int NG>
+__device__ __forceinline__ void flush_group(double* __restrict__ S, const double* __restrict__ stage, int64_t pl0,
+                                            int nrow, int nb, int sc0) {
+    __syncthreads();
+    double2* S2 = reinterpret_cast<double2*>(S);
+    const double2* st2 = reinterpret_cast<const double2*>(stage);
+    for (int q = threadIdx.x; q < nrow * 2 * NG; q += A_THREADS) {
+        const int row = q / (2 * NG), c = q - row * (2 * NG);
+        S2[((pl0 + row) * nb + sc0) * 2 + c] = st2[row * (A_OUTLD / 2) + c];
+    }
+    __syncthreads();
+}
+
+// one unit = exponents c in [C0, C1] of w; one kernel per unit (own register budget)
+template <int D, int C0, int C1>
+__global__ void __launch_bounds__(A_THREADS) moments3b_unit_kernel(Fast3Args A) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int64_t s_kbeg;
+    __shared__ int s_nrec;
+    constexpr int RS = RecStride<D>::value;
+    constexpr int NC = C1 - C0 + 1;
+    constexpr int EMAX = D - C0;            // largest x-exponent in this unit
+    const int tid = threadIdx.x;
+    const int64_t pl0 = (int64_t)blockIdx.x * A_THREADS;
+    const int64_t pl = pl0 + tid;
+    const bool live = pl < A.np;
+    const int nrow = (int)min((int64_t)A_THREADS, A.np - pl0);
+    const int64_t p = A.p0 + (live ? pl : pl0);
+    if (tid == 0) {
+        const int64_t kb = A.site_off[A.psite[A.p0 + pl0]];
+        const int64_t ke = A.site_off[A.psite[A.p0 + pl0 + nrow - 1] + 1];
+        s_kbeg = kb;
+        s_nrec = (int)min((int64_t)(A_MAXREC + 1), ke - kb);
+    }
+    __syncthreads();
+    const int64_t kbeg = s_kbeg;
+    const bool staged = s_nrec <= A_MAXREC;
+    if (staged) {
+        const double2* src = reinterpret_cast<const double2*>(A.rec + kbeg * RS);
+        double2* dst = reinterpret_cast<double2*>(sm);
+        const int n2 = s_nrec * (RS / 2);
+        for (int i = tid; i < n2; i += A_THREADS) dst[i] = __ldg(src + i);
+    }
+    double Z[NC][EMAX + 1];
+    double U[NC][EMAX + 1][3];
+#pragma unroll
+    for (int ci = 0; ci < NC; ++ci)
+#pragma unroll
+        for (int e = 0; e <= EMAX; ++e) { Z[ci][e] = 0.0; U[ci][e][0] = U[ci][e][1] = U[ci][e][2] = 0.0; }
+
+    const double* recp = A.rec + (int64_t)RS * p;
+    const double4 o0v = ld4(recp);
+    const double4 o1v = ld4(recp + 4);
+    const double Rj0 = o0v.x, Rj1 = o0v.y, Rj2 = o0v.z, rinvj = o0v.w;
+    const double dxj = o1v.y, fcj = o1v.z, dfcj = o1v.w;
+    const int64_t s = A.psite[p];
+    const int64_t k0 = A.site_off[s];
+    const int n = live ? (int)(A.site_off[s + 1] - k0) : 0;
+    const int jself = (int)(p - k0);
+    __syncthreads();
+    if (staged) moment_loop<D, C0, C1, NC, EMAX>(sm + (k0 - kbeg) * RS, n, jself, Rj0, Rj1, Rj2, Z, U);
+    else moment_loop<D, C0, C1, NC, EMAX>(A.rec + k0 * RS, n, jself, Rj0, Rj1, Rj2, Z, U);
+
+    // ---- combine into basis functions, staged through shared memory in groups of A_OUTG
     double X[EMAX + 1], dX[EMAX + 1];
 #pragma unroll
-    for (int e = 0; e <= EMAX; ++e) X[e] = __ldg(A.xpow + (int64_t)e * A.npairs + p);
+    for (int e = 0; e <= EMAX; ++e) X[e] = __ldg(recp + REC + e);
     dX[0] = 0.0;
 #pragma unroll
     for (int e = 1; e <= EMAX; ++e) dX[e] = (double)e * X[e - 1];
     const double tang = fcj * rinvj;
     const double fdx = fcj * dxj;
-    double4* Sp = reinterpret_cast<double4*>(A.S) + pl * A.nb;
-    int sc = scol_base(D, C0);
+    __syncthreads();                         // records are dead: the staging area reuses their memory
+    double* myrow = sm + tid * A_OUTLD;
+    constexpr int SC0 = scol_base(D, C0);
+    constexpr int NF = scol_base(D, C1 + 1) - SC0;
+    int f = 0;
 #pragma unroll
     for (int ci = 0; ci < NC; ++ci) {
         const int c = C0 + ci;
+        const double cc = (double)c;
+        const double tc = tang * cc;
 #pragma unroll
         for (int a = 0; a <= (D - c) / 2; ++a) {
 #pragma unroll
@@ -163,22 +235,20 @@ __device__ __forceinline__ void unit3b(const Fast3Args& A) {
                     T1 = fma(X[a], U[ci][b][1], X[b] * U[ci][a][1]);
                     T2 = fma(X[a], U[ci][b][2], X[b] * U[ci][a][2]);
                 }
-                const double cc = (double)c;
-                const double radial = fma(dfcj, S0, fdx * S1) - tang * cc * S0;   // coefficient of Rhat_j
-                const double tc = tang * cc;
-                double4 g;
-                g.x = fma(radial, Rj0, tc * T0);
-                g.y = fma(radial, Rj1, tc * T1);
-                g.z = fma(radial, Rj2, tc * T2);
-                g.w = 0.5 * fcj * S0;
-                Sp[sc] = g;
-                ++sc;
+                const double radial = fma(dfcj - tc, S0, fdx * S1);      // coefficient of Rhat_j
+                const int slot = f % A_OUTG;
+                *reinterpret_cast<double2*>(myrow + 4 * slot) = make_double2(fma(radial, Rj0, tc * T0), fma(radial, Rj1, tc * T1));
+                *reinterpret_cast<double2*>(myrow + 4 * slot + 2) = make_double2(fma(radial, Rj2, tc * T2), 0.5 * fcj * S0);
+                ++f;
+                if (f % A_OUTG == 0) flush_group<A_OUTG>(A.S, sm, pl0, nrow, A.nb, SC0 + f - A_OUTG);
             }
         }
     }
+    constexpr int REM = NF % A_OUTG;
+    if constexpr (REM > 0) flush_group<REM>(A.S, sm, pl0, nrow, A.nb, SC0 + NF - REM);
 }
 
-// unit tables: consecutive c packed while the accumulators fit (<= 56 doubles)
+// unit tables: consecutive c packed while the accumulators fit (<= 44 doubles)
 template <int D>
 struct UnitTable {
     int n = 0;
@@ -189,7 +259,7 @@ struct UnitTable {
             int acc = 0, e = c;
             while (e <= D) {
                 const int add = (e == 0 ? 1 : 4) * (D - e + 1);
-                if (acc > 0 && acc + add > 56) break;
+                if (acc > 0 && acc + add > 44) break;
                 acc += add;
                 ++e;
             }
@@ -200,23 +270,21 @@ struct UnitTable {
 };
 
 template <int D, int U>
-__device__ __forceinline__ void dispatch_unit(const Fast3Args& A, int unit) {
+void launch_units(ipf_ctx* ctx, const Fast3Args& A) {
     constexpr UnitTable<D> T{};
     if constexpr (U < T.n) {
-        if (unit == U) unit3b<D, T.c0[U], T.c1[U]>(A);
-        else dispatch_unit<D, U + 1>(A, unit);
+        const unsigned grid = (unsigned)((A.np + A_THREADS - 1) / A_THREADS);
+        auto kern = moments3b_unit_kernel<D, T.c0[U], T.c1[U]>;
+        constexpr size_t smem = moments_smem_bytes<D>();
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        kern<<<grid, A_THREADS, smem, ctx->stream>>>(A);
+        ctx->launches++;
+        launch_units<D, U + 1>(ctx, A);
     }
-}
-
-template <int D>
-__global__ void __launch_bounds__(A_THREADS) moments3b_kernel(Fast3Args A) {
-    dispatch_unit<D, 0>(A, blockIdx.y);
-}
-
-template <int D>
-int num_units() {
-    constexpr UnitTable<D> T{};
-    return T.n;
 }
 
 // ---- gather: S -> E / F / V rows ---------------------------------------------
@@ -304,13 +372,6 @@ __global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
     }
 }
 
-template <int D>
-int launch_moments(ipf_ctx* ctx, const Fast3Args& A) {
-    dim3 grid((unsigned)((A.np + A_THREADS - 1) / A_THREADS), (unsigned)num_units<D>());
-    moments3b_kernel<D><<<grid, A_THREADS, 0, ctx->stream>>>(A);
-    return IPF_OK;
-}
-
 }  // namespace
 
 // Returns IPF_OK and sets *handled when the block is the canonical nbpolys(3, desc, D) basis
@@ -350,8 +411,9 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     if (ch.ncfg == 0 || nl.npairs == 0) { *handled = true; return IPF_OK; }
 
     cudaStream_t st = ctx->stream;
-    const double *rec = nullptr, *xpow = nullptr;
-    IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &xpow));
+    const double* rec = nullptr;
+    int rs = 0;
+    IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &rs));
     // scratch column order = the order unit3b emits the functions: c ascending, then a, then b
     std::vector<int16_t> h_s2c;
     for (int c = 0; c <= D; ++c)
@@ -364,11 +426,14 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     IPF_CUDA(ctx, cudaMemcpyAsync(s2c.p, h_s2c.data(), sizeof(int16_t) * h_s2c.size(), cudaMemcpyHostToDevice, st));
     IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_s2c is a local
 
-    // batches of whole configurations; S (32 B per pair and function) lives in HBM
-    const size_t s_budget = (size_t)4 << 30;
+    // batches of whole configurations; S (32 B per pair and function) lives in HBM, double buffered:
+    // the gather of batch i (HBM bound, stream2) overlaps the moments of batch i+1 (FP64 bound, stream)
+    const size_t s_budget = (size_t)3 << 30;
     const int64_t max_pairs_batch = std::max<int64_t>(nl.maxpairs_cfg, (int64_t)(s_budget / (32 * (size_t)blk.nb)));
-    void* Sbuf = nullptr;
-    IPF_CHECK(ipf_scratch(ctx, 3, (size_t)32 * blk.nb * (size_t)std::min<int64_t>(max_pairs_batch, nl.npairs), &Sbuf));
+    const size_t s_bytes = (size_t)32 * blk.nb * (size_t)std::min<int64_t>(max_pairs_batch, nl.npairs);
+    void* Sbuf[2] = {nullptr, nullptr};
+    IPF_CHECK(ipf_scratch(ctx, 3, s_bytes, &Sbuf[0]));
+    IPF_CHECK(ipf_scratch(ctx, 4, s_bytes, &Sbuf[1]));
     if (ctx->profiling && !nl.h_site_off.empty()) {
         double tot = 0.0;
         for (int64_t s = 0; s < nl.nsites; ++s) {
@@ -379,44 +444,67 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         ctx->prof["count:ordered_pairs_3b"].ms += 2.0 * tot;
         ctx->prof["count:pairs_3b"].ms += (double)nl.npairs;
     }
+    constexpr size_t g_bytes = sizeof(double) * (32 * G_LDT + G_WARPS * 7 * 32);
+    static bool attr_set = false;
+    if (!attr_set) {
+        IPF_CUDA(ctx, cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes));
+        attr_set = true;
+    }
+    cudaStream_t st2 = ctx->stream2;
+    cudaEvent_t gathered[2] = {nullptr, nullptr};    // gather of the batch that last used buffer b
+    // everything queued so far on the main stream (neighbour list, Psi zero fill, ...) precedes the gathers
     int64_t c0 = 0;
+    int ib = 0;
     while (c0 < ch.ncfg) {
         int64_t c1 = c0 + 1;
         while (c1 < ch.ncfg && nl.h_cfg_pair_off[c1 + 1] - nl.h_cfg_pair_off[c0] <= max_pairs_batch) ++c1;
+        const int buf = ib & 1;
         Fast3Args A;
-        A.p0 = nl.h_cfg_pair_off[c0]; A.np = nl.h_cfg_pair_off[c1] - A.p0; A.npairs = nl.npairs;
-        A.rec = rec; A.xpow = xpow; A.site_off = nl.site_off.p; A.atom_off = ch.atom_off.p;
-        A.psite = nl.psite.p; A.nb = blk.nb; A.S = (double*)Sbuf;
+        A.p0 = nl.h_cfg_pair_off[c0]; A.np = nl.h_cfg_pair_off[c1] - A.p0;
+        A.rec = rec; A.site_off = nl.site_off.p; A.atom_off = ch.atom_off.p;
+        A.psite = nl.psite.p; A.nb = blk.nb; A.S = (double*)Sbuf[buf];
+        if (gathered[buf]) {      // buffer reuse: wait for the gather that read it
+            IPF_CUDA(ctx, cudaStreamWaitEvent(st, gathered[buf], 0));
+            cudaEventDestroy(gathered[buf]);
+            gathered[buf] = nullptr;
+        }
         if (A.np > 0) {
             ProfScope prof_(ctx, "site_deriv_3b");
             switch (D) {
-#define IPF_CASE(DD) case DD: launch_moments<DD>(ctx, A); break;
+#define IPF_CASE(DD) case DD: launch_units<DD, 0>(ctx, A); break;
                 IPF_CASE(2) IPF_CASE(3) IPF_CASE(4) IPF_CASE(5) IPF_CASE(6) IPF_CASE(7) IPF_CASE(8)
                 IPF_CASE(9) IPF_CASE(10) IPF_CASE(11) IPF_CASE(12) IPF_CASE(13) IPF_CASE(14)
 #undef IPF_CASE
                 default: return ipf_set_error(ctx, IPF_EINVAL, "3-body degree %d not instantiated", D);
             }
-            ctx->launches++;
         }
+        cudaEvent_t produced;
+        IPF_CUDA(ctx, cudaEventCreateWithFlags(&produced, cudaEventDisableTiming));
+        IPF_CUDA(ctx, cudaEventRecord(produced, st));
+        IPF_CUDA(ctx, cudaStreamWaitEvent(st2, produced, 0));
+        cudaEventDestroy(produced);
         Gather3Args G;
-        G.p0 = A.p0; G.c0 = c0; G.nb = blk.nb; G.S = (const double*)Sbuf; G.scol2col = s2c.p;
+        G.p0 = A.p0; G.c0 = c0; G.nb = blk.nb; G.S = (const double*)Sbuf[buf]; G.scol2col = s2c.p;
         G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
         G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;
         G.Psi = Psi->d; G.ld = Psi->ld; G.col0 = blk.col0;
         {
-            ProfScope prof_(ctx, "gather_3b");
+            ProfScope prof_(ctx, "gather_3b", st2);
             dim3 grid((unsigned)(c1 - c0), (unsigned)((blk.nb + 31) / 32));
-            constexpr size_t g_bytes = sizeof(double) * (32 * G_LDT + G_WARPS * 7 * 32);
-            static bool attr_set = false;
-            if (!attr_set) {
-                IPF_CUDA(ctx, cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes));
-                attr_set = true;
-            }
-            gather3b_kernel<<<grid, G_THREADS, g_bytes, st>>>(G);
+            gather3b_kernel<<<grid, G_THREADS, g_bytes, st2>>>(G);
             ctx->launches++;
         }
+        IPF_CUDA(ctx, cudaEventCreateWithFlags(&gathered[buf], cudaEventDisableTiming));
+        IPF_CUDA(ctx, cudaEventRecord(gathered[buf], st2));
         c0 = c1;
+        ++ib;
     }
+    // later work on the main stream (next block, arena reuse, the solve) must see the gathered rows
+    for (int b = 0; b < 2; ++b)
+        if (gathered[b]) {
+            IPF_CUDA(ctx, cudaStreamWaitEvent(st, gathered[b], 0));
+            cudaEventDestroy(gathered[b]);
+        }
     IPF_CUDA(ctx, cudaGetLastError());
     *handled = true;
     return IPF_OK;

@@ -23,12 +23,11 @@
 
 namespace {
 
-constexpr int REC = 8;   // doubles per pair record: Rh[3], 1/r, x, dx/dr, fc, dfc/dr
+constexpr int REC = 8;   // head of a pair record: Rh[3], 1/r, x, dx/dr, fc, dfc/dr; then x^0..x^maxdeg (stride rs)
 constexpr double kPi = 3.14159265358979323846;
 
 __global__ void pair_record_kernel(int64_t npairs, const double* __restrict__ pR, int transform, double a,
-                                   double r0, double rc1, double rc2, int maxdeg, double* __restrict__ rec,
-                                   double* __restrict__ xpow) {
+                                   double r0, double rc1, double rc2, int maxdeg, int rs, double* __restrict__ rec) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const double Rx = pR[3 * p], Ry = pR[3 * p + 1], Rz = pR[3 * p + 2];
@@ -48,11 +47,12 @@ __global__ void pair_record_kernel(int64_t npairs, const double* __restrict__ pR
         fc = 0.5 * (1.0 + cos(kPi * s));
         dfc = -0.5 * kPi / w * sin(kPi * s);
     }
-    double* o = rec + REC * p;
+    double* o = rec + (int64_t)rs * p;
     o[0] = Rx / r; o[1] = Ry / r; o[2] = Rz / r; o[3] = 1.0 / r;
     o[4] = x; o[5] = dx; o[6] = fc; o[7] = dfc;
     double v = 1.0;
-    for (int e = 0; e <= maxdeg; ++e) { xpow[(int64_t)e * npairs + p] = v; v *= x; }
+    for (int e = 0; e <= maxdeg; ++e) { o[REC + e] = v; v *= x; }
+    for (int e = REC + maxdeg + 1; e < rs; ++e) o[e] = 0.0;
 }
 
 __device__ __forceinline__ double ipow(double w, int e) {
@@ -73,7 +73,7 @@ struct GenArgs {
     const int32_t* prev;
     const double* pR;
     const double* rec;
-    const double* xpow;
+    int rs;                        // record stride in doubles
     int64_t npairs;
     const int64_t* rowE;
     const int64_t* rowF;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void cluster_accumulate(const GenArgs& A, int64_t p, 
     double FCp = 1.0;
 #pragma unroll
     for (int c = 0; c < NO; ++c) {
-        const double* r = A.rec + REC * oth[c];
+        const double* r = A.rec + (int64_t)A.rs * oth[c];
         orec_rh[c][0] = r[0]; orec_rh[c][1] = r[1]; orec_rh[c][2] = r[2];
         FCp *= r[6];
     }
@@ -123,11 +123,12 @@ __device__ __forceinline__ void cluster_accumulate(const GenArgs& A, int64_t p, 
     for (int m = m0; m < m1; ++m) {
         const uint8_t* ex = sexp + m * IPF_MAX_VARS;
         const int e0 = ex[0];
-        const double Aown = A.xpow[(int64_t)e0 * A.npairs + p];
-        const double dAown = e0 > 0 ? (double)e0 * A.xpow[(int64_t)(e0 - 1) * A.npairs + p] : 0.0;
+        const double* ownp = A.rec + (int64_t)A.rs * p + REC;
+        const double Aown = ownp[e0];
+        const double dAown = e0 > 0 ? (double)e0 * ownp[e0 - 1] : 0.0;
         double rest = 1.0;
 #pragma unroll
-        for (int c = 0; c < NO; ++c) rest *= A.xpow[(int64_t)ex[1 + c] * A.npairs + oth[c]];
+        for (int c = 0; c < NO; ++c) rest *= A.rec[(int64_t)A.rs * oth[c] + REC + ex[1 + c]];
         // w pairs not touching the own leg
 #pragma unroll
         for (int k = NO; k < NPAIR; ++k) rest *= ipow(w[k], ex[NX + k]);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
             const int64_t p = P0 + pl;
             double own[REC];
 #pragma unroll
-            for (int k = 0; k < REC; ++k) own[k] = A.rec[REC * p + k];
+            for (int k = 0; k < REC; ++k) own[k] = A.rec[(int64_t)A.rs * p + k];
             const int64_t s = a0 + A.pi[p];
             const int64_t o0 = A.site_off[s], o1 = A.site_off[s + 1];
             for (int bl = 0; bl < nbu; ++bl) {
@@ -282,20 +283,21 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
 
 }  // namespace
 
-// pair records (8 doubles) + power table xpow[e][pair] of one descriptor, in ctx scratch slots 1 and 2
-int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec_out, const double** xpow_out) {
+// pair records of one descriptor in ctx scratch slot 1: per pair `rs` doubles =
+// [Rh(3), 1/r, x, dx, fc, dfc, x^0 .. x^maxdeg, pad]; rs is even (16-byte aligned records)
+int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec_out, int* rs_out) {
     const int64_t npairs = nl.npairs;
-    void *rec = nullptr, *xpow = nullptr;
-    IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * REC * (size_t)(npairs + 1), &rec));
-    IPF_CHECK(ipf_scratch(ctx, 2, sizeof(double) * (size_t)(blk.maxdeg + 1) * (size_t)(npairs + 1), &xpow));
+    const int rs = (REC + blk.maxdeg + 1 + 1) & ~1;
+    void* rec = nullptr;
+    IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * rs * (size_t)(npairs + 1), &rec));
     if (npairs > 0) {
         ProfScope prof_(ctx, "pair_record");
         pair_record_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, ctx->stream>>>(
-            npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, (double*)rec, (double*)xpow);
+            npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, rs, (double*)rec);
         ctx->launches++;
     }
     *rec_out = (const double*)rec;
-    *xpow_out = (const double*)xpow;
+    *rs_out = rs;
     return IPF_OK;
 }
 
@@ -305,9 +307,10 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     if (ch.ncfg == 0 || blk.nb == 0) return IPF_OK;
     const int64_t npairs = nl.npairs;
     // pair records + power table for this descriptor
-    const double *rec = nullptr, *xpow = nullptr;
+    const double* rec = nullptr;
+    int rs = 0;
     void *scr = nullptr, *cnt = nullptr;
-    IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &xpow));
+    IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &rs));
     // unit size: bounded by the shared-memory monomial table and by 64 functions
     int unit = 64;
     {
@@ -335,7 +338,7 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     A.nitems = (int64_t)ch.ncfg * nunits; A.ncfg = ch.ncfg;
     A.mono_start = blk.mono_start; A.mono_exp = blk.mono_exp;
     A.atom_off = ch.atom_off.p; A.cfg_pair_off = nl.cfg_pair_off.p; A.site_off = nl.site_off.p;
-    A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = rec; A.xpow = xpow;
+    A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = rec; A.rs = rs;
     A.npairs = npairs; A.rowE = ch.rowE.p; A.rowF = ch.rowF.p; A.rowV = ch.rowV.p;
     A.Psi = Psi->d; A.ld = Psi->ld; A.col0 = blk.col0; A.scratch = (double*)scr; A.counter = (int*)cnt;
     if (ctx->profiling) {

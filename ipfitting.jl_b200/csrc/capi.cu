@@ -34,8 +34,10 @@ int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out) {
     return IPF_OK;
 }
 
-int ipf_arena_alloc(ipf_ctx* ctx, size_t bytes, void** out) {
-    Arena& a = ctx->arena;
+int ipf_arena_alloc(ipf_ctx* ctx, size_t bytes, void** out) { return ipf_arena_alloc_in(ctx, ctx->arena, bytes, out); }
+int ipf_arena_reset(ipf_ctx* ctx) { return ipf_arena_reset_in(ctx, ctx->arena); }
+
+int ipf_arena_alloc_in(ipf_ctx* ctx, Arena& a, size_t bytes, void** out) {
     bytes = (bytes + 255) & ~(size_t)255;
     a.need += bytes;
     if (a.off + bytes <= a.cap) {
@@ -50,8 +52,7 @@ int ipf_arena_alloc(ipf_ctx* ctx, size_t bytes, void** out) {
     return IPF_OK;
 }
 
-int ipf_arena_reset(ipf_ctx* ctx) {
-    Arena& a = ctx->arena;
+int ipf_arena_reset_in(ipf_ctx* ctx, Arena& a) {
     if (!a.spill.empty() || a.need > a.cap) {
         IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (ctx->stream2) IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
@@ -106,6 +107,8 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
         if (ctx->scratch[k]) cudaFree(ctx->scratch[k]);
     for (void* p : ctx->arena.spill) cudaFree(p);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
+    for (void* p : ctx->solve_arena.spill) cudaFree(p);
+    if (ctx->solve_arena.base) cudaFree(ctx->solve_arena.base);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     delete ctx;

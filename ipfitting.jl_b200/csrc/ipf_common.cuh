@@ -25,7 +25,9 @@ struct Arena {
 };
 
 struct ipf_ctx {
-    Arena arena;
+    Arena arena;                        // assembly temporaries (per chunk)
+    Arena solve_arena;                  // workspaces of the (single) active solver
+    int active_solvers = 0;
     cudaStream_t stream2 = nullptr;     // second stream: gather of batch n overlaps the moments of batch n+1
     bool profiling = false;
     bool force_generic = false;
@@ -81,16 +83,17 @@ struct ProfScope {
     ipf_ctx* ctx;
     ProfEntry* e = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
-    ProfScope(ipf_ctx* c, const char* name) : ctx(c) {
+    cudaStream_t st;
+    ProfScope(ipf_ctx* c, const char* name, cudaStream_t stream = nullptr) : ctx(c), st(stream ? stream : c->stream) {
         if (!c->profiling) return;
         e = &c->prof[name];
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
-        cudaEventRecord(e0, c->stream);
+        cudaEventRecord(e0, st);
     }
     ~ProfScope() {
         if (!e) return;
-        cudaEventRecord(e1, ctx->stream);
+        cudaEventRecord(e1, st);
         e->pending.emplace_back(e0, e1);
         e->count++;
     }
@@ -101,6 +104,8 @@ int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out);
 // arena: alloc is stream-ordered-safe on ctx->stream; reset recycles everything handed out so far
 int ipf_arena_alloc(ipf_ctx* ctx, size_t bytes, void** out);
 int ipf_arena_reset(ipf_ctx* ctx);
+int ipf_arena_alloc_in(ipf_ctx* ctx, Arena& a, size_t bytes, void** out);
+int ipf_arena_reset_in(ipf_ctx* ctx, Arena& a);
 
 template <class T>
 struct ABuf {          // arena-backed array (never freed individually)

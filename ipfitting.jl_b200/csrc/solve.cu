@@ -35,6 +35,7 @@ struct ipf_solver {
     double* dinv = nullptr;         // [n] or null
     int* flag = nullptr;            // device status word
     double* red = nullptr;          // reduction scratch
+    bool pooled = false;            // workspaces come from ctx->solve_arena (not freed individually)
     int pass = 0;
     int state = 0;                  // 0: need gram, 1: need factor, 2: done
     double defect = -1.0, shift = 0.0, gram_ms = 0.0, trsm_ms = 0.0;
@@ -352,6 +353,7 @@ int upload(ipf_ctx* ctx, T** d, const T* h, size_t n) {
 
 void free_solve(ipf_solver* S) {
     if (!S) return;
+    if (!S->pooled)
     for (void* p : {(void*)S->A, (void*)S->yorig, (void*)S->G, (void*)S->L, (void*)S->Rtot, (void*)S->Rtmp,
                     (void*)S->vec, (void*)S->dinv, (void*)S->flag, (void*)S->red})
         if (p) cudaFree(p);
@@ -391,22 +393,42 @@ int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* d
     S->ncp = ((S->n1 + 127) / 128) * 128;
     cudaStream_t st = ctx->stream;
     const size_t abytes = sizeof(double) * (size_t)S->Mpad * S->ncp;
-    auto fail = [&](int code) { free_solve(S); return code; };
-    cudaError_t e = cudaMalloc((void**)&S->A, abytes);
-    if (e != cudaSuccess) return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %zu bytes for the weighted system: %s", abytes, cudaGetErrorString(e)));
+    auto fail = [&](int code) { if (S->pooled) ctx->active_solvers--; free_solve(S); return code; };
+    cudaError_t e = cudaSuccess;
     const size_t nn = (size_t)S->n * S->n;
-    if ((e = cudaMalloc((void**)&S->G, sizeof(double) * (size_t)S->n1 * S->n1)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&S->L, sizeof(double) * nn)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&S->Rtot, sizeof(double) * nn)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&S->Rtmp, sizeof(double) * nn)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&S->vec, sizeof(double) * S->n1)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&S->flag, sizeof(int) * 4)) != cudaSuccess ||
-        (e = cudaMalloc((void**)&S->red, sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8))) != cudaSuccess)
-        return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %s", cudaGetErrorString(e)));
-    if (dDinv) {
-        if ((e = cudaMalloc((void**)&S->dinv, sizeof(double) * n64)) != cudaSuccess ||
-            (e = cudaMemcpyAsync(S->dinv, dDinv, sizeof(double) * n64, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+    // the workspaces of the first live solver of a ctx come from a recycled pool (no cudaMalloc /
+    // cudaFree per fit); a second concurrent solver falls back to plain allocations
+    S->pooled = ctx->active_solvers == 0;
+    if (S->pooled) {
+        ctx->active_solvers++;
+        int rc = ipf_arena_reset_in(ctx, ctx->solve_arena);
+        auto take = [&](size_t bytes, void** out) { if (rc == IPF_OK) rc = ipf_arena_alloc_in(ctx, ctx->solve_arena, bytes, out); };
+        take(abytes, (void**)&S->A);
+        take(sizeof(double) * (size_t)S->n1 * S->n1, (void**)&S->G);
+        take(sizeof(double) * nn, (void**)&S->L);
+        take(sizeof(double) * nn, (void**)&S->Rtot);
+        take(sizeof(double) * nn, (void**)&S->Rtmp);
+        take(sizeof(double) * S->n1, (void**)&S->vec);
+        take(sizeof(int) * 4, (void**)&S->flag);
+        take(sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8), (void**)&S->red);
+        if (dDinv) take(sizeof(double) * n64, (void**)&S->dinv);
+        if (rc != IPF_OK) return fail(rc);
+    } else {
+        e = cudaMalloc((void**)&S->A, abytes);
+        if (e != cudaSuccess) return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %zu bytes for the weighted system: %s", abytes, cudaGetErrorString(e)));
+        if ((e = cudaMalloc((void**)&S->G, sizeof(double) * (size_t)S->n1 * S->n1)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->L, sizeof(double) * nn)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->Rtot, sizeof(double) * nn)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->Rtmp, sizeof(double) * nn)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->vec, sizeof(double) * S->n1)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->flag, sizeof(int) * 4)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->red, sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8))) != cudaSuccess ||
+            (dDinv && (e = cudaMalloc((void**)&S->dinv, sizeof(double) * n64)) != cudaSuccess))
             return fail(ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_begin: %s", cudaGetErrorString(e)));
+    }
+    if (dDinv) {
+        if ((e = cudaMemcpyAsync(S->dinv, dDinv, sizeof(double) * n64, cudaMemcpyDeviceToDevice, st)) != cudaSuccess)
+            return fail(ipf_set_error(ctx, IPF_ECUDA, "ipf_solve_begin: %s", cudaGetErrorString(e)));
     }
     cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st);
     if (nrows) nan_check_kernel<<<(unsigned)((nrows + 255) / 256), 256, 0, st>>>(dY, dW, nrows, S->flag);
@@ -461,6 +483,7 @@ int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, co
 int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S) {
     if (!S) return IPF_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    if (ctx && S->pooled) ctx->active_solvers--;
     free_solve(S);
     return IPF_OK;
 }
