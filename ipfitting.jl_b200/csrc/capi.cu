@@ -107,6 +107,7 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
         if (ctx->scratch[k]) cudaFree(ctx->scratch[k]);
     for (void* p : ctx->arena.spill) cudaFree(p);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
+    if (ctx->matrix_cache) cudaFree(ctx->matrix_cache);
     for (void* p : ctx->solve_arena.spill) cudaFree(p);
     if (ctx->solve_arena.base) cudaFree(ctx->solve_arena.base);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -252,10 +253,18 @@ int32_t ipf_matrix_create(ipf_ctx* ctx, int64_t nrows, int64_t ncols, ipf_matrix
     if (!M) return IPF_ENOMEM;
     M->nrows = nrows; M->ncols = ncols; M->ld = nrows;
     const size_t bytes = sizeof(double) * (size_t)std::max<int64_t>(1, nrows * ncols);
-    cudaError_t e = cudaMalloc((void**)&M->d, bytes);
-    if (e != cudaSuccess) {
-        delete M;
-        return ipf_set_error(ctx, IPF_ENOMEM, "ipf_matrix_create(%lld x %lld): %s", (long long)nrows, (long long)ncols, cudaGetErrorString(e));
+    if (ctx->matrix_cache && ctx->matrix_cache_bytes >= bytes && ctx->matrix_cache_bytes <= 2 * bytes + (1 << 20)) {
+        M->d = ctx->matrix_cache;
+        M->bytes = ctx->matrix_cache_bytes;
+        ctx->matrix_cache = nullptr;
+        ctx->matrix_cache_bytes = 0;
+    } else {
+        cudaError_t e = cudaMalloc((void**)&M->d, bytes);
+        if (e != cudaSuccess) {
+            delete M;
+            return ipf_set_error(ctx, IPF_ENOMEM, "ipf_matrix_create(%lld x %lld): %s", (long long)nrows, (long long)ncols, cudaGetErrorString(e));
+        }
+        M->bytes = bytes;
     }
     IPF_CUDA(ctx, cudaMemsetAsync(M->d, 0, bytes, ctx->stream));
     IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -266,7 +275,15 @@ int32_t ipf_matrix_create(ipf_ctx* ctx, int64_t nrows, int64_t ncols, ipf_matrix
 int32_t ipf_matrix_destroy(ipf_ctx* ctx, ipf_matrix* M) {
     if (!M) return IPF_OK;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-    if (M->d) cudaFree(M->d);
+    if (M->d) {
+        if (ctx && M->bytes > ctx->matrix_cache_bytes) {       // keep the largest buffer for the next LsqDB
+            if (ctx->matrix_cache) cudaFree(ctx->matrix_cache);
+            ctx->matrix_cache = M->d;
+            ctx->matrix_cache_bytes = M->bytes;
+        } else {
+            cudaFree(M->d);
+        }
+    }
     delete M;
     return IPF_OK;
 }

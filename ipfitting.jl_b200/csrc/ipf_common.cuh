@@ -28,6 +28,8 @@ struct ipf_ctx {
     Arena arena;                        // assembly temporaries (per chunk)
     Arena solve_arena;                  // workspaces of the (single) active solver
     int active_solvers = 0;
+    double* matrix_cache = nullptr;     // one recycled design-matrix allocation (avoids cudaMalloc/cudaFree per LsqDB)
+    size_t matrix_cache_bytes = 0;
     cudaStream_t stream2 = nullptr;     // second stream: gather of batch n overlaps the moments of batch n+1
     bool profiling = false;
     bool force_generic = false;
@@ -45,6 +47,7 @@ struct ipf_ctx {
 struct ipf_matrix {
     int64_t nrows = 0, ncols = 0, ld = 0;
     double* d = nullptr;
+    size_t bytes = 0;       // size of the allocation behind d
 };
 
 struct BlockDev {

@@ -12,6 +12,8 @@ the whole-DB entry point is `LsqDB(...)` in lsq_db.py.
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 from .prototypes import ENERGY, FORCES, VIRIAL
@@ -55,7 +57,7 @@ def obs_len(okey: str, nat: int) -> int:
 
 def weighthook(okey: str, d) -> float:
     if okey in (ENERGY, VIRIAL):
-        return 1.0 / np.sqrt(len(d.at))
+        return 1.0 / math.sqrt(len(d.at))
     return 1.0
 
 

@@ -40,8 +40,9 @@ def _fix_weights(weights: Optional[dict]) -> dict:
     return weights
 
 
-def _get_weights(weights: dict, wh: float, dat, obskey: str, o: np.ndarray) -> np.ndarray:
-    """`_get_weights` (`src/lsq.jl:118-161`)."""
+def _get_weights(weights: dict, wh: float, dat, obskey: str, o: np.ndarray):
+    """`_get_weights` (`src/lsq.jl:118-161`).  Returns a scalar (broadcast over the block) or,
+    for E / V with a per-component `info["W"]` entry, a vector of length len(o)."""
     w = 0.0
     if "W" in dat.info:
         # overrides everything, weighthook included (`:125-131`)
@@ -52,16 +53,15 @@ def _get_weights(weights: dict, wh: float, dat, obskey: str, o: np.ndarray) -> n
         cfgkey = ct if ct in weights else "default"
         if obskey in weights[cfgkey]:
             w = weights[cfgkey][obskey] * wh
+    if isinstance(w, (int, float)):
+        return float(w)
     wa = np.atleast_1d(np.asarray(w, dtype=np.float64))
-    if obskey in (ENERGY, VIRIAL):
-        if wa.size == 1:
-            return np.full(len(o), wa[0])
-        if wa.size == len(o):
-            return wa.copy()
-    elif obskey == FORCES:
-        if wa.size != 1:
-            raise ValueError("_get_weights: a vector weight is not allowed for \"F\"")
-        return np.full(len(o), wa[0])
+    if wa.size == 1:
+        return float(wa[0])
+    if obskey in (ENERGY, VIRIAL) and wa.size == len(o):
+        return wa.copy()
+    if obskey == FORCES:
+        raise ValueError("_get_weights: a vector weight is not allowed for \"F\"")
     raise ValueError("_get_weights: length(w) is neither 1 nor length(o)?!?!?")
 
 
@@ -73,18 +73,26 @@ def collect_observations(db: LsqDB, weights: dict, Vref):
     W = np.zeros(nrows)
     Icfg = np.full(nrows, -1, dtype=np.int64)
     ignore = weights["ignore"]
-    for okey, dat, icfg in observations(db):
-        if dat.configtype in ignore or okey in ignore:
+    onebody = isinstance(Vref, OneBody)
+    for icfg, dat in enumerate(db.configs):
+        if dat.configtype in ignore:
             continue
-        irows = matrows(dat, okey)
-        obs = dat.D[okey]
-        if "Vref" in dat.info:
-            obs = obs - np.asarray(dat.info["Vref"][okey], dtype=np.float64)
-        elif Vref is not None:
-            obs = obs - vref_observation(Vref, okey, dat)
-        Y[irows] = obs
-        Icfg[irows] = icfg
-        W[irows] = _get_weights(weights, weighthook(okey, dat), dat, okey, obs)
+        info = dat.info
+        for okey in list(dat.D.keys()):          # same traversal as observations(db) (`src/obsiter.jl:36-59`)
+            if okey in ignore:
+                continue
+            f, n = dat.rows[okey]
+            obs = dat.D[okey]
+            if "Vref" in info:
+                obs = obs - np.asarray(info["Vref"][okey], dtype=np.float64)
+            elif onebody:
+                if okey == ENERGY:               # OneBody: zero forces and virial
+                    obs = obs - Vref.energy(dat.at)
+            elif Vref is not None:
+                obs = obs - vref_observation(Vref, okey, dat)
+            Y[f:f + n] = obs
+            Icfg[f:f + n] = icfg
+            W[f:f + n] = _get_weights(weights, weighthook(okey, dat), dat, okey, obs)
     return Y, W, Icfg
 
 
@@ -167,25 +175,33 @@ class _Solver:
             pass
 
 
+def run_staged(S, comm=None, device: int = 0, want_R: bool = True):
+    """The staged solve protocol (include/ipf_b200.h): gram -> [all-reduce] -> factor, repeated
+    until done; then finish.  `S` is a `_Solver` (device) -- or any object with the same four
+    methods (the gloo tests drive a numpy stand-in through exactly this function)."""
+    multi = comm is not None and comm.world_size > 1
+    while True:
+        g, n1 = S.gram()
+        if multi:
+            comm.allreduce_gram(g, n1 * n1, device)
+        if S.factor():
+            break
+    c, R, ssr, ssy = S.finish(want_R)
+    if multi:
+        ssr, ssy = comm.allreduce_scalars([ssr, ssy])
+    info = S.info()
+    info["rel_rms"] = math.sqrt(ssr) / math.sqrt(ssy) if ssy > 0 else float("nan")
+    return c, R, info
+
+
 def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None):
     """Weighted LSQ solve of the device-resident system.  `comm`: a
     `parallel.Communicator` (rows are sharded over its ranks) or None."""
     S = _Solver(ctx, Psi_dev, Y, W, Irows, Icols, Dinv)
     try:
-        while True:
-            gptr, n1 = S.gram()
-            if comm is not None and comm.world_size > 1:
-                comm.allreduce_device_f64(gptr, n1 * n1, ctx.device)
-            if S.factor():
-                break
-        c, R, ssr, ssy = S.finish(want_R)
-        if comm is not None and comm.world_size > 1:
-            ssr, ssy = comm.allreduce_scalars([ssr, ssy])
-        info = S.info()
+        return run_staged(S, comm, ctx.device, want_R)
     finally:
         S.close()
-    info["rel_rms"] = math.sqrt(ssr) / math.sqrt(ssy) if ssy > 0 else float("nan")
-    return c, R, info
 
 
 def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=None, Vref="default",

@@ -40,10 +40,11 @@ def _alloc_rows(configs: Sequence[Dat]) -> int:
     """Row assignment of `_alloc_lsq_matrix` (`src/lsq_db.jl:237-250`): prefix sum of the
     observation lengths in `observations(configs)` order.  Returns nrows."""
     nrows = 0
-    for okey, d, _ in observations(configs):
-        n = len(d.D[okey])
-        set_matrows(d, okey, nrows, n)
-        nrows += n
+    for d in configs:                       # observations(configs) order: config-major, then D's key order
+        for okey, v in d.D.items():
+            n = len(v)
+            d.rows[okey] = (nrows, n)
+            nrows += n
     return nrows
 
 

@@ -58,6 +58,14 @@ class Communicator:
         self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM, group=self.group)
         torch.cuda.synchronize(device)
 
+    def allreduce_gram(self, g, n: int, device: int):
+        """Sum of the per-rank Gram blocks: `g` is a device address (CUDA path) or a numpy array
+        (CPU stand-in of the tests), reduced in place."""
+        if isinstance(g, np.ndarray):
+            g[...] = self.allreduce_numpy(g).reshape(g.shape)
+        else:
+            self.allreduce_device_f64(g, n, device)
+
     def allreduce_numpy(self, a: np.ndarray) -> np.ndarray:
         import torch
         dev = "cuda" if self.backend == "nccl" else "cpu"

@@ -1,0 +1,111 @@
+# IPFittingB200.jl -- ccall shim that puts libipf_b200.so behind IPFitting.jl's own API.
+#
+# NOT EXECUTED in the build container (no Julia toolchain there); written against
+# include/ipf_b200.h and the reference sources it patches:
+#   (1) src/lsq_db.jl:181-185   tfor_observations(... safe_append! ...)      -> ipf_assemble
+#   (2) src/lsq.jl:306-307, 450-473, 593   weights, P-scaling, qr!, cond, \  -> ipf_solve
+#   (3) src/lsq.jl:642-648  add_fits_serial! + rmse                          -> ipf_residual_stats
+# Everything else (Dict weights, row allocation, combine, fitinfo) is the unchanged reference.
+module IPFittingB200
+
+using IPFitting, JuLIP, LinearAlgebra
+using IPFitting: Dat, LsqDB, observations, observation, weighthook, err_weighthook
+using IPFitting.DB: _alloc_lsq_matrix, matrows
+using IPFitting.Lsq: collect_observations, _fix_weights!
+
+const LIB = get(ENV, "IPF_B200_LIB", "libipf_b200.so")
+const MAX_VARS = 10
+
+struct BlockSpec            # mirrors ipf_block_spec
+   N::Int32; nb::Int32; nmono::Int32; transform::Int32
+   a::Float64; r0::Float64; rc1::Float64; rc2::Float64
+   mono_b::Ptr{Int32}; mono_exp::Ptr{UInt8}
+end
+
+mutable struct Ctx
+   h::Ptr{Cvoid}
+   function Ctx(device::Integer = 0)
+      ref = Ref{Ptr{Cvoid}}(C_NULL)
+      rc = ccall((:ipf_init, LIB), Int32, (Int32, Ref{Ptr{Cvoid}}), device, ref)
+      ctx = new(ref[])
+      rc == 0 || error(lasterror(ctx))
+      finalizer(c -> ccall((:ipf_destroy, LIB), Int32, (Ptr{Cvoid},), c.h), ctx)
+   end
+end
+lasterror(ctx::Ctx) = unsafe_string(ccall((:ipf_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h))
+check(ctx::Ctx, rc) = (rc == 0 || error(lasterror(ctx)); nothing)   # NaN codes carry the reference's messages
+
+const CTX = Ref{Union{Nothing, Ctx}}(nothing)
+context() = (CTX[] === nothing && (CTX[] = Ctx(parse(Int, get(ENV, "LOCAL_RANK", "0")))); CTX[])
+
+"""
+`blockspecs(basis)`: the (N, descriptor, monomial table) runs of an NBodyIPs-style basis.
+A basis element must expose `bodyorder`, its descriptor (transform id, a, r0, rc1, rc2) and the
+exponent tuples of its monomial orbit -- the tables `ipfitting.jl_b200/basis.py` emits.
+"""
+function blockspecs end
+
+# ---------------------------------------------------------------- (1) assembly
+function IPFitting.DB.LsqDB(dbpath::AbstractString, basis, configs::AbstractVector{Dat};
+                            verbose = true, maxnthreads = 0, device = true)
+   Ψ = _alloc_lsq_matrix(configs, basis)          # unchanged: assigns rows in Dict key order
+   db = LsqDB(basis, configs, Ψ, dbpath)
+   ctx = context()
+   specs, keep = blockspecs(basis)
+   hb = Ref{Ptr{Cvoid}}(C_NULL)
+   GC.@preserve keep specs begin
+      check(ctx, ccall((:ipf_basis_create, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{BlockSpec}, Ref{Ptr{Cvoid}}),
+                       ctx.h, length(specs), specs, hb))
+   end
+   ncfg = length(configs)
+   atom_off = cumsum(vcat(0, [length(c.at) for c in configs]))
+   pos  = reduce(hcat, [mat(positions(c.at)) for c in configs])          # 3 x natoms, column-major = atom-major xyz
+   cell = reduce(hcat, [reshape(Matrix(JuLIP.cell(c.at))', 9) for c in configs])   # rows = lattice vectors
+   pbc  = reduce(vcat, [UInt8.(collect(JuLIP.pbc(c.at))) for c in configs])
+   Z    = reduce(vcat, [Int32.(c.at.Z) for c in configs])
+   row(c, k) = haskey(c.D, k) ? Int64(first(matrows(c, k))) : Int64(0)  # 1-based first row, 0 = absent
+   rowE = [row(c, "E") for c in configs]; rowF = [row(c, "F") for c in configs]; rowV = [row(c, "V") for c in configs]
+   hm = Ref{Ptr{Cvoid}}(C_NULL)
+   check(ctx, ccall((:ipf_matrix_create, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}),
+                    ctx.h, size(Ψ, 1), size(Ψ, 2), hm))
+   check(ctx, ccall((:ipf_assemble, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{UInt8}, Ptr{Int32},
+                     Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Cvoid}),
+                    ctx.h, hb[], ncfg, Int64.(atom_off), pos, cell, pbc, Z, rowE, rowF, rowV, hm[]))
+   # materialise on the host (db.Ψ is a Julia Matrix); keep hm[] in a side table to skip the H2D in lsqfit
+   check(ctx, ccall((:ipf_matrix_to_host, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64),
+                    ctx.h, hm[], db.Ψ, size(Ψ, 1)))
+   DEVICE_PSI[objectid(db)] = hm[]
+   ccall((:ipf_basis_destroy, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), ctx.h, hb[])
+   dbpath != "" && IPFitting.DB.flush(db)
+   return db
+end
+const DEVICE_PSI = Dict{UInt, Ptr{Cvoid}}()
+
+# ---------------------------------------------------------------- (2) solve: replaces src/lsq.jl:436-473,593
+function solve_qr(db::LsqDB, Y::Vector{Float64}, W::Vector{Float64}, Irows::Vector{Int}, Icols, Dinv)
+   ctx = context()
+   hm = get(DEVICE_PSI, objectid(db), C_NULL)
+   if hm == C_NULL                       # db loaded from disk: upload once
+      r = Ref{Ptr{Cvoid}}(C_NULL)
+      check(ctx, ccall((:ipf_matrix_create, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ref{Ptr{Cvoid}}), ctx.h, size(db.Ψ)..., r))
+      check(ctx, ccall((:ipf_matrix_from_host, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Int64), ctx.h, r[], db.Ψ, size(db.Ψ, 1)))
+      hm = DEVICE_PSI[objectid(db)] = r[]
+   end
+   n = Icols isa Colon ? size(db.Ψ, 2) : length(Icols)
+   c = zeros(n); R = zeros(n, n); rel = Ref{Float64}(0.0)
+   ir = Int64.(Irows .- 1)                                            # 0-based at the ABI
+   ic = Icols isa Colon ? C_NULL : Int64.(collect(Icols) .- 1)
+   check(ctx, ccall((:ipf_solve, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Int64}, Int64, Ptr{Int64}, Int64,
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}),
+                    ctx.h, hm, Y, W, ir, length(ir), ic, n, Dinv === nothing ? C_NULL : Dinv, c, R, rel))
+   return c, cond(UpperTriangular(R)), rel[]          # c already multiplied by D_inv (src/lsq.jl:593)
+end
+# In IPFitting.Lsq.lsqfit the :qr branch becomes
+#     Y, W, Icfg = collect_observations(db, weights, Vref)                      (unchanged)
+#     Irows = intersect(findall(W .!= 0) |> sort, findall(in.(Icfg, Ref(Itrain))))   (unchanged, src/lsq.jl:277)
+#     c, κ, rel_rms = IPFittingB200.solve_qr(db, Y, W, Irows, Ibasis, diag(pinv(P)))
+# and, per SURVEY Q8, `c` is scattered into a full-length vector before `combine(db.basis, c)`.
+
+end # module
