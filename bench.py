@@ -203,6 +203,7 @@ def run_ours(args):
     comm = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = parallel.Communicator()
 
@@ -322,6 +323,9 @@ def run_ours(args):
     d2h = 8 * ncols + 8 * ncols * ncols + 16
 
     if rank != 0:
+        if comm is not None:
+            dist.barrier()
+            dist.destroy_process_group()
         return
     # ---- rooflines: the three heavy kernels, the slowest one is reported as `roofline`
     blk3 = [b for b in basis.blocks if b.N == 3][0]
@@ -394,6 +398,9 @@ def run_ours(args):
             "cpu_baseline": cpu, "fit": {"rel_rms": math.sqrt(ssr / ssy) if comm is None else rel_e2e,
                                          "coeff_diff_dev_vs_e2e": float(np.linalg.norm(c_dev - c_e2e) / np.linalg.norm(c_e2e))}}
     print(json.dumps(line), flush=True)
+    if comm is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():

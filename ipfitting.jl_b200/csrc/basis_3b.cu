@@ -12,11 +12,16 @@
 //     T  = c (x^a U_c[b] + x^b U_c[a]) - c S0 Rhat_j                 (x = x_j; a = b: one term)
 //     g_p = (fc_j' S0 + fc_j x_j' S1) Rhat_j + fc_j/r_j T,     e_p = fc_j S0 / 2.
 // The (e, c) plane is cut into units of consecutive c (register budget); a CTA
-// runs one unit for 128 consecutive pairs.  (g_p, e_p) go to the HBM scratch
-// S[pair][scol][4] (scol = unit-major column order, so a thread writes its unit's
-// functions contiguously); gather3b_kernel sums them in a fixed order into the
-// E / F / V rows (deterministic, no atomics) with fully coalesced 1 KB reads per
-// (pair, 32 columns), own and reverse pair alike.
+// runs one unit for 128 consecutive pairs.  Outputs are staged through shared memory in
+// groups of 8 functions: g_p goes to the HBM scratch S[pair][scol][3] (scol = unit-major
+// column order; contiguous 192-byte runs per pair), and the per-centre-atom sums
+// O[site][slot][scol] = sum_{p in out(a)} (g_p, e_p) are reduced in the CTA in row order
+// (slot 1 = continuation of a site that started in the previous CTA).  gather3b_kernel then
+// needs only the REVERSE entries:  F_b[a] = O[a] - sum_{p in out(a)} g_rev(p),
+// Vir_b = + sum_p g_rev(p) (x) R_p  (rev is a bijection and R_rev(p) = -R_p), E_b = sum_a O[a].e
+// -- everything in a fixed order, no atomics, 768-byte coalesced reads per (pair, 32 columns).
+#include <cstdlib>
+
 #include "ipf_common.cuh"
 
 int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec, int* rs);
@@ -33,8 +38,13 @@ struct Fast3Args {
     const int64_t* site_off;
     const int64_t* atom_off;
     const int32_t* psite;          // chunk-global site of every pair
+    const int64_t* pbeg;           // first pair of that site's list
+    const int32_t* pcnt;           // length of that list
     int nb;
-    double* S;                     // [np][nb][4], scol order
+    double* S;                     // [np][nb][3], scol order: g_p
+    double* O;                     // [nsites_batch][nslot][nb][4]: own sums (gx, gy, gz, e) per centre atom and slot
+    int64_t s0;                    // first site of the batch
+    int nslot;                     // slot = (batch row / 32) - (site's first batch row / 32): warp-local piece sums
 };
 
 // number of basis functions with w-exponent c (degree-D basis): pairs a <= b, a + b <= D - c, minus the constant
@@ -71,7 +81,7 @@ __device__ __forceinline__ double ipow_c(double w) {
 template <int D>
 struct RecStride { static constexpr int value = (REC + D + 2) & ~1; };
 
-constexpr int A_MAXREC = 288;              // pair records staged in shared memory per CTA
+constexpr int A_MAXREC = 224;              // pair records staged in shared memory per CTA
 constexpr int A_OUTG = 8;                  // functions per staged output group
 constexpr int A_OUTLD = 4 * A_OUTG + 2;    // doubles per staged row (+2: conflict-free 16-byte columns)
 
@@ -79,7 +89,7 @@ template <int D>
 __host__ __device__ constexpr size_t moments_smem_bytes() {
     constexpr size_t a = sizeof(double) * (size_t)A_MAXREC * RecStride<D>::value;
     constexpr size_t b = sizeof(double) * (size_t)A_THREADS * A_OUTLD;
-    return a > b ? a : b;
+    return a + b;
 }
 
 // moment accumulation over the neighbours of the thread's centre atom; RK points at the record of
@@ -135,50 +145,83 @@ __device__ __forceinline__ void moment_loop(const double* __restrict__ rk, int n
     }
 }
 
-// coalesced write-out of NG staged functions of all rows of the CTA: S[(pl0+row)*nb + sc0 .. +NG)
-template <int NG>
-__device__ __forceinline__ void flush_group(double* __restrict__ S, const double* __restrict__ stage, int64_t pl0,
-                                            int nrow, int nb, int sc0) {
-    __syncthreads();
-    double2* S2 = reinterpret_cast<double2*>(S);
-    const double2* st2 = reinterpret_cast<const double2*>(stage);
-    for (int q = threadIdx.x; q < nrow * 2 * NG; q += A_THREADS) {
-        const int row = q / (2 * NG), c = q - row * (2 * NG);
-        S2[((pl0 + row) * nb + sc0) * 2 + c] = st2[row * (A_OUTLD / 2) + c];
+constexpr int A_EOFF = 3 * A_OUTG;         // staged row: [g(3) x A_OUTG][e x A_OUTG][pad 2]
+
+// sum of column `lane` of the staged tile over rows [r0, r1): four interleaved partial sums (fixed order)
+__device__ __forceinline__ double column_sum(const double* __restrict__ stage, int r0, int r1, int lane) {
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    int r = r0;
+    for (; r + 3 < r1; r += 4) {
+        a0 += stage[r * A_OUTLD + lane];
+        a1 += stage[(r + 1) * A_OUTLD + lane];
+        a2 += stage[(r + 2) * A_OUTLD + lane];
+        a3 += stage[(r + 3) * A_OUTLD + lane];
     }
-    __syncthreads();
+    for (; r < r1; ++r) a0 += stage[r * A_OUTLD + lane];
+    return (a0 + a1) + (a2 + a3);
 }
 
-// one unit = exponents c in [C0, C1] of w; one kernel per unit (own register budget)
-template <int D, int C0, int C1>
-__global__ void __launch_bounds__(A_THREADS) moments3b_unit_kernel(Fast3Args A) {
-    extern __shared__ __align__(16) double sm[];
-    __shared__ int64_t s_kbeg;
-    __shared__ int s_nrec;
-    constexpr int RS = RecStride<D>::value;
+// Warp-synchronous write-out of NG staged functions of the warp's own 32 rows (`wstage`):
+//   S[(row)*nb + sc0 .. +NG)[3]  (contiguous 24*NG bytes per row), and
+//   O[site][slot][sc0 .. +NG)[4] = column sums over each of the warp's centre-atom pieces, rows in order.
+// pmask: bit r set = row r of the warp opens a piece; pout[r]: O row (site, slot) of the piece opening at r.
+template <int NG>
+__device__ __forceinline__ void flush_group(const Fast3Args& A, const double* __restrict__ wstage, int64_t plw,
+                                            int nrw, int sc0, unsigned pmask, int pout) {
+    __syncwarp();
+    const int lane = threadIdx.x & 31;
+    if constexpr (NG % 2 == 0) {
+        constexpr int CH = 3 * NG / 2;            // 16-byte chunks per row
+        double2* S2 = reinterpret_cast<double2*>(A.S);
+        const double2* st2 = reinterpret_cast<const double2*>(wstage);
+        for (int q = lane; q < nrw * CH; q += 32) {
+            const int row = q / CH, c = q - row * CH;
+            S2[((plw + row) * A.nb + sc0) * 3 / 2 + c] = st2[row * (A_OUTLD / 2) + c];
+        }
+    } else {
+        for (int q = lane; q < nrw * 3 * NG; q += 32) {
+            const int row = q / (3 * NG), c = q - row * (3 * NG);
+            A.S[((plw + row) * A.nb + sc0) * 3 + c] = wstage[row * A_OUTLD + c];
+        }
+    }
+    // column sums: lane = staged column v (0..23: g of function v/3, component v%3; 24..31: e of function v-24)
+    const bool vlive = lane < 3 * NG || (lane >= A_EOFF && lane < A_EOFF + NG);
+    const int f = lane < A_EOFF ? lane / 3 : lane - A_EOFF;
+    const int d = lane < A_EOFF ? lane - 3 * f : 3;
+    unsigned m = pmask;
+    while (m) {
+        const int r0 = __ffs(m) - 1;
+        m &= m - 1;
+        const int r1 = m ? (__ffs(m) - 1) : nrw;
+        const double acc = column_sum(wstage, r0, r1, lane);
+        const int orow = __shfl_sync(0xffffffffu, pout, r0);
+        if (vlive) A.O[((int64_t)orow * A.nb + sc0 + f) * 4 + d] = acc;
+    }
+    __syncwarp();
+}
+
+// state shared by all units of a CTA (computed once in the kernel prologue)
+struct CtaState {
+    const double* recp;          // own pair record (global)
+    const double* rk0;           // record of the centre atom's first neighbour (shared or global memory)
+    bool staged;
+    int n, jself;
+    double Rj0, Rj1, Rj2, rinvj, dxj, fcj, dfcj;
+    double* wstage;              // this warp's staging rows
+    int64_t plw;                 // batch row of the warp's first lane
+    int nrw;                     // live rows of the warp
+    unsigned pmask;
+    int pout;
+};
+
+// one unit = exponents c in [C0, C1] of w
+template <int D, int C0, int C1, int SCB>
+__device__ __forceinline__ void unit3b(const Fast3Args& A, const CtaState& T) {
     constexpr int NC = C1 - C0 + 1;
     constexpr int EMAX = D - C0;            // largest x-exponent in this unit
-    const int tid = threadIdx.x;
-    const int64_t pl0 = (int64_t)blockIdx.x * A_THREADS;
-    const int64_t pl = pl0 + tid;
-    const bool live = pl < A.np;
-    const int nrow = (int)min((int64_t)A_THREADS, A.np - pl0);
-    const int64_t p = A.p0 + (live ? pl : pl0);
-    if (tid == 0) {
-        const int64_t kb = A.site_off[A.psite[A.p0 + pl0]];
-        const int64_t ke = A.site_off[A.psite[A.p0 + pl0 + nrow - 1] + 1];
-        s_kbeg = kb;
-        s_nrec = (int)min((int64_t)(A_MAXREC + 1), ke - kb);
-    }
-    __syncthreads();
-    const int64_t kbeg = s_kbeg;
-    const bool staged = s_nrec <= A_MAXREC;
-    if (staged) {
-        const double2* src = reinterpret_cast<const double2*>(A.rec + kbeg * RS);
-        double2* dst = reinterpret_cast<double2*>(sm);
-        const int n2 = s_nrec * (RS / 2);
-        for (int i = tid; i < n2; i += A_THREADS) dst[i] = __ldg(src + i);
-    }
+    const int lane = threadIdx.x & 31;
+    const double Rj0 = T.Rj0, Rj1 = T.Rj1, Rj2 = T.Rj2, rinvj = T.rinvj, dxj = T.dxj, fcj = T.fcj, dfcj = T.dfcj;
+    const double* recp = T.recp;
     double Z[NC][EMAX + 1];
     double U[NC][EMAX + 1][3];
 #pragma unroll
@@ -186,18 +229,8 @@ __global__ void __launch_bounds__(A_THREADS) moments3b_unit_kernel(Fast3Args A) 
 #pragma unroll
         for (int e = 0; e <= EMAX; ++e) { Z[ci][e] = 0.0; U[ci][e][0] = U[ci][e][1] = U[ci][e][2] = 0.0; }
 
-    const double* recp = A.rec + (int64_t)RS * p;
-    const double4 o0v = ld4(recp);
-    const double4 o1v = ld4(recp + 4);
-    const double Rj0 = o0v.x, Rj1 = o0v.y, Rj2 = o0v.z, rinvj = o0v.w;
-    const double dxj = o1v.y, fcj = o1v.z, dfcj = o1v.w;
-    const int64_t s = A.psite[p];
-    const int64_t k0 = A.site_off[s];
-    const int n = live ? (int)(A.site_off[s + 1] - k0) : 0;
-    const int jself = (int)(p - k0);
-    __syncthreads();
-    if (staged) moment_loop<D, C0, C1, NC, EMAX>(sm + (k0 - kbeg) * RS, n, jself, Rj0, Rj1, Rj2, Z, U);
-    else moment_loop<D, C0, C1, NC, EMAX>(A.rec + k0 * RS, n, jself, Rj0, Rj1, Rj2, Z, U);
+    if (T.staged) moment_loop<D, C0, C1, NC, EMAX>(T.rk0, T.n, T.jself, Rj0, Rj1, Rj2, Z, U);
+    else moment_loop<D, C0, C1, NC, EMAX>(T.rk0, T.n, T.jself, Rj0, Rj1, Rj2, Z, U);
 
     // ---- combine into basis functions, staged through shared memory in groups of A_OUTG
     double X[EMAX + 1], dX[EMAX + 1];
@@ -208,10 +241,14 @@ __global__ void __launch_bounds__(A_THREADS) moments3b_unit_kernel(Fast3Args A) 
     for (int e = 1; e <= EMAX; ++e) dX[e] = (double)e * X[e - 1];
     const double tang = fcj * rinvj;
     const double fdx = fcj * dxj;
-    __syncthreads();                         // records are dead: the staging area reuses their memory
-    double* myrow = sm + tid * A_OUTLD;
-    constexpr int SC0 = scol_base(D, C0);
-    constexpr int NF = scol_base(D, C1 + 1) - SC0;
+    double* wstage = T.wstage;
+    double* myrow = wstage + lane * A_OUTLD;
+    const int64_t plw = T.plw;
+    const int nrw = T.nrw;
+    const unsigned pmask = T.pmask;
+    const int pout = T.pout;
+    constexpr int SC0 = SCB;                                       // even: 16-byte aligned scratch rows
+    constexpr int NF = scol_base(D, C1 + 1) - scol_base(D, C0);
     int f = 0;
 #pragma unroll
     for (int ci = 0; ci < NC; ++ci) {
@@ -237,15 +274,73 @@ __global__ void __launch_bounds__(A_THREADS) moments3b_unit_kernel(Fast3Args A) 
                 }
                 const double radial = fma(dfcj - tc, S0, fdx * S1);      // coefficient of Rhat_j
                 const int slot = f % A_OUTG;
-                *reinterpret_cast<double2*>(myrow + 4 * slot) = make_double2(fma(radial, Rj0, tc * T0), fma(radial, Rj1, tc * T1));
-                *reinterpret_cast<double2*>(myrow + 4 * slot + 2) = make_double2(fma(radial, Rj2, tc * T2), 0.5 * fcj * S0);
+                myrow[3 * slot] = fma(radial, Rj0, tc * T0);
+                myrow[3 * slot + 1] = fma(radial, Rj1, tc * T1);
+                myrow[3 * slot + 2] = fma(radial, Rj2, tc * T2);
+                myrow[A_EOFF + slot] = 0.5 * fcj * S0;
                 ++f;
-                if (f % A_OUTG == 0) flush_group<A_OUTG>(A.S, sm, pl0, nrow, A.nb, SC0 + f - A_OUTG);
+                if (f % A_OUTG == 0) flush_group<A_OUTG>(A, wstage, plw, nrw, SC0 + f - A_OUTG, pmask, pout);
             }
         }
     }
     constexpr int REM = NF % A_OUTG;
-    if constexpr (REM > 0) flush_group<REM>(A.S, sm, pl0, nrow, A.nb, SC0 + NF - REM);
+    if constexpr (REM > 0) flush_group<REM>(A, wstage, plw, nrw, SC0 + NF - REM, pmask, pout);
+}
+
+template <int D> struct UnitTable;
+
+template <int D, int U>
+__device__ __forceinline__ void run_unit(const Fast3Args& A, const CtaState& T);
+
+// CTA = 128 consecutive ordered pairs x one unit (one kernel per unit: own register budget and occupancy;
+// running all units in one kernel was measured 1.6x slower)
+template <int D, int U>
+__global__ void __launch_bounds__(A_THREADS) moments3b_kernel(Fast3Args A) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int64_t s_kbeg;
+    __shared__ int s_nrec;
+    constexpr int RS = RecStride<D>::value;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int64_t pl0 = (int64_t)blockIdx.x * A_THREADS;
+    const int64_t pl = pl0 + tid;
+    const bool live = pl < A.np;
+    const int nrow = (int)min((int64_t)A_THREADS, A.np - pl0);
+    const int64_t p = A.p0 + (live ? pl : pl0);
+    const int64_t k0 = A.pbeg[p];                      // first pair of the centre atom's list
+    const int n = live ? A.pcnt[p] : 0;                // its length
+    const int site = A.psite[p];
+    if (tid == 0) { s_kbeg = k0; }
+    if (tid == nrow - 1) { s_nrec = (int)min((int64_t)(A_MAXREC + 1), k0 + A.pcnt[p] - A.pbeg[A.p0 + pl0]); }
+    CtaState T;
+    // pieces of this warp's rows: a piece opens where the centre atom changes or at the warp's first row
+    const int site_prev = __shfl_up_sync(0xffffffffu, site, 1);
+    const bool piece_start = live && (lane == 0 || site != site_prev);
+    T.pmask = __ballot_sync(0xffffffffu, piece_start);
+    // O row of my piece: slot = warp-row-block index relative to the block holding the site's first pair
+    T.pout = (int)(site - A.s0) * A.nslot + (int)((pl >> 5) - ((k0 - A.p0) >> 5));
+    __syncthreads();
+    const int64_t kbeg = s_kbeg;
+    T.staged = s_nrec <= A_MAXREC;
+    if (T.staged) {
+        const double2* src = reinterpret_cast<const double2*>(A.rec + kbeg * RS);
+        double2* dst = reinterpret_cast<double2*>(sm);
+        const int n2 = s_nrec * (RS / 2);
+        for (int i = tid; i < n2; i += A_THREADS) dst[i] = __ldg(src + i);
+    }
+    T.recp = A.rec + (int64_t)RS * p;
+    const double4 o0v = ld4(T.recp);
+    const double4 o1v = ld4(T.recp + 4);
+    T.Rj0 = o0v.x; T.Rj1 = o0v.y; T.Rj2 = o0v.z; T.rinvj = o0v.w;
+    T.dxj = o1v.y; T.fcj = o1v.z; T.dfcj = o1v.w;
+    T.n = n;
+    T.jself = (int)(p - k0);
+    T.rk0 = T.staged ? sm + (k0 - kbeg) * RS : A.rec + k0 * RS;
+    // output staging has its own region behind the records: no CTA barrier after this one
+    T.wstage = sm + (size_t)A_MAXREC * RS + (size_t)(tid >> 5) * 32 * A_OUTLD;
+    T.plw = pl0 + (tid & ~31);
+    T.nrw = max(0, min(32, nrow - (tid & ~31)));
+    __syncthreads();
+    run_unit<D, U>(A, T);
 }
 
 // unit tables: consecutive c packed while the accumulators fit (<= 44 doubles)
@@ -253,8 +348,10 @@ template <int D>
 struct UnitTable {
     int n = 0;
     int c0[MAXD + 1] = {}, c1[MAXD + 1] = {};
+    int base[MAXD + 2] = {};      // first scratch column of every unit (unit sizes padded to even), [n] = row length
     constexpr UnitTable() {
         int c = 0;
+        int b = 0;
         while (c <= D) {
             int acc = 0, e = c;
             while (e <= D) {
@@ -263,18 +360,30 @@ struct UnitTable {
                 acc += add;
                 ++e;
             }
-            c0[n] = c; c1[n] = e - 1; ++n;
+            c0[n] = c; c1[n] = e - 1;
+            base[n] = b;
+            int nf = 0;
+            for (int cc = c; cc < e; ++cc) nf += nfun_c(D, cc);
+            b += (nf + 1) & ~1;
+            ++n;
             c = e;
         }
+        base[n] = b;
     }
 };
 
 template <int D, int U>
-void launch_units(ipf_ctx* ctx, const Fast3Args& A) {
-    constexpr UnitTable<D> T{};
-    if constexpr (U < T.n) {
+__device__ __forceinline__ void run_unit(const Fast3Args& A, const CtaState& T) {
+    constexpr UnitTable<D> UT{};
+    unit3b<D, UT.c0[U], UT.c1[U], UT.base[U]>(A, T);
+}
+
+template <int D, int U>
+void launch_moments_from(ipf_ctx* ctx, const Fast3Args& A) {
+    constexpr UnitTable<D> UT{};
+    if constexpr (U < UT.n) {
         const unsigned grid = (unsigned)((A.np + A_THREADS - 1) / A_THREADS);
-        auto kern = moments3b_unit_kernel<D, T.c0[U], T.c1[U]>;
+        auto kern = moments3b_kernel<D, U>;
         constexpr size_t smem = moments_smem_bytes<D>();
         static bool attr_set = false;
         if (!attr_set) {
@@ -283,16 +392,22 @@ void launch_units(ipf_ctx* ctx, const Fast3Args& A) {
         }
         kern<<<grid, A_THREADS, smem, ctx->stream>>>(A);
         ctx->launches++;
-        launch_units<D, U + 1>(ctx, A);
+        launch_moments_from<D, U + 1>(ctx, A);
     }
 }
 
-// ---- gather: S -> E / F / V rows ---------------------------------------------
+template <int D>
+void launch_moments(ipf_ctx* ctx, const Fast3Args& A) { launch_moments_from<D, 0>(ctx, A); }
+
+// ---- gather: S (reverse entries) + O (own sums) -> E / F / V rows ------------------
 struct Gather3Args {
     int64_t p0;               // first pair of the batch
     int64_t c0;               // first config (chunk-local) of the batch
+    int64_t s0;               // first site of the batch
     int nb;
-    const double* S;
+    const double* S;          // [np][nb][3]
+    const double* O;          // [nsites][nslot][nb][4]
+    int nslot;
     const int16_t* scol2col;  // [nb] scratch column -> local basis column
     const int64_t* atom_off;
     const int64_t* site_off;
@@ -318,27 +433,36 @@ __global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
     const int c = (int)(A.c0 + blockIdx.x);
     const int sc = blockIdx.y * 32 + (threadIdx.x & 31);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool live = sc < A.nb;
+    const bool live = sc < A.nb && A.scol2col[sc] >= 0;
+    const int scl = sc < A.nb ? sc : 0;
     const int64_t a0 = A.atom_off[c];
     const int nat = (int)(A.atom_off[c + 1] - a0);
     const int64_t rE = A.rowE[c], rF = A.rowF[c], rV = A.rowV[c];
-    const double4* S4 = reinterpret_cast<const double4*>(A.S) + (live ? sc : 0);
+    const double* S3 = A.S + 3 * scl;
+    const double4* O4 = reinterpret_cast<const double4*>(A.O) + scl;
     double e = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
     for (int ab = 0; ab < nat; ab += G_ACH) {
         const int na = min(G_ACH, nat - ab);
         for (int al = warp; al < na; al += G_WARPS) {
             const int64_t s = a0 + ab + al;
-            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
             const int64_t q0 = A.site_off[s], q1 = A.site_off[s + 1];
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            if (q1 > q0) {
+                // own sums: one slot per 32-row block of the producer that holds pairs of this atom
+                const int ns = (int)(((q1 - 1 - A.p0) >> 5) - ((q0 - A.p0) >> 5)) + 1;
+                for (int sl = 0; sl < ns; ++sl) {
+                    const double4 o = O4[((s - A.s0) * A.nslot + sl) * A.nb];
+                    f0 += o.x; f1 += o.y; f2 += o.z; e += o.w;
+                }
+            }
 #pragma unroll 4
             for (int64_t p = q0; p < q1; ++p) {
-                const double4 g = S4[(p - A.p0) * A.nb];
-                const double4 h = S4[((int64_t)A.prev[p] - A.p0) * A.nb];
+                const double* h = S3 + ((int64_t)A.prev[p] - A.p0) * A.nb * 3;
+                const double hx = __ldg(h), hy = __ldg(h + 1), hz = __ldg(h + 2);
                 const double r0 = A.pR[3 * p], r1 = A.pR[3 * p + 1], r2 = A.pR[3 * p + 2];
-                f0 += g.x - h.x; f1 += g.y - h.y; f2 += g.z - h.z;
-                e += g.w;
-                v0 -= g.x * r0; v1 -= g.y * r1; v2 -= g.z * r2;      // xx, yy, zz
-                v3 -= g.z * r1; v4 -= g.z * r0; v5 -= g.y * r0;      // zy, zx, yx
+                f0 -= hx; f1 -= hy; f2 -= hz;
+                v0 += hx * r0; v1 += hy * r1; v2 += hz * r2;      // xx, yy, zz
+                v3 += hz * r1; v4 += hz * r0; v5 += hy * r0;      // zy, zx, yx
             }
             Fs[lane * G_LDT + 3 * al] = f0;
             Fs[lane * G_LDT + 3 * al + 1] = f1;
@@ -348,9 +472,10 @@ __global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
         if (rF) {
             const int nrow = 3 * na;
             for (int cl = 0; cl < 32; ++cl) {
-                const int scl = blockIdx.y * 32 + cl;
-                if (scl >= A.nb) break;
-                double* colp = A.Psi + (size_t)(A.col0 + A.scol2col[scl]) * A.ld + (rF - 1) + 3 * ab;
+                const int scc = blockIdx.y * 32 + cl;
+                if (scc >= A.nb) break;
+                if (A.scol2col[scc] < 0) continue;
+                double* colp = A.Psi + (size_t)(A.col0 + A.scol2col[scc]) * A.ld + (rF - 1) + 3 * ab;
                 for (int r = threadIdx.x; r < nrow; r += G_THREADS) colp[r] = Fs[cl * G_LDT + r];
             }
         }
@@ -372,6 +497,23 @@ __global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
     }
 }
 
+template <int D>
+void unit_layout_t(std::vector<int>& ub, std::vector<int>& uc0, std::vector<int>& uc1, int& nbs) {
+    constexpr UnitTable<D> T{};
+    for (int u = 0; u < T.n; ++u) { ub.push_back(T.base[u]); uc0.push_back(T.c0[u]); uc1.push_back(T.c1[u]); }
+    nbs = T.base[T.n];
+}
+
+void unit_layout(int D, std::vector<int>& ub, std::vector<int>& uc0, std::vector<int>& uc1, int& nbs) {
+    switch (D) {
+#define IPF_CASE(DD) case DD: unit_layout_t<DD>(ub, uc0, uc1, nbs); break;
+        IPF_CASE(2) IPF_CASE(3) IPF_CASE(4) IPF_CASE(5) IPF_CASE(6) IPF_CASE(7) IPF_CASE(8)
+        IPF_CASE(9) IPF_CASE(10) IPF_CASE(11) IPF_CASE(12) IPF_CASE(13) IPF_CASE(14)
+#undef IPF_CASE
+        default: nbs = 0;
+    }
+}
+
 }  // namespace
 
 // Returns IPF_OK and sets *handled when the block is the canonical nbpolys(3, desc, D) basis
@@ -380,6 +522,7 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
                           ipf_matrix* Psi, bool* handled) {
     *handled = false;
     if (blk.N != 3 || blk.maxdeg > MAXD) return IPF_OK;
+    if (nl.max_nbrs > A_THREADS) return IPF_OK;      // a site must not span more than two producer CTAs
     // ---- canonical check + column map
     int D = 0;
     for (int m = 0; m < blk.nmono; ++m) {
@@ -414,13 +557,24 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     const double* rec = nullptr;
     int rs = 0;
     IPF_CHECK(ipf_pair_records(ctx, blk, nl, &rec, &rs));
-    // scratch column order = the order unit3b emits the functions: c ascending, then a, then b
+    // scratch column order = the order the unit kernels emit the functions (c ascending, then a, then b),
+    // every unit padded to an even number of columns (-1 = padding)
     std::vector<int16_t> h_s2c;
-    for (int c = 0; c <= D; ++c)
-        for (int a = 0; a <= (D - c) / 2; ++a)
-            for (int b = a; b <= D - c - a; ++b)
-                if (a + b + c > 0) h_s2c.push_back(colmap[cmidx(c, a, b)]);
-    if ((int)h_s2c.size() != blk.nb) return ipf_set_error(ctx, IPF_EINVAL, "internal: 3-body column count mismatch");
+    int nbs = 0;
+    {
+        std::vector<int> ub, uc0, uc1;
+        unit_layout(D, ub, uc0, uc1, nbs);
+        h_s2c.assign(nbs, -1);
+        int nreal = 0;
+        for (size_t u = 0; u < uc0.size(); ++u) {
+            int sc = ub[u];
+            for (int c = uc0[u]; c <= uc1[u]; ++c)
+                for (int a = 0; a <= (D - c) / 2; ++a)
+                    for (int b = a; b <= D - c - a; ++b)
+                        if (a + b + c > 0) { h_s2c[sc++] = colmap[cmidx(c, a, b)]; ++nreal; }
+        }
+        if (nreal != blk.nb) return ipf_set_error(ctx, IPF_EINVAL, "internal: 3-body column count mismatch");
+    }
     ABuf<int16_t> s2c;
     IPF_CHECK(s2c.alloc(ctx, h_s2c.size()));
     IPF_CUDA(ctx, cudaMemcpyAsync(s2c.p, h_s2c.data(), sizeof(int16_t) * h_s2c.size(), cudaMemcpyHostToDevice, st));
@@ -429,11 +583,28 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     // batches of whole configurations; S (32 B per pair and function) lives in HBM, double buffered:
     // the gather of batch i (HBM bound, stream2) overlaps the moments of batch i+1 (FP64 bound, stream)
     const size_t s_budget = (size_t)3 << 30;
-    const int64_t max_pairs_batch = std::max<int64_t>(nl.maxpairs_cfg, (int64_t)(s_budget / (32 * (size_t)blk.nb)));
-    const size_t s_bytes = (size_t)32 * blk.nb * (size_t)std::min<int64_t>(max_pairs_batch, nl.npairs);
+    const int64_t max_pairs_batch = std::max<int64_t>(nl.maxpairs_cfg, (int64_t)(s_budget / (24 * (size_t)nbs)));
+    const size_t s_bytes = (size_t)24 * nbs * (size_t)std::min<int64_t>(max_pairs_batch, nl.npairs);
+    // own-sum buffer: sites of a batch <= pairs of a batch (every site of the fast path has >= 0 pairs;
+    // sized by the largest batch in sites)
+    int64_t max_sites_batch = 0;
+    {
+        int64_t c0 = 0;
+        while (c0 < ch.ncfg) {
+            int64_t c1 = c0 + 1;
+            while (c1 < ch.ncfg && nl.h_cfg_pair_off[c1 + 1] - nl.h_cfg_pair_off[c0] <= max_pairs_batch) ++c1;
+            max_sites_batch = std::max(max_sites_batch, ch.h_atom_off[c1] - ch.h_atom_off[c0]);
+            c0 = c1;
+        }
+    }
+    const int nslot = (nl.max_nbrs + 31) / 32 + 1;
+    const size_t o_bytes = (size_t)32 * nslot * nbs * (size_t)max_sites_batch;
     void* Sbuf[2] = {nullptr, nullptr};
+    void* Obuf[2] = {nullptr, nullptr};
     IPF_CHECK(ipf_scratch(ctx, 3, s_bytes, &Sbuf[0]));
     IPF_CHECK(ipf_scratch(ctx, 4, s_bytes, &Sbuf[1]));
+    IPF_CHECK(ipf_scratch(ctx, 5, o_bytes, &Obuf[0]));
+    IPF_CHECK(ipf_scratch(ctx, 0, o_bytes, &Obuf[1]));
     if (ctx->profiling && !nl.h_site_off.empty()) {
         double tot = 0.0;
         for (int64_t s = 0; s < nl.nsites; ++s) {
@@ -450,7 +621,8 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         IPF_CUDA(ctx, cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes));
         attr_set = true;
     }
-    cudaStream_t st2 = ctx->stream2;
+    static const bool no_overlap = getenv("IPF_NO_OVERLAP") != nullptr;
+    cudaStream_t st2 = no_overlap ? ctx->stream : ctx->stream2;
     cudaEvent_t gathered[2] = {nullptr, nullptr};    // gather of the batch that last used buffer b
     // everything queued so far on the main stream (neighbour list, Psi zero fill, ...) precedes the gathers
     int64_t c0 = 0;
@@ -462,7 +634,9 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         Fast3Args A;
         A.p0 = nl.h_cfg_pair_off[c0]; A.np = nl.h_cfg_pair_off[c1] - A.p0;
         A.rec = rec; A.site_off = nl.site_off.p; A.atom_off = ch.atom_off.p;
-        A.psite = nl.psite.p; A.nb = blk.nb; A.S = (double*)Sbuf[buf];
+        A.psite = nl.psite.p; A.nb = nbs; A.S = (double*)Sbuf[buf];
+        A.O = (double*)Obuf[buf]; A.s0 = ch.h_atom_off[c0]; A.nslot = nslot;
+        A.pbeg = nl.pbeg.p; A.pcnt = nl.pcnt.p;
         if (gathered[buf]) {      // buffer reuse: wait for the gather that read it
             IPF_CUDA(ctx, cudaStreamWaitEvent(st, gathered[buf], 0));
             cudaEventDestroy(gathered[buf]);
@@ -471,7 +645,7 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         if (A.np > 0) {
             ProfScope prof_(ctx, "site_deriv_3b");
             switch (D) {
-#define IPF_CASE(DD) case DD: launch_units<DD, 0>(ctx, A); break;
+#define IPF_CASE(DD) case DD: launch_moments<DD>(ctx, A); break;
                 IPF_CASE(2) IPF_CASE(3) IPF_CASE(4) IPF_CASE(5) IPF_CASE(6) IPF_CASE(7) IPF_CASE(8)
                 IPF_CASE(9) IPF_CASE(10) IPF_CASE(11) IPF_CASE(12) IPF_CASE(13) IPF_CASE(14)
 #undef IPF_CASE
@@ -484,13 +658,14 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         IPF_CUDA(ctx, cudaStreamWaitEvent(st2, produced, 0));
         cudaEventDestroy(produced);
         Gather3Args G;
-        G.p0 = A.p0; G.c0 = c0; G.nb = blk.nb; G.S = (const double*)Sbuf[buf]; G.scol2col = s2c.p;
+        G.p0 = A.p0; G.c0 = c0; G.s0 = A.s0; G.nb = nbs; G.S = (const double*)Sbuf[buf];
+        G.O = (const double*)Obuf[buf]; G.nslot = nslot; G.scol2col = s2c.p;
         G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
         G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;
         G.Psi = Psi->d; G.ld = Psi->ld; G.col0 = blk.col0;
         {
             ProfScope prof_(ctx, "gather_3b", st2);
-            dim3 grid((unsigned)(c1 - c0), (unsigned)((blk.nb + 31) / 32));
+            dim3 grid((unsigned)(c1 - c0), (unsigned)((nbs + 31) / 32));
             gather3b_kernel<<<grid, G_THREADS, g_bytes, st2>>>(G);
             ctx->launches++;
         }

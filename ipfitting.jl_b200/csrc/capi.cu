@@ -22,6 +22,7 @@ int ipf_scratch(ipf_ctx* ctx, int slot, size_t bytes, void** out) {
     if (ctx->scratch_bytes[slot] < bytes) {
         if (ctx->scratch[slot]) {
             IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->stream2) IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream2));
             cudaFree(ctx->scratch[slot]);
             ctx->scratch[slot] = nullptr;
             ctx->scratch_bytes[slot] = 0;

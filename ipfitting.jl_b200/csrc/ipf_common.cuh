@@ -141,11 +141,14 @@ struct NeighList {
     int64_t nsites = 0;       // atoms in the chunk
     int64_t npairs = 0;
     int32_t maxpairs_cfg = 0; // max pairs of one config
+    int32_t max_nbrs = 0;     // max neighbours of one site
     double rcut = 0;
     ABuf<int64_t> site_off;       // [nsites+1] pair offsets (chunk-global)
     ABuf<int32_t> pi;             // [npairs] centre atom, local index in its config
     ABuf<int32_t> pj;             // [npairs] neighbour atom, local index in its config
     ABuf<int32_t> psite;          // [npairs] centre atom, chunk-global site index
+    ABuf<int64_t> pbeg;           // [npairs] first pair of the centre atom's list (= site_off[psite])
+    ABuf<int32_t> pcnt;           // [npairs] length of that list
     ABuf<int32_t> pS;             // [npairs*3] image shift
     ABuf<double> pR;              // [npairs*3] bond vector R_ij = X_j + S C - X_i
     ABuf<int32_t> prev;           // [npairs] chunk-global index of the reverse pair (j,i,-S)

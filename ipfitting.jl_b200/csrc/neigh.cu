@@ -118,7 +118,7 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
                                 const int32_t* __restrict__ cell_atoms, const int32_t* __restrict__ atom_cell,
                                 const int32_t* __restrict__ atom_wrap, int64_t* __restrict__ counts,
                                 const int64_t* __restrict__ site_off, unsigned long long* __restrict__ keys,
-                                double* __restrict__ Rtmp) {
+                                double* __restrict__ Rtmp, unsigned long long* __restrict__ maxn) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsites) return;
     const int c = site_cfg[s];
@@ -164,7 +164,7 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
             }
         }
     }
-    if (!FILL) counts[s] = n;
+    if (!FILL) { counts[s] = n; atomicMax(maxn, (unsigned long long)n); }
 }
 
 __global__ void cfg_offsets_kernel(int64_t ncfg, const int64_t* __restrict__ atom_off,
@@ -178,6 +178,7 @@ __global__ void nl_sort_kernel(int64_t npairs, int64_t nsites, const int64_t* __
                                const int32_t* __restrict__ site_cfg, const int64_t* __restrict__ atom_off,
                                const unsigned long long* __restrict__ keys, const double* __restrict__ Rtmp,
                                int32_t* __restrict__ pi, int32_t* __restrict__ pj, int32_t* __restrict__ psite,
+                               int64_t* __restrict__ pbeg, int32_t* __restrict__ pcnt,
                                int32_t* __restrict__ pS, double* __restrict__ pR,
                                unsigned long long* __restrict__ keys_sorted) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,6 +195,8 @@ __global__ void nl_sort_kernel(int64_t npairs, int64_t nsites, const int64_t* __
     pi[dst] = (int32_t)(s - atom_off[site_cfg[s]]);
     pj[dst] = (int32_t)(k >> 32);
     psite[dst] = (int32_t)s;
+    pbeg[dst] = o0;
+    pcnt[dst] = (int32_t)(o1 - o0);
     pS[3 * dst] = (int)((k >> 20) & 1023) - SHIFT_BIAS;
     pS[3 * dst + 1] = (int)((k >> 10) & 1023) - SHIFT_BIAS;
     pS[3 * dst + 2] = (int)(k & 1023) - SHIFT_BIAS;
@@ -237,14 +240,15 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     nl.rcut = rcut;
     nl.npairs = 0;
     nl.maxpairs_cfg = 0;
-    nl.h_cfg_pair_off.assign(ncfg + 1, 0);
+    nl.h_cfg_pair_off.assign(ncfg + 2, 0);
     nl.h_site_off.clear();
+    nl.max_nbrs = 0;
     cudaStream_t st = ctx->stream;
     IPF_CHECK(nl.site_off.alloc(ctx, nsites + 1));
-    IPF_CHECK(nl.cfg_pair_off.alloc(ctx, ncfg + 1));
+    IPF_CHECK(nl.cfg_pair_off.alloc(ctx, ncfg + 2));     // [ncfg+1] = max neighbours of one site
     if (nsites == 0) {
         IPF_CUDA(ctx, cudaMemsetAsync(nl.site_off.p, 0, sizeof(int64_t), st));
-        IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p, 0, sizeof(int64_t) * (ncfg + 1), st));
+        IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p, 0, sizeof(int64_t) * (ncfg + 2), st));
         return IPF_OK;
     }
     ProfScope prof_(ctx, "neighbour_list");
@@ -264,9 +268,11 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     const double rc2 = rcut * rcut;
     const unsigned nb_sites = (unsigned)((nsites + 127) / 128);
     IPF_CUDA(ctx, cudaMemsetAsync(counts.p + nsites, 0, sizeof(int64_t), st));
+    IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p + ncfg + 1, 0, sizeof(int64_t), st));
     nl_pairs_kernel<false><<<nb_sites, 128, 0, st>>>(nsites, site_cfg, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
                                                      grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
-                                                     counts.p, nullptr, nullptr, nullptr);
+                                                     counts.p, nullptr, nullptr, nullptr,
+                                                     (unsigned long long*)(nl.cfg_pair_off.p + ncfg + 1));
     ctx->launches++;
     size_t tmp_bytes = 0;
     cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st);
@@ -277,7 +283,7 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     // per-config pair offsets (ncfg+1 values) to the host; gives the total too
     cfg_offsets_kernel<<<(unsigned)((ncfg + 256) / 256), 256, 0, st>>>(ncfg, ch.atom_off.p, nl.site_off.p, nl.cfg_pair_off.p);
     ctx->launches++;
-    IPF_CUDA(ctx, cudaMemcpyAsync(nl.h_cfg_pair_off.data(), nl.cfg_pair_off.p, sizeof(int64_t) * (ncfg + 1),
+    IPF_CUDA(ctx, cudaMemcpyAsync(nl.h_cfg_pair_off.data(), nl.cfg_pair_off.p, sizeof(int64_t) * (ncfg + 2),
                                   cudaMemcpyDeviceToHost, st));
     if (ctx->profiling) {
         nl.h_site_off.assign(nsites + 1, 0);
@@ -286,6 +292,7 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     }
     IPF_CUDA(ctx, cudaStreamSynchronize(st));
     const int64_t npairs = nl.h_cfg_pair_off[ncfg];
+    nl.max_nbrs = (int32_t)nl.h_cfg_pair_off[ncfg + 1];
     nl.npairs = npairs;
     int64_t mx = 0;
     for (int64_t c = 0; c < ncfg; ++c) mx = std::max<int64_t>(mx, nl.h_cfg_pair_off[c + 1] - nl.h_cfg_pair_off[c]);
@@ -293,6 +300,8 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     IPF_CHECK(nl.pi.alloc(ctx, npairs));
     IPF_CHECK(nl.pj.alloc(ctx, npairs));
     IPF_CHECK(nl.psite.alloc(ctx, npairs));
+    IPF_CHECK(nl.pbeg.alloc(ctx, npairs));
+    IPF_CHECK(nl.pcnt.alloc(ctx, npairs));
     IPF_CHECK(nl.pS.alloc(ctx, 3 * npairs));
     IPF_CHECK(nl.pR.alloc(ctx, 3 * npairs));
     IPF_CHECK(nl.prev.alloc(ctx, npairs));
@@ -304,10 +313,10 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     IPF_CHECK(Rtmp.alloc(ctx, 3 * npairs));
     nl_pairs_kernel<true><<<nb_sites, 128, 0, st>>>(nsites, site_cfg, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
                                                     grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
-                                                    nullptr, nl.site_off.p, keys.p, Rtmp.p);
+                                                    nullptr, nl.site_off.p, keys.p, Rtmp.p, nullptr);
     const unsigned nb_pairs = (unsigned)((npairs + 255) / 256);
     nl_sort_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nsites, nl.site_off.p, site_cfg, ch.atom_off.p, keys.p,
-                                             Rtmp.p, nl.pi.p, nl.pj.p, nl.psite.p, nl.pS.p, nl.pR.p, keys_sorted.p);
+                                             Rtmp.p, nl.pi.p, nl.pj.p, nl.psite.p, nl.pbeg.p, nl.pcnt.p, nl.pS.p, nl.pR.p, keys_sorted.p);
     nl_reverse_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nl.site_off.p, site_cfg, ch.atom_off.p, nsites,
                                                 nl.pi.p, nl.pj.p, nl.pS.p, keys_sorted.p, nl.prev.p);
     ctx->launches += 3;
