@@ -250,8 +250,9 @@ def run_ours(args):
             c = np.empty(ncols)
             ssr, ssy = C.c_double(), C.c_double()
             ctx.check(lib.ipf_solve_finish(ctx.h, h, _capi.ptr(c, C.c_double), None, C.byref(ssr), C.byref(ssy)))
-            npass = C.c_int32()
-            lib.ipf_solve_info(h, C.byref(npass), None, None, None, None)
+            npass, defect, shift = C.c_int32(), C.c_double(), C.c_double()
+            lib.ipf_solve_info(h, C.byref(npass), C.byref(defect), C.byref(shift), None, None)
+            solve_dev.info = {"passes": npass.value, "orth_defect_last_pass": defect.value, "shift": shift.value}
         finally:
             lib.ipf_solve_destroy(ctx.h, h)
         return c, ssr.value, ssy.value, npass.value
@@ -396,7 +397,8 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks.summary(), "roofline": roofline,
             "roofline_other": cands[1:], "kernels": kernels,
             "cpu_baseline": cpu, "fit": {"rel_rms": math.sqrt(ssr / ssy) if comm is None else rel_e2e,
-                                         "coeff_diff_dev_vs_e2e": float(np.linalg.norm(c_dev - c_e2e) / np.linalg.norm(c_e2e))}}
+                                         "coeff_diff_dev_vs_e2e": float(np.linalg.norm(c_dev - c_e2e) / np.linalg.norm(c_e2e)),
+                                         "solve_info": getattr(solve_dev, "info", None)}}
     print(json.dumps(line), flush=True)
     if comm is not None:
         dist.barrier()

@@ -32,6 +32,9 @@ struct ipf_solver {
     double* Rtot = nullptr;         // n x n  upper, product of the passes
     double* Rtmp = nullptr;         // n x n
     double* vec = nullptr;          // [n] work vector
+    double* dscale = nullptr;       // [n] column equilibration of the current pass
+    double* work = nullptr;         // [4*n1] small vectors of the final solve
+    double* Lt = nullptr;           // n x n transpose of the final L
     double* dinv = nullptr;         // [n] or null
     int* flag = nullptr;            // device status word
     double* red = nullptr;          // reduction scratch
@@ -111,11 +114,30 @@ __global__ void chol_lower_kernel(double* __restrict__ L, int n, int* __restrict
     }
 }
 
-__global__ void copy_shift_kernel(const double* __restrict__ G, int n1, double* __restrict__ L, int n, double shift) {
+// column equilibration: d[i] = 1/sqrt(G_ii).  Cholesky of D G D (unit diagonal) breaks down only when the
+// EQUILIBRATED matrix is numerically singular, and a shift relative to 1 does not swamp small columns.
+__global__ void equil_kernel(const double* __restrict__ G, int n1, int n, double* __restrict__ d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double g = G[(size_t)i * n1 + i];
+    d[i] = (g > 0.0 && isfinite(g)) ? rsqrt(g) : 1.0;
+}
+
+// L <- D G D + shift I
+__global__ void copy_shift_kernel(const double* __restrict__ G, int n1, double* __restrict__ L, int n,
+                                  const double* __restrict__ d, double shift) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)n * n) return;
     const int r = (int)(e % n), c = (int)(e / n);
-    L[e] = G[(size_t)c * n1 + r] + (r == c ? shift : 0.0);
+    L[e] = G[(size_t)c * n1 + r] * d[r] * d[c] + (r == c ? shift : 0.0);
+}
+
+// L <- D^-1 L  (chol(D G D) = L~  =>  G = (D^-1 L~)(D^-1 L~)^T)
+__global__ void unscale_rows_kernel(double* __restrict__ L, int n, const double* __restrict__ d) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * n) return;
+    const int r = (int)(e % n);
+    L[e] /= d[r];
 }
 
 // |G[0:n,0:n] - I|_F^2 and max diagonal; out[0] = frob^2, out[1] = maxdiag (single CTA, deterministic)
@@ -290,6 +312,21 @@ __global__ void sum_pairs_kernel(const double* __restrict__ partial, int64_t nbl
     }
 }
 
+// g = z - G[0:n,0:n] x   (z = column n of G); then x is refined by G^-1 g
+__global__ void normal_residual_kernel(const double* __restrict__ G, int n1, int n, const double* __restrict__ x,
+                                       double* __restrict__ g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = G[(size_t)n * n1 + i];
+    for (int j = 0; j < n; ++j) acc -= G[(size_t)j * n1 + i] * x[j];
+    g[i] = acc;
+}
+
+__global__ void add_vec_kernel(double* __restrict__ x, const double* __restrict__ d, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) x[k] += d[k];
+}
+
 __global__ void scale_vec_kernel(double* __restrict__ c, const double* __restrict__ d, int n) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k < n) c[k] *= d[k];
@@ -355,7 +392,7 @@ void free_solve(ipf_solver* S) {
     if (!S) return;
     if (!S->pooled)
     for (void* p : {(void*)S->A, (void*)S->yorig, (void*)S->G, (void*)S->L, (void*)S->Rtot, (void*)S->Rtmp,
-                    (void*)S->vec, (void*)S->dinv, (void*)S->flag, (void*)S->red})
+                    (void*)S->vec, (void*)S->dscale, (void*)S->work, (void*)S->Lt, (void*)S->dinv, (void*)S->flag, (void*)S->red})
         if (p) cudaFree(p);
     delete S;
 }
@@ -409,6 +446,9 @@ int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* d
         take(sizeof(double) * nn, (void**)&S->Rtot);
         take(sizeof(double) * nn, (void**)&S->Rtmp);
         take(sizeof(double) * S->n1, (void**)&S->vec);
+        take(sizeof(double) * S->n1, (void**)&S->dscale);
+        take(sizeof(double) * 4 * S->n1, (void**)&S->work);
+        take(sizeof(double) * nn, (void**)&S->Lt);
         take(sizeof(int) * 4, (void**)&S->flag);
         take(sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8), (void**)&S->red);
         if (dDinv) take(sizeof(double) * n64, (void**)&S->dinv);
@@ -421,6 +461,9 @@ int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* d
             (e = cudaMalloc((void**)&S->Rtot, sizeof(double) * nn)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->Rtmp, sizeof(double) * nn)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->vec, sizeof(double) * S->n1)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->dscale, sizeof(double) * S->n1)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->work, sizeof(double) * 4 * S->n1)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->Lt, sizeof(double) * nn)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->flag, sizeof(int) * 4)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->red, sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8))) != cudaSuccess ||
             (dDinv && (e = cudaMalloc((void**)&S->dinv, sizeof(double) * n64)) != cudaSuccess))
@@ -535,15 +578,17 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     IPF_CUDA(ctx, cudaStreamSynchronize(st));
     if (!std::isfinite(h[0]) || !std::isfinite(h[1]))
         return ipf_set_error(ctx, IPF_ESINGULAR, "ipf_solve_factor: non-finite Gram matrix");
-    const double defect = std::sqrt(h[0]), maxdiag = h[1];
-    const bool final_pass = S->pass >= 1 && defect <= 0.1;
+    const double defect = std::sqrt(h[0]);
+    bool final_pass = S->pass >= 1 && defect <= 0.1;
     if (S->pass >= 1) S->defect = defect;
     if (!final_pass && S->pass >= 6)
         return ipf_set_error(ctx, IPF_ESINGULAR, "CholeskyQR did not reach orthogonality in %d passes (defect %.3e)", S->pass, defect);
     // Cholesky with escalating shift
     double shift = 0.0;
+    equil_kernel<<<(n + 255) / 256, 256, 0, st>>>(S->G, n1, n, S->dscale);
+    ctx->launches++;
     for (int attempt = 0;; ++attempt) {
-        copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, shift);
+        copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, S->dscale, shift);
         IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
         { ProfScope prof_(ctx, "cholesky");
         chol_lower_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->flag); }
@@ -555,8 +600,22 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         if (!hf[1]) break;
         if (attempt >= 12)
             return ipf_set_error(ctx, IPF_ESINGULAR, "Cholesky of the Gram matrix failed at column %d even with shift %.3e", hf[2], shift);
-        shift = (shift == 0.0) ? 1e-15 * (double)n * maxdiag : shift * 100.0;
+        shift = (shift == 0.0) ? 1e-15 * (double)n : shift * 100.0;      // relative to the unit diagonal
     }
+    if (!final_pass && S->pass >= 1 && shift == 0.0) {
+        // A is not orthonormal yet, but if the EQUILIBRATED Gram matrix is well conditioned the normal
+        // equations of this pass (plus one refinement step in finish) are as accurate as another pass:
+        // estimate cond(D G D) from the diagonal of its Cholesky factor
+        std::vector<double> hd((size_t)n);
+        IPF_CUDA(ctx, cudaMemcpy2DAsync(hd.data(), sizeof(double), S->L, sizeof(double) * (size_t)(n + 1), sizeof(double), n,
+                                        cudaMemcpyDeviceToHost, st));
+        IPF_CUDA(ctx, cudaStreamSynchronize(st));
+        double lo = hd[0], hi = hd[0];
+        for (double v : hd) { lo = std::min(lo, v); hi = std::max(hi, v); }
+        if (lo > 0.0 && (hi / lo) * (hi / lo) <= 1e3) final_pass = true;
+    }
+    unscale_rows_kernel<<<nblk, 256, 0, st>>>(S->L, n, S->dscale);
+    ctx->launches++;
     S->shift = std::max(S->shift, shift);
     // Rtot <- L^T Rtot
     rprod_kernel<<<nblk, 256, 0, st>>>(S->L, S->pass == 0 ? nullptr : S->Rtot, S->Rtmp, n);
@@ -601,24 +660,31 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int n = S->n;
-    // vec holds w = L^-1 z.  Coefficients in the current (orthonormalised) basis: cc = L^-T w.
-    // L^T is the upper factor: reuse trsv mode 1 on L^T stored as Rtmp = transpose(L).
-    // rprod with Rold = null writes L^T into Rtmp.
+    // vec holds w = L^-1 z.  Coefficients in the basis of the current A: cc = L^-T w, refined once against
+    // the normal equations G cc = z of this pass (G is the exact Gram matrix of the current A).
     const size_t nn = (size_t)n * n;
     const unsigned nblk = (unsigned)((nn + 255) / 256);
-    rprod_kernel<<<nblk, 256, 0, st>>>(S->L, nullptr, S->Rtmp, n);
-    double* cc = S->G;     // Gram storage is free now: [0..n) = cc, [n1..n1+n) = final c
+    const unsigned nvb = (unsigned)((n + 255) / 256);
+    rprod_kernel<<<nblk, 256, 0, st>>>(S->L, nullptr, S->Lt, n);          // Lt = L^T
+    double* cc = S->work;
+    double* g = S->work + S->n1;
+    double* cf = S->work + 2 * S->n1;
     IPF_CUDA(ctx, cudaMemcpyAsync(cc, S->vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtmp, n, cc, 1);
+    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Lt, n, cc, 1);
+    normal_residual_kernel<<<nvb, 256, 0, st>>>(S->G, S->n1, n, cc, g);
+    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, g, 0);
+    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Lt, n, g, 1);
+    add_vec_kernel<<<nvb, 256, 0, st>>>(cc, g, n);
     const int64_t nb = (S->Mpad + 255) / 256;
     { ProfScope prof_(ctx, "residual");
     residual_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, n, cc, S->red + 8); }
     sum_pairs_kernel<<<1, 1024, 0, st>>>(S->red + 8, nb, S->red);
-    // solution in the original (scaled) basis: c = Rtot^-1 w
-    double* cf = S->G + S->n1;
-    IPF_CUDA(ctx, cudaMemcpyAsync(cf, S->vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtot, n, cf, 1);
+    // solution in the original (scaled) basis: A_p = A_0 Rprev^-1  =>  c = Rprev^-1 cc
+    // (Rtmp holds Rprev: factor swapped it out when it formed Rtot = L^T Rprev)
+    IPF_CUDA(ctx, cudaMemcpyAsync(cf, cc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtmp, n, cf, 1);
     if (S->dinv) scale_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(cf, S->dinv, n);
+    ctx->launches += 4;
     ctx->launches += 6;
     double h[2];
     IPF_CUDA(ctx, cudaMemcpyAsync(c, cf, sizeof(double) * n, cudaMemcpyDeviceToHost, st));

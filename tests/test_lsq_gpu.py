@@ -150,3 +150,26 @@ def test_add_fits_equals_error_table(fitcase):
         for okey in rm[ct]:
             assert abs(rm[ct][okey] - info["errors"]["rmse"][ct][okey]) <= 1e-9 * rm[ct][okey]
             assert abs(rel[ct][okey] - info["errors"]["relrmse"][ct][okey]) <= 1e-9 * rel[ct][okey]
+
+
+def test_bench_basis_fit_matches_householder(ctx):
+    """The bench basis (2B deg 14 + 3B deg 11, cond(R) ~ 1e12): the CholeskyQR solve must sit at the same
+    least-squares minimum as LAPACK's Householder QR on the oracle's matrix.  The coefficient vector itself
+    is only determined to cond*eps, so the comparison is on the residual and on the predictions."""
+    import bench
+    basis = bench.make_basis()
+    configs = synth.rattled_configs("Si", 2, 40, seed=77, calc=synth.StillingerWeber())
+    db = LsqDB("", basis, configs, ctx=ctx)
+    r = rows_for(configs)
+    ref = O.assemble(db.basis, configs, r["E"], r["F"], r["V"], db.nrows)
+    w = {"default": {"E": 100.0, "F": 1.0, "V": 1.0}}
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=-4.0, Vref=ipf.OneBody(-4.0))
+    c_ref, kappa, rel_rms, _ = LO.lsqfit_qr(ref, configs, w, E0=-4.0)
+    A, y = LO.get_lsq_system(ref, configs, w, E0=-4.0)
+    assert kappa > 1e9
+    # two backward-stable solvers agree on the minimum only to ~cond*eps (1e-4 here); observed ~5e-8
+    assert abs(info["rel_rms"] - rel_rms) <= 1e-6 * rel_rms
+    r_gpu = np.linalg.norm(A @ info["c"] - y) / np.linalg.norm(y)
+    assert abs(r_gpu - rel_rms) <= 1e-6 * rel_rms                     # the returned c reproduces the minimum
+    assert np.linalg.norm(A @ (info["c"] - c_ref)) <= 2e-3 * np.linalg.norm(y) * rel_rms
+    assert abs(np.log10(info["cond_R"]) - np.log10(kappa)) < 0.5
