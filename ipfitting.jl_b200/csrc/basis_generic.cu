@@ -287,6 +287,15 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
 // [Rh(3), 1/r, x, dx, fc, dfc, x^0 .. x^maxdeg, pad]; rs is even (16-byte aligned records)
 int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec_out, int* rs_out) {
     const int64_t npairs = nl.npairs;
+    // reuse the records of the previous block when it had the same descriptor on the same neighbour list
+    // (e.g. nbpolys(2, D, 14) followed by nbpolys(3, D, 11)) and at least this block's degree
+    if (ctx->rec_nl == (const void*)&nl && ctx->rec_npairs == npairs && ctx->rec_transform == blk.transform &&
+        ctx->rec_a == blk.a && ctx->rec_r0 == blk.r0 && ctx->rec_rc1 == blk.rc1 && ctx->rec_rc2 == blk.rc2 &&
+        ctx->rec_maxdeg == blk.maxdeg && ctx->rec_ptr) {
+        *rec_out = ctx->rec_ptr;
+        *rs_out = ctx->rec_rs;
+        return IPF_OK;
+    }
     const int rs = (REC + blk.maxdeg + 1 + 1) & ~1;
     void* rec = nullptr;
     IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * rs * (size_t)(npairs + 1), &rec));
@@ -298,6 +307,9 @@ int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, con
     }
     *rec_out = (const double*)rec;
     *rs_out = rs;
+    ctx->rec_nl = (const void*)&nl; ctx->rec_npairs = npairs; ctx->rec_transform = blk.transform;
+    ctx->rec_a = blk.a; ctx->rec_r0 = blk.r0; ctx->rec_rc1 = blk.rc1; ctx->rec_rc2 = blk.rc2;
+    ctx->rec_maxdeg = blk.maxdeg; ctx->rec_ptr = (const double*)rec; ctx->rec_rs = rs;
     return IPF_OK;
 }
 

@@ -469,7 +469,8 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
             for (size_t k2 = k; k2 < basis->blocks.size(); ++k2)
                 if (basis->blocks[k2].rc2 == rc) {
                     bool handled = false;
-                    if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_3b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
+                    if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_2b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
+                    if (!ctx->force_generic && !handled) IPF_CHECK(ipf_assemble_block_3b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!handled) IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
                 }
         }

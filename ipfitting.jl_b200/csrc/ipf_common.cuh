@@ -28,6 +28,9 @@ struct ipf_ctx {
     Arena arena;                        // assembly temporaries (per chunk)
     Arena solve_arena;                  // workspaces of the (single) active solver
     int active_solvers = 0;
+    // pair-record cache key (see ipf_pair_records)
+    const void* rec_nl = nullptr; int64_t rec_npairs = -1; int rec_transform = -1, rec_maxdeg = -1, rec_rs = 0;
+    double rec_a = 0, rec_r0 = 0, rec_rc1 = 0, rec_rc2 = 0; const double* rec_ptr = nullptr;
     double* matrix_cache = nullptr;     // one recycled design-matrix allocation (avoids cudaMalloc/cudaFree per LsqDB)
     size_t matrix_cache_bytes = 0;
     cudaStream_t stream2 = nullptr;     // second stream: gather of batch n overlaps the moments of batch n+1
@@ -172,6 +175,8 @@ struct ChunkDev {
 int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighList& nl);
 int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
                                const NeighList& nl, ipf_matrix* Psi);
+int ipf_assemble_block_2b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                          ipf_matrix* Psi, bool* handled);
 int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
                           ipf_matrix* Psi, bool* handled);
 

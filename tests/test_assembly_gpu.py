@@ -107,3 +107,17 @@ def test_non_canonical_3b_uses_table_driven_path(ctx):
     _check(B, configs, ctx)
     assert ctx.profile_get("gather_3b")[1] == 0
     ctx.profile(False)
+
+
+def test_2b_specialised_equals_table_driven(ctx):
+    configs = synth.rattled_configs("Si", 2, 2, seed=60, calc=synth.StillingerWeber()) + \
+        synth.rattled_configs("W", 2, 2, seed=61, calc=synth.PairPotential(ipf.rnn("W")), vacancies=2)
+    B = ipf.nbpolys(2, si_desc(), 14)
+    fast = LsqDB("", B, configs, ctx=ctx).Psi
+    ctx.force_generic(True)
+    try:
+        slow = LsqDB("", B, configs, ctx=ctx).Psi
+    finally:
+        ctx.force_generic(False)
+    scale = np.abs(slow).max(axis=0)
+    assert (np.abs(fast - slow).max(axis=0) <= 1e-13 * scale).all()
