@@ -338,9 +338,9 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6553.9))
     fp64_peak, dmma_peak = 33.9, 37.1      # TFLOP/s, tools/peaks.cu on this pool (profiles/r01_fp64_peaks.jsonl)
     # (a) moments kernel: FP64 operations of the factorised algorithm (FMA = 2, MUL = ADD = 1), DESIGN.md §kernels
-    f_k = 5 + D + 9 * (D * (D + 1) // 2) + 2 * (D + 1)          # per ordered neighbour pair (j, k)
+    f_k = 15 + D + 7 * (D * (D + 1) // 2) + 2 * (D + 1)         # per ordered neighbour pair (j, k)
     n_single = int(np.sum(np.bincount(blk3.mono_b) == 1)); n_double = blk3.nb - n_single
-    f_comb = 33 * n_double + 25 * n_single                      # per own leg: combine moments into all functions
+    f_comb = 36 * n_double + 30 * n_single                      # per own leg: combine moments into all functions
     flops3 = ordered3 * f_k + pairs3 * f_comb
     ms3, n3 = prof["site_deriv_3b"]
     ach3 = flops3 / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0

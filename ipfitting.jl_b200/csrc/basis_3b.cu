@@ -4,13 +4,16 @@
 // p = (i, j)), but the sum over the second leg k is factorised.  Every monomial
 //     x_j^a x_k^b w_jk^c            (orbit partner: x_j^b x_k^a w_jk^c)
 // is (thread constant) x (function of k only), so per own leg only the MOMENTS
-//     Z_c[e] = sum_k fc_k x_k^e w_jk^c                 (scalar,  e + c <= D)
-//     U_c[e] = sum_k fc_k x_k^e w_jk^(c-1) Rhat_k      (vector,  c >= 1)
-// are accumulated in the k loop (5 FP64 instructions per (e, c) and k instead of
-// ~7 per basis function and k), and the basis functions (a <= b, c) follow from
+//     Z_c[e] = sum_k fc_k x_k^e w_jk^c                         (scalar,  e + c <= D)
+//     Q_c[e] = sum_k fc_k x_k^e w_jk^(c-1) (q1_k, q2_k)        (c >= 1)
+// are accumulated in the k loop, where (q1, q2) are the components of Rhat_k in an orthonormal
+// basis (e1, e2) of the plane perpendicular to Rhat_j: the Rhat_j component of the vector moment
+// sum_k .. Rhat_k equals Z_c[e] and cancels against the -w Rhat_j part of dw/dR_j, so only the
+// in-plane part is needed (4 FP64 instructions per (e, c) and k instead of ~7 per basis function).
+// The basis functions (a <= b, c) follow from
 //     S0 = x^a Z_c[b] + x^b Z_c[a]        S1 = a x^(a-1) Z_c[b] + b x^(b-1) Z_c[a]
-//     T  = c (x^a U_c[b] + x^b U_c[a]) - c S0 Rhat_j                 (x = x_j; a = b: one term)
-//     g_p = (fc_j' S0 + fc_j x_j' S1) Rhat_j + fc_j/r_j T,     e_p = fc_j S0 / 2.
+//     T  = c (x^a Q_c[b] + x^b Q_c[a])  (in-plane)                   (x = x_j; a = b: one term)
+//     g_p = (fc_j' S0 + fc_j x_j' S1) Rhat_j + fc_j/r_j (T1 e1 + T2 e2),     e_p = fc_j S0 / 2.
 // The (e, c) plane is cut into units of consecutive c (register budget); a CTA
 // runs one unit for 128 consecutive pairs.  Outputs are staged through shared memory in
 // groups of 8 functions: g_p goes to the HBM scratch S[pair][scol][3] (scol = unit-major
@@ -96,7 +99,8 @@ __host__ __device__ constexpr size_t moments_smem_bytes() {
 // the first neighbour (shared or global memory: the caller instantiates one copy per address space)
 template <int D, int C0, int C1, int NC, int EMAX>
 __device__ __forceinline__ void moment_loop(const double* __restrict__ rk, int n, int jself, double Rj0, double Rj1,
-                                            double Rj2, double (&Z)[NC][EMAX + 1], double (&U)[NC][EMAX + 1][3]) {
+                                            double Rj2, const double (&E1)[3], const double (&E2)[3],
+                                            double (&Z)[NC][EMAX + 1], double (&U)[NC][EMAX + 1][2]) {
     constexpr int RS = RecStride<D>::value;
     for (int kk = 0; kk < n; ++kk, rk += RS) {
         const double2 r01 = *reinterpret_cast<const double2*>(rk);
@@ -109,6 +113,8 @@ __device__ __forceinline__ void moment_loop(const double* __restrict__ rk, int n
             xe[e] = v.x; xe[e + 1] = v.y;
         }
         const double w = Rj0 * r01.x + Rj1 * r01.y + Rj2 * r23.x;
+        const double q1 = E1[0] * r01.x + E1[1] * r01.y + E1[2] * r23.x;      // in-plane components of Rhat_k
+        const double q2 = E2[0] * r01.x + E2[1] * r01.y + E2[2] * r23.x;
         const double fck = (kk == jself) ? 0.0 : a1.x;      // the own leg is not its own partner
         // wl[ci] = fck w^(c-1), c = C0 + ci  (unused for c = 0)
         double wl[NC];
@@ -134,9 +140,8 @@ __device__ __forceinline__ void moment_loop(const double* __restrict__ rk, int n
                         Z[ci][e] = fma(xe[e], fck, Z[ci][e]);
                     } else {
                         const double t = xe[e] * wl[ci];          // fck x^e w^(c-1)
-                        U[ci][e][0] = fma(t, r01.x, U[ci][e][0]);
-                        U[ci][e][1] = fma(t, r01.y, U[ci][e][1]);
-                        U[ci][e][2] = fma(t, r23.x, U[ci][e][2]);
+                        U[ci][e][0] = fma(t, q1, U[ci][e][0]);
+                        U[ci][e][1] = fma(t, q2, U[ci][e][1]);
                         Z[ci][e] = fma(t, w, Z[ci][e]);
                     }
                 }
@@ -188,14 +193,16 @@ __device__ __forceinline__ void flush_group(const Fast3Args& A, const double* __
     const bool vlive = lane < 3 * NG || (lane >= A_EOFF && lane < A_EOFF + NG);
     const int f = lane < A_EOFF ? lane / 3 : lane - A_EOFF;
     const int d = lane < A_EOFF ? lane - 3 * f : 3;
-    unsigned m = pmask;
-    while (m) {
-        const int r0 = __ffs(m) - 1;
-        m &= m - 1;
-        const int r1 = m ? (__ffs(m) - 1) : nrw;
-        const double acc = column_sum(wstage, r0, r1, lane);
-        const int orow = __shfl_sync(0xffffffffu, pout, r0);
-        if (vlive) A.O[((int64_t)orow * A.nb + sc0 + f) * 4 + d] = acc;
+    {
+        unsigned m = pmask;
+        while (m) {
+            const int r0 = __ffs(m) - 1;
+            m &= m - 1;
+            const int r1 = m ? (__ffs(m) - 1) : nrw;
+            const double acc = column_sum(wstage, r0, r1, lane);
+            const int orow = __shfl_sync(0xffffffffu, pout, r0);
+            if (vlive) A.O[((int64_t)orow * A.nb + sc0 + f) * 4 + d] = acc;
+        }
     }
     __syncwarp();
 }
@@ -203,7 +210,8 @@ __device__ __forceinline__ void flush_group(const Fast3Args& A, const double* __
 // state shared by all units of a CTA (computed once in the kernel prologue)
 struct CtaState {
     const double* recp;          // own pair record (global)
-    const double* rk0;           // record of the centre atom's first neighbour (shared or global memory)
+    int64_t rk_off;              // offset (doubles) of the centre atom's first neighbour record: in the staged
+                                 // window (shared memory) when `staged`, else in A.rec (global)
     bool staged;
     int n, jself;
     double Rj0, Rj1, Rj2, rinvj, dxj, fcj, dfcj;
@@ -223,14 +231,30 @@ __device__ __forceinline__ void unit3b(const Fast3Args& A, const CtaState& T) {
     const double Rj0 = T.Rj0, Rj1 = T.Rj1, Rj2 = T.Rj2, rinvj = T.rinvj, dxj = T.dxj, fcj = T.fcj, dfcj = T.dfcj;
     const double* recp = T.recp;
     double Z[NC][EMAX + 1];
-    double U[NC][EMAX + 1][3];
+    double U[NC][EMAX + 1][2];
 #pragma unroll
     for (int ci = 0; ci < NC; ++ci)
 #pragma unroll
-        for (int e = 0; e <= EMAX; ++e) { Z[ci][e] = 0.0; U[ci][e][0] = U[ci][e][1] = U[ci][e][2] = 0.0; }
+        for (int e = 0; e <= EMAX; ++e) { Z[ci][e] = 0.0; U[ci][e][0] = U[ci][e][1] = 0.0; }
+    // orthonormal basis (E1, E2) of the plane perpendicular to Rhat_j
+    double E1[3], E2[3];
+    {
+        const bool usex = fabs(Rj0) < 0.8;
+        // E1 = normalise(Rhat_j x axis), axis = x or y
+        double c0 = usex ? 0.0 : -Rj2, c1 = usex ? Rj2 : 0.0, c2 = usex ? -Rj1 : Rj0;
+        const double inv = rsqrt(c0 * c0 + c1 * c1 + c2 * c2);
+        E1[0] = c0 * inv; E1[1] = c1 * inv; E1[2] = c2 * inv;
+        E2[0] = Rj1 * E1[2] - Rj2 * E1[1];
+        E2[1] = Rj2 * E1[0] - Rj0 * E1[2];
+        E2[2] = Rj0 * E1[1] - Rj1 * E1[0];
+    }
 
-    if (T.staged) moment_loop<D, C0, C1, NC, EMAX>(T.rk0, T.n, T.jself, Rj0, Rj1, Rj2, Z, U);
-    else moment_loop<D, C0, C1, NC, EMAX>(T.rk0, T.n, T.jself, Rj0, Rj1, Rj2, Z, U);
+    {
+        extern __shared__ __align__(16) double sm_rec[];
+        // two instantiations so that the loop body uses LDS (shared) resp. LDG (global), not generic loads
+        if (T.staged) moment_loop<D, C0, C1, NC, EMAX>(sm_rec + T.rk_off, T.n, T.jself, Rj0, Rj1, Rj2, E1, E2, Z, U);
+        else moment_loop<D, C0, C1, NC, EMAX>(A.rec + T.rk_off, T.n, T.jself, Rj0, Rj1, Rj2, E1, E2, Z, U);
+    }
 
     // ---- combine into basis functions, staged through shared memory in groups of A_OUTG
     double X[EMAX + 1], dX[EMAX + 1];
@@ -260,23 +284,23 @@ __device__ __forceinline__ void unit3b(const Fast3Args& A, const CtaState& T) {
 #pragma unroll
             for (int b = a; b <= D - c - a; ++b) {
                 if (a + b + c == 0) continue;
-                double S0, S1, T0, T1, T2;
+                double S0, S1, T1, T2;
                 if (a == b) {
                     S0 = X[a] * Z[ci][a];
                     S1 = dX[a] * Z[ci][a];
-                    T0 = X[a] * U[ci][a][0]; T1 = X[a] * U[ci][a][1]; T2 = X[a] * U[ci][a][2];
+                    T1 = X[a] * U[ci][a][0]; T2 = X[a] * U[ci][a][1];
                 } else {
                     S0 = fma(X[a], Z[ci][b], X[b] * Z[ci][a]);
                     S1 = fma(dX[a], Z[ci][b], dX[b] * Z[ci][a]);
-                    T0 = fma(X[a], U[ci][b][0], X[b] * U[ci][a][0]);
-                    T1 = fma(X[a], U[ci][b][1], X[b] * U[ci][a][1]);
-                    T2 = fma(X[a], U[ci][b][2], X[b] * U[ci][a][2]);
+                    T1 = fma(X[a], U[ci][b][0], X[b] * U[ci][a][0]);
+                    T2 = fma(X[a], U[ci][b][1], X[b] * U[ci][a][1]);
                 }
-                const double radial = fma(dfcj - tc, S0, fdx * S1);      // coefficient of Rhat_j
+                const double radial = fma(dfcj, S0, fdx * S1);      // coefficient of Rhat_j
+                T1 *= tc; T2 *= tc;
                 const int slot = f % A_OUTG;
-                myrow[3 * slot] = fma(radial, Rj0, tc * T0);
-                myrow[3 * slot + 1] = fma(radial, Rj1, tc * T1);
-                myrow[3 * slot + 2] = fma(radial, Rj2, tc * T2);
+                myrow[3 * slot] = fma(radial, Rj0, fma(T1, E1[0], T2 * E2[0]));
+                myrow[3 * slot + 1] = fma(radial, Rj1, fma(T1, E1[1], T2 * E2[1]));
+                myrow[3 * slot + 2] = fma(radial, Rj2, fma(T1, E1[2], T2 * E2[2]));
                 myrow[A_EOFF + slot] = 0.5 * fcj * S0;
                 ++f;
                 if (f % A_OUTG == 0) flush_group<A_OUTG>(A, wstage, plw, nrw, SC0 + f - A_OUTG, pmask, pout);
@@ -291,6 +315,8 @@ template <int D> struct UnitTable;
 
 template <int D, int U>
 __device__ __forceinline__ void run_unit(const Fast3Args& A, const CtaState& T);
+template <int D, int U>
+__device__ __forceinline__ void run_all_units(const Fast3Args& A, const CtaState& T);
 
 // CTA = 128 consecutive ordered pairs x one unit (one kernel per unit: own register budget and occupancy;
 // running all units in one kernel was measured 1.6x slower)
@@ -334,13 +360,14 @@ __global__ void __launch_bounds__(A_THREADS) moments3b_kernel(Fast3Args A) {
     T.dxj = o1v.y; T.fcj = o1v.z; T.dfcj = o1v.w;
     T.n = n;
     T.jself = (int)(p - k0);
-    T.rk0 = T.staged ? sm + (k0 - kbeg) * RS : A.rec + k0 * RS;
+    T.rk_off = T.staged ? (k0 - kbeg) * RS : k0 * RS;
     // output staging has its own region behind the records: no CTA barrier after this one
     T.wstage = sm + (size_t)A_MAXREC * RS + (size_t)(tid >> 5) * 32 * A_OUTLD;
     T.plw = pl0 + (tid & ~31);
     T.nrw = max(0, min(32, nrow - (tid & ~31)));
     __syncthreads();
-    run_unit<D, U>(A, T);
+    if constexpr (U >= 0) run_unit<D, U>(A, T);
+    else run_all_units<D, 0>(A, T);
 }
 
 // unit tables: consecutive c packed while the accumulators fit (<= 44 doubles)
@@ -355,8 +382,8 @@ struct UnitTable {
         while (c <= D) {
             int acc = 0, e = c;
             while (e <= D) {
-                const int add = (e == 0 ? 1 : 4) * (D - e + 1);
-                if (acc > 0 && acc + add > 44) break;
+                const int add = (e == 0 ? 1 : 3) * (D - e + 1);
+                if (acc > 0 && acc + add > 36) break;
                 acc += add;
                 ++e;
             }
@@ -379,6 +406,15 @@ __device__ __forceinline__ void run_unit(const Fast3Args& A, const CtaState& T) 
 }
 
 template <int D, int U>
+__device__ __forceinline__ void run_all_units(const Fast3Args& A, const CtaState& T) {
+    constexpr UnitTable<D> UT{};
+    if constexpr (U < UT.n) {
+        unit3b<D, UT.c0[U], UT.c1[U], UT.base[U]>(A, T);
+        run_all_units<D, U + 1>(A, T);
+    }
+}
+
+template <int D, int U>
 void launch_moments_from(ipf_ctx* ctx, const Fast3Args& A) {
     constexpr UnitTable<D> UT{};
     if constexpr (U < UT.n) {
@@ -397,7 +433,20 @@ void launch_moments_from(ipf_ctx* ctx, const Fast3Args& A) {
 }
 
 template <int D>
-void launch_moments(ipf_ctx* ctx, const Fast3Args& A) { launch_moments_from<D, 0>(ctx, A); }
+void launch_moments(ipf_ctx* ctx, const Fast3Args& A) {
+    static const bool all_units = getenv("IPF_3B_ALLUNITS") != nullptr;     // experiment switch
+    if (!all_units) { launch_moments_from<D, 0>(ctx, A); return; }
+    const unsigned grid = (unsigned)((A.np + A_THREADS - 1) / A_THREADS);
+    auto kern = moments3b_kernel<D, -1>;
+    constexpr size_t smem = moments_smem_bytes<D>();
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    kern<<<grid, A_THREADS, smem, ctx->stream>>>(A);
+    ctx->launches++;
+}
 
 // ---- gather: S (reverse entries) + O (own sums) -> E / F / V rows ------------------
 struct Gather3Args {
