@@ -201,16 +201,21 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local)
     comm = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # stdout carries exactly one JSON line
+        # stdout must carry exactly one JSON line: NCCL prints its version banner there, so fd 1 points
+        # to stderr until the line is printed
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         comm = parallel.Communicator()
 
     ctx = _capi.Context(local)
     lib = ctx.lib
     basis = make_basis()
-    configs = make_configs(args.ncfg, seed=1 + rank)
+    configs = make_configs(args.ncfg, seed=1 if os.environ.get("IPF_BENCH_SAME_SEED") else 1 + rank)
     nrows = _alloc_rows(configs)
     ncols = len(basis)
     entries_local = nrows * ncols
@@ -399,6 +404,9 @@ def run_ours(args):
             "cpu_baseline": cpu, "fit": {"rel_rms": math.sqrt(ssr / ssy) if comm is None else rel_e2e,
                                          "coeff_diff_dev_vs_e2e": float(np.linalg.norm(c_dev - c_e2e) / np.linalg.norm(c_e2e)),
                                          "solve_info": getattr(solve_dev, "info", None)}}
+    if saved_stdout is not None:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if comm is not None:
         dist.barrier()
