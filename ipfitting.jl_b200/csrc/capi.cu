@@ -109,6 +109,8 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
     for (void* p : ctx->arena.spill) cudaFree(p);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->matrix_cache) cudaFree(ctx->matrix_cache);
+    for (void* p : ctx->chunk_arena.spill) cudaFree(p);
+    if (ctx->chunk_arena.base) cudaFree(ctx->chunk_arena.base);
     for (void* p : ctx->solve_arena.spill) cudaFree(p);
     if (ctx->solve_arena.base) cudaFree(ctx->solve_arena.base);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -319,7 +321,7 @@ void* ipf_matrix_device_ptr(const ipf_matrix* M) { return M ? (void*)M->d : null
 // ---------------------------------------------------------------- chunk upload
 static int upload_chunk(ipf_ctx* ctx, int64_t c0, int64_t c1, const int64_t* atom_off, const double* pos,
                         const double* cell, const uint8_t* pbc, const int64_t* rowE, const int64_t* rowF,
-                        const int64_t* rowV, ChunkDev& ch) {
+                        const int64_t* rowV, ChunkDev& ch, Arena* arena = nullptr) {
     cudaStream_t st = ctx->stream;
     const int64_t ncfg = c1 - c0;
     const int64_t a0 = atom_off[c0], natoms = atom_off[c1] - a0;
@@ -327,14 +329,14 @@ static int upload_chunk(ipf_ctx* ctx, int64_t c0, int64_t c1, const int64_t* ato
     ch.h_atom_off.resize(ncfg + 1);
     for (int64_t c = 0; c <= ncfg; ++c) ch.h_atom_off[c] = atom_off[c0 + c] - a0;
     std::vector<int64_t> zeros(ncfg, 0);
-    IPF_CUDA(ctx, ch.atom_off.alloc(ncfg + 1));
-    IPF_CUDA(ctx, ch.pos.alloc(3 * natoms));
-    IPF_CUDA(ctx, ch.cell.alloc(9 * ncfg));
-    IPF_CUDA(ctx, ch.pbc.alloc(3 * ncfg));
-    IPF_CUDA(ctx, ch.rowE.alloc(ncfg));
-    IPF_CUDA(ctx, ch.rowF.alloc(ncfg));
-    IPF_CUDA(ctx, ch.rowV.alloc(ncfg));
-    IPF_CUDA(ctx, ch.site_cfg.alloc(natoms));
+    IPF_CHECK(ch.atom_off.alloc(ctx, arena, ncfg + 1));
+    IPF_CHECK(ch.pos.alloc(ctx, arena, 3 * natoms));
+    IPF_CHECK(ch.cell.alloc(ctx, arena, 9 * ncfg));
+    IPF_CHECK(ch.pbc.alloc(ctx, arena, 3 * ncfg));
+    IPF_CHECK(ch.rowE.alloc(ctx, arena, ncfg));
+    IPF_CHECK(ch.rowF.alloc(ctx, arena, ncfg));
+    IPF_CHECK(ch.rowV.alloc(ctx, arena, ncfg));
+    IPF_CHECK(ch.site_cfg.alloc(ctx, arena, natoms));
     std::vector<int32_t> h_site_cfg((size_t)natoms);
     for (int64_t c = 0; c < ncfg; ++c)
         for (int64_t s = ch.h_atom_off[c]; s < ch.h_atom_off[c + 1]; ++s) h_site_cfg[s] = (int32_t)c;
@@ -400,9 +402,19 @@ struct ipf_configs {
     ~ipf_configs() { for (auto* c : chunks) delete c; }
 };
 
+static int32_t configs_create_impl(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
+                                   const double* cell, const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
+                                   const int64_t* rowF, const int64_t* rowV, ipf_configs** out, Arena* arena);
+
 int32_t ipf_configs_create(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
                            const double* cell, const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
                            const int64_t* rowF, const int64_t* rowV, ipf_configs** out) {
+    return configs_create_impl(ctx, ncfg, atom_off, pos, cell, pbc, Z, rowE, rowF, rowV, out, nullptr);
+}
+
+static int32_t configs_create_impl(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
+                                   const double* cell, const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
+                                   const int64_t* rowF, const int64_t* rowV, ipf_configs** out, Arena* arena) {
     (void)Z;
     if (!ctx || !out || ncfg < 0 || !atom_off || (ncfg && (!cell || !pbc || !rowE || !rowF || !rowV)))
         return ipf_set_error(ctx, IPF_EINVAL, "ipf_configs_create: bad arguments");
@@ -432,7 +444,7 @@ int32_t ipf_configs_create(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, 
         ChunkDev* ch = new (std::nothrow) ChunkDev();
         if (!ch) { delete cf; return IPF_ENOMEM; }
         cf->chunks.push_back(ch);
-        int rc = upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, *ch);
+        int rc = upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, *ch, arena);
         if (rc != IPF_OK) { delete cf; return rc; }
         c0 = c1;
     }
@@ -484,7 +496,9 @@ int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg, const i
                      const int64_t* rowE, const int64_t* rowF, const int64_t* rowV, ipf_matrix* Psi) {
     if (!ctx || !basis || !Psi) return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: bad arguments");
     ipf_configs* cf = nullptr;
-    IPF_CHECK(ipf_configs_create(ctx, ncfg, atom_off, pos, cell, pbc, Z, rowE, rowF, rowV, &cf));
+    // transient chunks: carved from a recycled arena (no cudaMalloc/cudaFree per call)
+    IPF_CHECK(ipf_arena_reset_in(ctx, ctx->chunk_arena));
+    IPF_CHECK(configs_create_impl(ctx, ncfg, atom_off, pos, cell, pbc, Z, rowE, rowF, rowV, &cf, &ctx->chunk_arena));
     const int rc = ipf_assemble_configs(ctx, basis, cf, Psi);
     ipf_configs_destroy(ctx, cf);
     return rc;

@@ -27,6 +27,7 @@ struct Arena {
 struct ipf_ctx {
     Arena arena;                        // assembly temporaries (per chunk)
     Arena solve_arena;                  // workspaces of the (single) active solver
+    Arena chunk_arena;                  // configuration chunks of the host-pointer ipf_assemble (transient)
     int active_solvers = 0;
     // pair-record cache key (see ipf_pair_records)
     const void* rec_nl = nullptr; int64_t rec_npairs = -1; int rec_transform = -1, rec_maxdeg = -1, rec_rs = 0;
@@ -139,6 +140,32 @@ struct DevBuf {
     }
 };
 
+// device array that is either owned (cudaMalloc/cudaFree) or carved from an arena (never freed individually)
+template <class T>
+struct FlexBuf {
+    T* p = nullptr;
+    bool owned = false;
+    ~FlexBuf() { if (p && owned) cudaFree(p); }
+    FlexBuf() = default;
+    FlexBuf(const FlexBuf&) = delete;
+    FlexBuf& operator=(const FlexBuf&) = delete;
+    int alloc(ipf_ctx* ctx, Arena* arena, size_t count) {
+        if (p && owned) cudaFree(p);
+        p = nullptr;
+        if (arena) {
+            owned = false;
+            void* q = nullptr;
+            int rc = ipf_arena_alloc_in(ctx, *arena, sizeof(T) * (count ? count : 1), &q);
+            p = (T*)q;
+            return rc;
+        }
+        owned = true;
+        cudaError_t e = cudaMalloc((void**)&p, sizeof(T) * (count ? count : 1));
+        if (e != cudaSuccess) { p = nullptr; return ipf_set_error(ctx, IPF_ENOMEM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+        return IPF_OK;
+    }
+};
+
 // ---- neighbour list of a chunk of configurations (device resident, arena backed) -------
 struct NeighList {
     int64_t nsites = 0;       // atoms in the chunk
@@ -163,12 +190,12 @@ struct NeighList {
 // Config chunk resident on the device
 struct ChunkDev {
     int64_t ncfg = 0, natoms = 0;
-    DevBuf<int64_t> atom_off;   // [ncfg+1], chunk-local
-    DevBuf<double> pos;         // [3*natoms]
-    DevBuf<double> cell;        // [9*ncfg]
-    DevBuf<uint8_t> pbc;        // [3*ncfg]
-    DevBuf<int64_t> rowE, rowF, rowV;   // [ncfg] 1-based, 0 = absent
-    DevBuf<int32_t> site_cfg;           // [natoms] config of every atom
+    FlexBuf<int64_t> atom_off;   // [ncfg+1], chunk-local
+    FlexBuf<double> pos;         // [3*natoms]
+    FlexBuf<double> cell;        // [9*ncfg]
+    FlexBuf<uint8_t> pbc;        // [3*ncfg]
+    FlexBuf<int64_t> rowE, rowF, rowV;   // [ncfg] 1-based, 0 = absent
+    FlexBuf<int32_t> site_cfg;           // [natoms] config of every atom
     std::vector<int64_t> h_atom_off;
 };
 

@@ -230,6 +230,7 @@ trsm_rows_kernel(double* __restrict__ A, int64_t ld, int64_t M, const double* __
             }
             __syncthreads();
             if (live) {
+#pragma unroll 4
                 for (int m = 0; m < mm; ++m) {
                     const double xm = A[(int64_t)(m0 + m) * ld + r];
                     const double2* row = reinterpret_cast<const double2*>(sL + m * TB);
@@ -507,17 +508,19 @@ int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, co
     if (M < 0 || n64 <= 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad system size");
     if (Irows) for (int64_t r = 0; r < M; ++r) if (Irows[r] < 0 || Irows[r] >= nrows) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: row index out of range");
     if (Icols) for (int64_t c = 0; c < n64; ++c) if (Icols[c] < 0 || Icols[c] >= Psi->ncols) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: column index out of range");
-    DevBuf<double> dY, dW, dD;
-    DevBuf<int64_t> dIr, dIc;
+    // staging copies of the host vectors: carved from the assembly arena (idle during a solve)
+    ABuf<double> dY, dW, dD;
+    ABuf<int64_t> dIr, dIc;
     cudaStream_t st = ctx->stream;
-    IPF_CUDA(ctx, dY.alloc(nrows)); IPF_CUDA(ctx, dW.alloc(nrows));
+    IPF_CHECK(ipf_arena_reset(ctx));
+    IPF_CHECK(dY.alloc(ctx, nrows)); IPF_CHECK(dW.alloc(ctx, nrows));
     if (nrows) {
         IPF_CUDA(ctx, cudaMemcpyAsync(dY.p, Y, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
         IPF_CUDA(ctx, cudaMemcpyAsync(dW.p, W, sizeof(double) * nrows, cudaMemcpyHostToDevice, st));
     }
-    if (Irows) { IPF_CUDA(ctx, dIr.alloc(M)); if (M) IPF_CUDA(ctx, cudaMemcpyAsync(dIr.p, Irows, sizeof(int64_t) * M, cudaMemcpyHostToDevice, st)); }
-    if (Icols) { IPF_CUDA(ctx, dIc.alloc(n64)); IPF_CUDA(ctx, cudaMemcpyAsync(dIc.p, Icols, sizeof(int64_t) * n64, cudaMemcpyHostToDevice, st)); }
-    if (Dinv) { IPF_CUDA(ctx, dD.alloc(n64)); IPF_CUDA(ctx, cudaMemcpyAsync(dD.p, Dinv, sizeof(double) * n64, cudaMemcpyHostToDevice, st)); }
+    if (Irows) { IPF_CHECK(dIr.alloc(ctx, M)); if (M) IPF_CUDA(ctx, cudaMemcpyAsync(dIr.p, Irows, sizeof(int64_t) * M, cudaMemcpyHostToDevice, st)); }
+    if (Icols) { IPF_CHECK(dIc.alloc(ctx, n64)); IPF_CUDA(ctx, cudaMemcpyAsync(dIc.p, Icols, sizeof(int64_t) * n64, cudaMemcpyHostToDevice, st)); }
+    if (Dinv) { IPF_CHECK(dD.alloc(ctx, n64)); IPF_CUDA(ctx, cudaMemcpyAsync(dD.p, Dinv, sizeof(double) * n64, cudaMemcpyHostToDevice, st)); }
     // (ipf_solve_begin_dev synchronises the stream before returning, so the temporaries may be freed)
     return ipf_solve_begin_dev(ctx, Psi, dY.p, dW.p, Irows ? dIr.p : nullptr, M, Icols ? dIc.p : nullptr, n64,
                                Dinv ? dD.p : nullptr, out);

@@ -65,15 +65,86 @@ def _get_weights(weights: dict, wh: float, dat, obskey: str, o: np.ndarray):
     raise ValueError("_get_weights: length(w) is neither 1 nor length(o)?!?!?")
 
 
+_OKEYS = (ENERGY, FORCES, VIRIAL)
+
+
+def _observation_layout(db):
+    """Per-observation arrays in `observations(db)` order, cached on the db (rows never change after
+    `_alloc_lsq_matrix`): config index, okey id, first row, length, natoms, configtype id."""
+    lay = getattr(db, "_obs_layout", None)
+    if lay and lay.get("nconfigs") == len(db.configs):
+        return lay
+    cfg, key, first, length, nat, ctid = [], [], [], [], [], []
+    cts = {}
+    plain = True
+    for icfg, d in enumerate(db.configs):
+        ci = cts.setdefault(d.configtype, len(cts))
+        n = len(d.at)
+        for okey in d.D.keys():
+            if okey not in _OKEYS:
+                plain = False
+                continue
+            f, ln = d.rows[okey]
+            cfg.append(icfg); key.append(_OKEYS.index(okey)); first.append(f); length.append(ln)
+            nat.append(n); ctid.append(ci)
+    lay = {"nconfigs": len(db.configs), "plain": plain, "cts": list(cts.keys()),
+           "cfg": np.asarray(cfg, dtype=np.int64), "key": np.asarray(key, dtype=np.int64),
+           "first": np.asarray(first, dtype=np.int64), "len": np.asarray(length, dtype=np.int64),
+           "nat": np.asarray(nat, dtype=np.float64), "ctid": np.asarray(ctid, dtype=np.int64)}
+    # rows in traversal order are contiguous and ascending (that is how they were assigned)
+    lay["contiguous"] = bool(len(first) == 0 or (np.array_equal(lay["first"][1:], lay["first"][:-1] + lay["len"][:-1])
+                                                  and lay["first"][0] == 0))
+    try:
+        db._obs_layout = lay
+    except Exception:
+        pass
+    return lay
+
+
 def collect_observations(db: LsqDB, weights: dict, Vref):
     """`collect_observations(db, weights, Vref) -> Y, W, Icfg` (`src/lsq.jl:74-109`).
-    Icfg is 0-based here, -1 for rows that were skipped."""
+    Icfg is 0-based here, -1 for rows that were skipped.  Vectorised when no configuration carries
+    `info["W"]` / `info["Vref"]` overrides and Vref is None or a OneBody; otherwise the
+    observation-by-observation loop of the reference."""
     nrows = db.nrows
+    ignore = weights["ignore"]
+    onebody = isinstance(Vref, OneBody)
+    lay = _observation_layout(db)
+    simple = (lay["plain"] and lay["contiguous"] and (Vref is None or onebody) and int(lay["len"].sum()) == nrows
+              and not any(("W" in d.info) or ("Vref" in d.info) for d in db.configs))
+    if simple:
+        Y = (np.concatenate([v for d in db.configs for v in d.D.values()]) if nrows else np.zeros(0)).astype(np.float64, copy=False)
+        nobs = len(lay["cfg"])
+        wobs = np.zeros(nobs)
+        live = np.ones(nobs, dtype=bool)
+        hook = np.where(lay["key"] == 1, 1.0, 1.0 / np.sqrt(lay["nat"]))       # weighthook: E, V -> 1/sqrt(N)
+        for ci, ct in enumerate(lay["cts"]):
+            sel_ct = lay["ctid"] == ci
+            if ct in ignore:
+                live &= ~sel_ct
+                continue
+            table = weights[ct] if ct in weights else weights["default"]
+            for ki, okey in enumerate(_OKEYS):
+                if okey in table:
+                    m = sel_ct & (lay["key"] == ki)
+                    wobs[m] = float(table[okey]) * hook[m]
+        for ki, okey in enumerate(_OKEYS):
+            if okey in ignore:
+                live &= lay["key"] != ki
+        if onebody:
+            esel = (lay["key"] == 0) & live
+            if esel.any():
+                e0 = np.array([Vref.energy(db.configs[i].at) for i in lay["cfg"][esel]])
+                Y = Y.copy()
+                Y[lay["first"][esel]] -= e0
+        W = np.repeat(np.where(live, wobs, 0.0), lay["len"])
+        Icfg = np.repeat(np.where(live, lay["cfg"], -1), lay["len"])
+        if not live.all():
+            Y = np.where(np.repeat(live, lay["len"]), Y, 0.0)
+        return Y, W, Icfg
     Y = np.zeros(nrows)
     W = np.zeros(nrows)
     Icfg = np.full(nrows, -1, dtype=np.int64)
-    ignore = weights["ignore"]
-    onebody = isinstance(Vref, OneBody)
     for icfg, dat in enumerate(db.configs):
         if dat.configtype in ignore:
             continue

@@ -36,15 +36,35 @@ def set_matrows(d: Dat, okey: str, first: int, n: int) -> Dat:
     return d
 
 
-def _alloc_rows(configs: Sequence[Dat]) -> int:
+_OKEY_ID = {ENERGY: 0, FORCES: 1, VIRIAL: 2}
+
+
+def _alloc_rows(configs: Sequence[Dat], layout: dict = None) -> int:
     """Row assignment of `_alloc_lsq_matrix` (`src/lsq_db.jl:237-250`): prefix sum of the
-    observation lengths in `observations(configs)` order.  Returns nrows."""
+    observation lengths in `observations(configs)` order.  Returns nrows.  When `layout` is a dict
+    it receives the per-observation arrays (config, okey id, first row, length, natoms, configtype id)
+    that `collect_observations` uses for its vectorised path."""
     nrows = 0
-    for d in configs:                       # observations(configs) order: config-major, then D's key order
+    cfg, key, first, length, nat, ctid = [], [], [], [], [], []
+    cts = {}
+    plain = True
+    for icfg, d in enumerate(configs):      # observations(configs) order: config-major, then D's key order
+        ci = cts.setdefault(d.configtype, len(cts))
+        na = len(d.at)
         for okey, v in d.D.items():
             n = len(v)
             d.rows[okey] = (nrows, n)
+            k = _OKEY_ID.get(okey)
+            if k is None:
+                plain = False
+            else:
+                cfg.append(icfg); key.append(k); first.append(nrows); length.append(n); nat.append(na); ctid.append(ci)
             nrows += n
+    if layout is not None:
+        layout.update(nconfigs=len(configs), plain=plain, cts=list(cts.keys()), contiguous=plain,
+                      cfg=np.asarray(cfg, dtype=np.int64), key=np.asarray(key, dtype=np.int64),
+                      first=np.asarray(first, dtype=np.int64), len=np.asarray(length, dtype=np.int64),
+                      nat=np.asarray(nat, dtype=np.float64), ctid=np.asarray(ctid, dtype=np.int64))
     return nrows
 
 
@@ -98,7 +118,8 @@ class LsqDB:
         self._Psi_dev = None
         self._Psi_host = None
         self._dev_basis = None
-        self.nrows = _alloc_rows(self.configs)
+        self._obs_layout = {}
+        self.nrows = _alloc_rows(self.configs, self._obs_layout)
         if _assemble:
             self._assemble()
             if dbpath != "":
