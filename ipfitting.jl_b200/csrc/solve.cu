@@ -79,31 +79,86 @@ __global__ void k4_build_kernel(const double* __restrict__ Psi, int64_t ldp, con
     if (bad) atomicOr(flag, 1);
 }
 
-// ---- K6: small dense kernels on the n x n factor (single CTA) ---------------
-// lower Cholesky, column-major, in place on L (copy of G[0:n,0:n] + shift I)
-__global__ void chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
-    extern __shared__ double s_col[];
-    __shared__ double s_d;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
-    for (int j = 0; j < n; ++j) {
-        if (tid == 0) s_d = L[(size_t)j * n + j];
+// ---- K6: small dense kernels on the n x n factor (single CTA, blocked by 32) ---------------
+constexpr int KB = 32;
+
+// lower Cholesky, column-major, in place on L (copy of D G D + shift I).  Per block column:
+// warp 0 factors the 32x32 diagonal block in shared memory, every thread solves panel rows against it,
+// then the trailing matrix gets a rank-32 update -- 3 barriers per 32 columns instead of 3 per column.
+__global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
+    __shared__ double sD[KB][KB + 1];
+    __shared__ int s_fail;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_fail = -1;
+    __syncthreads();
+    for (int J0 = 0; J0 < n; J0 += KB) {
+        const int nbk = min(KB, n - J0);
+        for (int e = tid; e < KB * KB; e += blockDim.x) {
+            const int i = e % KB, j = e / KB;
+            sD[i][j] = (i < nbk && j < nbk && i >= j) ? L[(size_t)(J0 + j) * n + J0 + i] : (i == j ? 1.0 : 0.0);
+        }
         __syncthreads();
-        const double d = s_d;
-        if (!(d > 0.0) || !isfinite(d)) {
-            if (tid == 0) { flag[1] = 1; flag[2] = j; }
+        if (warp == 0) {
+            for (int j = 0; j < nbk; ++j) {
+                const double d = sD[j][j];
+                if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) s_fail = J0 + j; break; }
+                const double ljj = sqrt(d);
+                __syncwarp();
+                if (lane == j) sD[j][j] = ljj;
+                if (lane > j && lane < nbk) sD[lane][j] = sD[lane][j] / ljj;
+                __syncwarp();
+                if (lane > j && lane < nbk) {
+                    const double lij = sD[lane][j];
+                    for (int k = j + 1; k <= lane; ++k) sD[lane][k] -= lij * sD[k][j];
+                }
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (s_fail >= 0) {
+            if (tid == 0) { flag[1] = 1; flag[2] = s_fail; }
             return;
         }
-        const double ljj = sqrt(d);
-        for (int k = j + tid; k < n; k += blockDim.x) {
-            const double v = (k == j) ? ljj : L[(size_t)j * n + k] / ljj;
-            L[(size_t)j * n + k] = v;
-            s_col[k] = v;
+        for (int e = tid; e < nbk * nbk; e += blockDim.x) {
+            const int i = e % nbk, j = e / nbk;
+            if (i >= j) L[(size_t)(J0 + j) * n + J0 + i] = sD[i][j];
+        }
+        // panel: rows below the block, X Ld^T = P  (forward substitution per row)
+        const int r0 = J0 + nbk;
+        for (int r = r0 + tid; r < n; r += blockDim.x) {
+            // sD is padded with the identity beyond nbk, so the loops run over the full block
+            double x[KB];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) x[k] = (k < nbk) ? L[(size_t)(J0 + k) * n + r] : 0.0;
+#pragma unroll
+            for (int k = 0; k < KB; ++k) {
+                double v = x[k];
+#pragma unroll
+                for (int m = 0; m < k; ++m) v -= x[m] * sD[k][m];
+                x[k] = v / sD[k][k];
+            }
+#pragma unroll
+            for (int k = 0; k < KB; ++k) if (k < nbk) L[(size_t)(J0 + k) * n + r] = x[k];
         }
         __syncthreads();
-        for (int i = j + 1 + warp; i < n; i += nwarp) {
-            const double lij = s_col[i];
-            double* col = L + (size_t)i * n;
-            for (int k = i + lane; k < n; k += 32) col[k] -= s_col[k] * lij;
+        // trailing update: L[r][c] -= sum_k L[r][J0+k] L[c][J0+k],  c >= r0, r >= c
+        const int nt = n - r0;
+        for (int c = warp; c < nt; c += (int)(blockDim.x >> 5)) {
+            double lc[KB];
+#pragma unroll
+            for (int k = 0; k < KB; ++k) lc[k] = (k < nbk) ? L[(size_t)(J0 + k) * n + r0 + c] : 0.0;
+            double* col = L + (size_t)(r0 + c) * n;
+            for (int r = r0 + c + lane; r < n; r += 32) {
+                double acc = col[r];
+                if (nbk == KB) {
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) acc -= L[(size_t)(J0 + k) * n + r] * lc[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KB; ++k) if (k < nbk) acc -= L[(size_t)(J0 + k) * n + r] * lc[k];
+                }
+                col[r] = acc;
+            }
         }
         __syncthreads();
     }
@@ -180,27 +235,45 @@ __global__ void rprod_kernel(const double* __restrict__ L, const double* __restr
 }
 
 // mode 0: solve L w = b (lower, forward);  mode 1: solve R x = b (upper, backward).  x overwrites b.
-__global__ void trsv_kernel(const double* __restrict__ T, int n, double* __restrict__ b, int mode) {
+// Blocked by 32: warp 0 solves the diagonal block, all threads update the remaining right-hand side.
+__global__ void __launch_bounds__(1024) trsv_kernel(const double* __restrict__ T, int n, double* __restrict__ b, int mode) {
     extern __shared__ double s_x[];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < n; k += blockDim.x) s_x[k] = b[k];
     __syncthreads();
-    if (mode == 0) {
-        for (int j = 0; j < n; ++j) {
-            const double xj = s_x[j] / T[(size_t)j * n + j];
-            __syncthreads();
-            if (tid == 0) s_x[j] = xj;
-            for (int k = j + 1 + tid; k < n; k += blockDim.x) s_x[k] -= T[(size_t)j * n + k] * xj;
-            __syncthreads();
+    const int nblk = (n + KB - 1) / KB;
+    for (int bi = 0; bi < nblk; ++bi) {
+        const int J0 = (mode == 0) ? bi * KB : (nblk - 1 - bi) * KB;
+        const int nbk = min(KB, n - J0);
+        if (warp == 0) {
+            if (mode == 0) {
+                for (int j = 0; j < nbk; ++j) {
+                    const double xj = s_x[J0 + j] / T[(size_t)(J0 + j) * n + J0 + j];
+                    __syncwarp();
+                    if (lane == j) s_x[J0 + j] = xj;
+                    if (lane > j && lane < nbk) s_x[J0 + lane] -= T[(size_t)(J0 + j) * n + J0 + lane] * xj;
+                    __syncwarp();
+                }
+            } else {
+                for (int j = nbk - 1; j >= 0; --j) {
+                    const double xj = s_x[J0 + j] / T[(size_t)(J0 + j) * n + J0 + j];
+                    __syncwarp();
+                    if (lane == j) s_x[J0 + j] = xj;
+                    if (lane < j) s_x[J0 + lane] -= T[(size_t)(J0 + j) * n + J0 + lane] * xj;
+                    __syncwarp();
+                }
+            }
         }
-    } else {
-        for (int j = n - 1; j >= 0; --j) {
-            const double xj = s_x[j] / T[(size_t)j * n + j];
-            __syncthreads();
-            if (tid == 0) s_x[j] = xj;
-            for (int k = tid; k < j; k += blockDim.x) s_x[k] -= T[(size_t)j * n + k] * xj;
-            __syncthreads();
+        __syncthreads();
+        // update the rest: rows below (mode 0) / above (mode 1) the block
+        const int lo = (mode == 0) ? J0 + nbk : 0;
+        const int hi = (mode == 0) ? n : J0;
+        for (int i = lo + tid; i < hi; i += blockDim.x) {
+            double acc = s_x[i];
+            for (int k = 0; k < nbk; ++k) acc -= T[(size_t)(J0 + k) * n + i] * s_x[J0 + k];
+            s_x[i] = acc;
         }
+        __syncthreads();
     }
     for (int k = tid; k < n; k += blockDim.x) b[k] = s_x[k];
 }
@@ -594,7 +667,7 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, S->dscale, shift);
         IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
         { ProfScope prof_(ctx, "cholesky");
-        chol_lower_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->flag); }
+        chol_lower_kernel<<<1, 256, 0, st>>>(S->L, n, S->flag); }
         ctx->launches += 2;
         int hf[4];
         IPF_CUDA(ctx, cudaMemcpyAsync(hf, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
