@@ -169,6 +169,15 @@ int32_t ipf_solve_begin(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, co
 int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* dY, const double* dW,
                             const int64_t* dIrows, int64_t nIrows, const int64_t* dIcols,
                             int64_t nIcols, const double* dDinv, ipf_solver** S);
+/* Force preconditioner (_forceprecon, src/lsq.jl:184-234; P from e.g. AdjacancyPrecon,
+ * src/preconditioners.jl:54-74).  Block b replaces the rows [row0[b], row0[b]+m[b]) of the weighted system
+ * (positions in the SELECTED row numbering, all columns and y) by rtP_b \ rows, where
+ *   solver 0 ("chol"): P holds P_b, rtP_b = cholesky(P_b).L          (src/lsq.jl:215-221)
+ *   solver 1 ("sqrt"): P holds sqrt(P_b) (symmetric), applied as its inverse   (src/lsq.jl:222-223)
+ * P: packed column-major m[b] x m[b] blocks at P[Poff[b]], Plen doubles in total.  The scalar row weight of a
+ * force block commutes with rtP \ ., so this is called after ipf_solve_begin and before the first ipf_solve_gram. */
+int32_t ipf_solve_precon(ipf_ctx* ctx, ipf_solver* S, int64_t nblocks, const int64_t* row0, const int32_t* m,
+                         const int64_t* Poff, const double* P, int64_t Plen, int32_t solver);
 int32_t ipf_solve_shape(const ipf_solver* S, int64_t* M, int64_t* n);
 /* the weighted system itself (get_lsq_system, src/lsq.jl:245-311): Aw [M x n] column-major, yw [M] */
 int32_t ipf_solve_system_to_host(ipf_ctx* ctx, const ipf_solver* S, double* Aw, int64_t ld, double* yw);

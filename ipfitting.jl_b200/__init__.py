@@ -12,3 +12,4 @@ from .lsq_db import LsqDB, matrows, filter_basis, filter_configs, dbpath
 from .lsq import lsqfit, get_lsq_system, collect_observations
 from .lsqerrors import add_fits, rmse, mae
 from . import synth, parallel
+from .preconditioners import AdjacancyPrecon

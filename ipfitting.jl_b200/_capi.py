@@ -71,6 +71,7 @@ SIGNATURES = {
     "ipf_assemble_configs": (C.c_int32, [_vp, _vp, _vp, _vp]),
     "ipf_solve_begin_dev": (C.c_int32, [_vp, _vp, _vp, _vp, _vp, C.c_int64, _vp, C.c_int64, _vp, C.POINTER(_vp)]),
     "ipf_solve_begin": (C.c_int32, [_vp, _vp, _dp, _dp, _lp, C.c_int64, _lp, C.c_int64, _dp, C.POINTER(_vp)]),
+    "ipf_solve_precon": (C.c_int32, [_vp, _vp, C.c_int64, _lp, _ip, _lp, _dp, C.c_int64, C.c_int32]),
     "ipf_solve_shape": (C.c_int32, [_vp, _lp, _lp]),
     "ipf_solve_system_to_host": (C.c_int32, [_vp, _vp, _dp, C.c_int64, _dp]),
     "ipf_solve_gram": (C.c_int32, [_vp, _vp, C.POINTER(_vp), _lp]),

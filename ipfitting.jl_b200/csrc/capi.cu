@@ -387,11 +387,14 @@ int32_t ipf_neighbours(ipf_ctx* ctx, int32_t nat, const double* pos, const doubl
     *n = nl.npairs;
     const int64_t m = std::min<int64_t>(cap, nl.npairs);
     if (m > 0) {
-        if (I) IPF_CUDA(ctx, cudaMemcpy(I, nl.pi.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
-        if (J) IPF_CUDA(ctx, cudaMemcpy(J, nl.pj.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost));
-        if (S) IPF_CUDA(ctx, cudaMemcpy(S, nl.pS.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost));
-        if (R) IPF_CUDA(ctx, cudaMemcpy(R, nl.pR.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost));
+        // same stream as the kernels that produce the list (a non-blocking stream does not order against stream 0)
+        cudaStream_t st = ctx->stream;
+        if (I) IPF_CUDA(ctx, cudaMemcpyAsync(I, nl.pi.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+        if (J) IPF_CUDA(ctx, cudaMemcpyAsync(J, nl.pj.p, sizeof(int32_t) * m, cudaMemcpyDeviceToHost, st));
+        if (S) IPF_CUDA(ctx, cudaMemcpyAsync(S, nl.pS.p, sizeof(int32_t) * 3 * m, cudaMemcpyDeviceToHost, st));
+        if (R) IPF_CUDA(ctx, cudaMemcpyAsync(R, nl.pR.p, sizeof(double) * 3 * m, cudaMemcpyDeviceToHost, st));
     }
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IPF_OK;
 }
 

@@ -85,7 +85,7 @@ constexpr int KB = 32;
 // lower Cholesky, column-major, in place on L (copy of D G D + shift I).  Per block column:
 // warp 0 factors the 32x32 diagonal block in shared memory, every thread solves panel rows against it,
 // then the trailing matrix gets a rank-32 update -- 3 barriers per 32 columns instead of 3 per column.
-__global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
+__device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, int* __restrict__ flag) {
     __shared__ double sD[KB][KB + 1];
     __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -166,6 +166,108 @@ __global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L,
     for (int64_t e = tid; e < (int64_t)n * n; e += blockDim.x) {
         const int r = (int)(e % n), c = (int)(e / n);
         if (r < c) L[e] = 0.0;
+    }
+}
+
+__global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
+    chol_lower_body(L, n, flag);
+}
+
+// ---- K8: force preconditioner (src/lsq.jl:184-234): batched per-configuration blocks --------------
+// one CTA per block: in-place lower Cholesky of P_b (flag[1] / flag[2] report the first failure)
+__global__ void __launch_bounds__(256) chol_batched_kernel(double* __restrict__ P, const int64_t* __restrict__ off,
+                                                           const int32_t* __restrict__ m, int* __restrict__ flag) {
+    chol_lower_body(P + off[blockIdx.x], m[blockIdx.x], flag);
+}
+
+// rows [row0, row0+m) of A (all ncol columns, leading dimension ld) <- L_b^-1 rows  (forward substitution);
+// with `back` also <- L_b^-T (so that the rows are multiplied by (L L^T)^-1).  One CTA per block, thread per column;
+// 32-row blocks of the solution live in registers, L tiles are staged in shared memory.
+__global__ void __launch_bounds__(256) precon_apply_kernel(double* __restrict__ A, int64_t ld, int ncol,
+                                                           const int64_t* __restrict__ row0, const int32_t* __restrict__ mm,
+                                                           const int64_t* __restrict__ off, const double* __restrict__ P,
+                                                           int back) {
+    __shared__ double sL[KB][KB + 1];
+    const int b = blockIdx.x;
+    const int m = mm[b];
+    const double* L = P + off[b];
+    const int nblk = (m + KB - 1) / KB;
+    for (int c0 = 0; c0 < ncol; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        const bool live = c < ncol;
+        double* col = A + (int64_t)(live ? c : 0) * ld + row0[b];
+        // forward: x_I = L_II^-1 (b_I - sum_{K<I} L_IK x_K)
+        for (int I = 0; I < nblk; ++I) {
+            double x[KB];
+#pragma unroll
+            for (int i = 0; i < KB; ++i) x[i] = (live && I * KB + i < m) ? col[I * KB + i] : 0.0;
+            for (int K = 0; K <= I; ++K) {
+                __syncthreads();
+                for (int e = threadIdx.x; e < KB * KB; e += blockDim.x) {
+                    const int i = e % KB, k = e / KB;
+                    const int gi = I * KB + i, gk = K * KB + k;
+                    sL[i][k] = (gi < m && gk < m && gi >= gk) ? L[(size_t)gk * m + gi] : ((gi == gk) ? 1.0 : 0.0);
+                }
+                __syncthreads();
+                if (K < I) {
+#pragma unroll 4
+                    for (int k = 0; k < KB; ++k) {
+                        const double xk = (live && K * KB + k < m) ? col[K * KB + k] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < KB; ++i) x[i] -= sL[i][k] * xk;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < KB; ++i) {
+                        double v = x[i];
+#pragma unroll
+                        for (int k = 0; k < i; ++k) v -= sL[i][k] * x[k];
+                        x[i] = v / sL[i][i];
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < KB; ++i) if (I * KB + i < m) col[I * KB + i] = x[i];
+            }
+        }
+        if (!back) continue;
+        // backward: x_I = L_II^-T (b_I - sum_{K>I} L_KI^T x_K)
+        for (int I = nblk - 1; I >= 0; --I) {
+            double x[KB];
+#pragma unroll
+            for (int i = 0; i < KB; ++i) x[i] = (live && I * KB + i < m) ? col[I * KB + i] : 0.0;
+            for (int K = nblk - 1; K >= I; --K) {
+                __syncthreads();
+                // sL[i][k] = L[K*KB + k][I*KB + i]  (transposed tile)
+                for (int e = threadIdx.x; e < KB * KB; e += blockDim.x) {
+                    const int k = e % KB, i = e / KB;
+                    const int gi = I * KB + i, gk = K * KB + k;
+                    sL[i][k] = (gi < m && gk < m && gk >= gi) ? L[(size_t)gi * m + gk] : ((gi == gk) ? 1.0 : 0.0);
+                }
+                __syncthreads();
+                if (K > I) {
+#pragma unroll 4
+                    for (int k = 0; k < KB; ++k) {
+                        const double xk = (live && K * KB + k < m) ? col[K * KB + k] : 0.0;
+#pragma unroll
+                        for (int i = 0; i < KB; ++i) x[i] -= sL[i][k] * xk;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = KB - 1; i >= 0; --i) {
+                        double v = x[i];
+#pragma unroll
+                        for (int k = i + 1; k < KB; ++k) v -= sL[i][k] * x[k];
+                        x[i] = v / sL[i][i];
+                    }
+                }
+            }
+            if (live) {
+#pragma unroll
+                for (int i = 0; i < KB; ++i) if (I * KB + i < m) col[I * KB + i] = x[i];
+            }
+        }
     }
 }
 
@@ -604,6 +706,47 @@ int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     if (ctx && S->pooled) ctx->active_solvers--;
     free_solve(S);
+    return IPF_OK;
+}
+
+// Force preconditioner blocks applied to the weighted system (see include/ipf_b200.h)
+int32_t ipf_solve_precon(ipf_ctx* ctx, ipf_solver* S, int64_t nblocks, const int64_t* row0, const int32_t* m,
+                         const int64_t* Poff, const double* P, int64_t Plen, int32_t solver) {
+    if (!ctx || !S || nblocks < 0 || (nblocks && (!row0 || !m || !Poff || !P)) || (solver != 0 && solver != 1))
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_precon: bad arguments");
+    if (S->state != 0 || S->pass != 0) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_precon: call after ipf_solve_begin and before ipf_solve_gram");
+    if (nblocks == 0) return IPF_OK;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        if (m[b] <= 0 || row0[b] < 0 || row0[b] + m[b] > S->M || Poff[b] < 0 || Poff[b] + (int64_t)m[b] * m[b] > Plen)
+            return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_precon: block %lld out of range", (long long)b);
+        for (int64_t k = Poff[b]; k < Poff[b] + (int64_t)m[b] * m[b]; ++k)
+            if (!std::isfinite(P[k])) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_precon: non-finite preconditioner entry");
+    }
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    IPF_CHECK(ipf_arena_reset(ctx));            // the assembly arena is idle during a solve
+    ABuf<double> dP;
+    ABuf<int64_t> dro, dof;
+    ABuf<int32_t> dm, dflag;
+    IPF_CHECK(dP.alloc(ctx, Plen)); IPF_CHECK(dro.alloc(ctx, nblocks)); IPF_CHECK(dof.alloc(ctx, nblocks));
+    IPF_CHECK(dm.alloc(ctx, nblocks)); IPF_CHECK(dflag.alloc(ctx, 4));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dP.p, P, sizeof(double) * Plen, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dro.p, row0, sizeof(int64_t) * nblocks, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dof.p, Poff, sizeof(int64_t) * nblocks, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dm.p, m, sizeof(int32_t) * nblocks, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemsetAsync(dflag.p, 0, sizeof(int32_t) * 4, st));
+    {
+        ProfScope prof_(ctx, "precon");
+        chol_batched_kernel<<<(unsigned)nblocks, 256, 0, st>>>(dP.p, dof.p, dm.p, dflag.p);
+        // solver 0: rows <- chol(P).L \ rows;  solver 1: P holds sqrt(P): rows <- sqrt(P)^-1 rows = C^-T C^-1 rows
+        precon_apply_kernel<<<(unsigned)nblocks, 256, 0, st>>>(S->A, S->Mpad, S->n1, dro.p, dm.p, dof.p, dP.p, solver);
+        ctx->launches += 2;
+    }
+    int hf[4];
+    IPF_CUDA(ctx, cudaMemcpyAsync(hf, dflag.p, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    IPF_CUDA(ctx, cudaGetLastError());
+    if (hf[1]) return ipf_set_error(ctx, IPF_ESINGULAR, "ipf_solve_precon: a preconditioner block is not positive definite");
     return IPF_OK;
 }
 

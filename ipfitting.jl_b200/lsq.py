@@ -181,6 +181,40 @@ def _select(db: LsqDB, Y, W, Icfg, Ibasis, Itrain):
     return Irows, Icols
 
 
+def _precon_blocks(db, weights, Irows):
+    """The (row position in the selected system, matrix) pairs `_forceprecon` acts on (`src/lsq.jl:184-234`):
+    every "F" observation whose configtype (or "default") has an entry in `weights["precon"]`."""
+    pre = weights.get("precon")
+    if not pre:
+        return [], [], "chol"
+    solver = pre.get("_solver", "chol")
+    if solver not in ("chol", "sqrt"):
+        raise ValueError("unknown root solver")
+    row0, blocks = [], []
+    for okey, dat, _ in observations(db):
+        if okey != FORCES:
+            continue
+        ct = dat.configtype
+        fn = pre.get(ct, pre.get("default"))
+        if fn is None:
+            continue
+        f, n = dat.rows[okey]
+        pos = int(np.searchsorted(Irows, f))
+        if pos >= len(Irows) or Irows[pos] != f:
+            continue                                  # the force rows carry zero weight: not part of the system
+        if pos + n > len(Irows) or Irows[pos + n - 1] != f + n - 1:
+            raise ValueError("force block only partially selected")
+        P = np.asarray(fn(dat.at), dtype=np.float64)
+        if P.shape != (n, n):
+            raise ValueError("preconditioner has the wrong shape")
+        if solver == "sqrt":
+            import scipy.linalg as sla
+            P = np.real(sla.sqrtm(P))
+        row0.append(pos)
+        blocks.append(P)
+    return row0, blocks, solver
+
+
 class _Solver:
     """RAII wrapper of the staged `ipf_solve_*` calls."""
 
@@ -201,6 +235,22 @@ class _Solver:
         M, n = C.c_int64(), C.c_int64()
         ctx.lib.ipf_solve_shape(h, C.byref(M), C.byref(n))
         self.M, self.n = M.value, n.value
+
+    def apply_precon(self, row0, blocks, solver: str = "chol"):
+        """`_forceprecon` (`src/lsq.jl:184-234`) on the device: block b (an m x m matrix P_b, or sqrt(P_b) for
+        solver "sqrt") acts on the rows [row0[b], row0[b] + m) of the weighted system."""
+        if solver not in ("chol", "sqrt"):
+            raise ValueError("unknown root solver")
+        if not blocks:
+            return
+        m = np.array([b.shape[0] for b in blocks], dtype=np.int32)
+        off = np.zeros(len(blocks), dtype=np.int64)
+        np.cumsum(m[:-1].astype(np.int64) ** 2, out=off[1:])
+        P = np.concatenate([np.asfortranarray(b, dtype=np.float64).reshape(-1, order="F") for b in blocks])
+        r0 = np.ascontiguousarray(row0, dtype=np.int64)
+        self.ctx.check(self.ctx.lib.ipf_solve_precon(
+            self.ctx.h, self.h, len(blocks), _capi.ptr(r0, C.c_int64), _capi.ptr(m, C.c_int32), _capi.ptr(off, C.c_int64),
+            _capi.ptr(P, C.c_double), len(P), 0 if solver == "chol" else 1))
 
     def system_to_host(self):
         A = np.empty((self.M, self.n), order="F")
@@ -265,11 +315,13 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True):
     return c, R, info
 
 
-def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None):
+def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None, precon=None):
     """Weighted LSQ solve of the device-resident system.  `comm`: a
-    `parallel.Communicator` (rows are sharded over its ranks) or None."""
+    `parallel.Communicator` (rows are sharded over its ranks) or None.  `precon`: (row0, blocks, solver)."""
     S = _Solver(ctx, Psi_dev, Y, W, Irows, Icols, Dinv)
     try:
+        if precon is not None and precon[1]:
+            S.apply_precon(*precon)
         return run_staged(S, comm, ctx.device, want_R)
     finally:
         S.close()
@@ -288,6 +340,8 @@ def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=Non
     Irows, Icols = _select(db, Y, W, Icfg, Ibasis, Itrain)
     S = _Solver(db._context(), db.Psi_dev, Y, W, Irows, Icols, None)
     try:
+        row0, blocks, psolver = _precon_blocks(db, weights, Irows)
+        S.apply_precon(row0, blocks, psolver)
         return S.system_to_host()
     finally:
         S.close()
@@ -335,7 +389,8 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     Dinv = _diag_of(solver.get("P"), n)
     if "P" in solver:
         del solver["P"]          # `src/lsq.jl:460-462`
-    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm)
+    precon = _precon_blocks(db, weights, Irows)
+    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm, precon=precon)
     kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
     if isinstance(saveqr, dict):
         saveqr["R"] = R

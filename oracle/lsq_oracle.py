@@ -128,3 +128,53 @@ def rmse_table(Psi, configs, cfull, E0=None):
             nrm[ct][okey] = np.sqrt(nrm[ct][okey] / ln[ct][okey])
             rel[ct][okey] = err[ct][okey] / nrm[ct][okey]
     return err, rel
+
+
+# ---------------------------------------------------------------- force preconditioner
+def adjacency_precon(at, intervals, stab=1e-4, innerstab=0.1):
+    """AdjacancyPrecon(at) restated loop by loop (src/preconditioners.jl:42-74); neighbour list from the
+    C oracle's brute-force enumeration."""
+    import ipf_oracle as O
+    n = len(at)
+    rc = max(i[1] for i in intervals)
+    I, J, S, R = O.neighbours(at.X, at.cell, at.pbc, rc)
+    P = np.zeros((3 * n, 3 * n))
+    for i, j, Rij in zip(I, J, R):
+        if j < i:
+            continue
+        r = np.linalg.norm(Rij)
+        Rh = Rij / r
+        Pi = (1 - innerstab) * np.outer(Rh, Rh) + innerstab * np.eye(3)
+        Pij = 0.0 * Pi
+        for (r0, r1, k) in intervals:
+            if r0 <= r <= r1:
+                Pij = k * Pi
+                break
+        for a in range(3):
+            for b in range(3):
+                P[3 * i + a, 3 * j + b] -= Pij[a, b]
+                P[3 * j + b, 3 * i + a] -= Pij[a, b]
+                P[3 * i + a, 3 * i + b] += Pij[a, b]
+                P[3 * j + a, 3 * j + b] += Pij[a, b]
+    return P + stab * np.eye(3 * n)
+
+
+def forceprecon_system(Psi, configs, weights, precon_fn, E0=0.0, solver="chol"):
+    """get_lsq_system with _forceprecon (src/lsq.jl:184-234, 245-311): rtP \\ on the F rows of Psi and Y
+    BEFORE the weights are applied."""
+    weights = fix_weights(weights)
+    Y, W, Icfg = collect_observations(configs, Psi.shape[0], weights, E0)
+    Psi = Psi.copy()
+    for okey, d, _ in observations(configs):
+        if okey != "F":
+            continue
+        P = precon_fn(d.at)
+        if solver == "chol":
+            rt = np.linalg.cholesky(P)
+        else:
+            rt = np.real(sla.sqrtm(P))
+        rows = rows_of(d, okey)
+        Y[rows] = np.linalg.solve(rt, Y[rows])
+        Psi[rows, :] = np.linalg.solve(rt, Psi[rows, :])
+    keep = np.nonzero(W != 0)[0]
+    return W[keep, None] * Psi[keep, :], W[keep] * Y[keep]
