@@ -1,5 +1,6 @@
 // capi.cu -- extern "C" entry points of libipf_b200 (see include/ipf_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <cmath>
@@ -485,6 +486,10 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
                 if (basis->blocks[k2].rc2 == rc) {
                     bool handled = false;
                     if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_2b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
+                    // IPF_3B_MOM=1 selects the "raw moments in HBM + combine" variant (basis_3b_mom.cu): parity-green,
+                    // producer 1.6x faster, consumer still latency-bound (50 vs 34 ms/step in round 1) -> off by default
+                    static const bool mom3b = getenv("IPF_3B_MOM") != nullptr;
+                    if (!ctx->force_generic && !handled && mom3b) IPF_CHECK(ipf_assemble_block_3b_mom(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!ctx->force_generic && !handled) IPF_CHECK(ipf_assemble_block_3b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!handled) IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
                 }

@@ -204,6 +204,8 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
                                const NeighList& nl, ipf_matrix* Psi);
 int ipf_assemble_block_2b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
                           ipf_matrix* Psi, bool* handled);
+int ipf_assemble_block_3b_mom(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                              ipf_matrix* Psi, bool* handled);
 int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
                           ipf_matrix* Psi, bool* handled);
 
