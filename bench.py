@@ -350,17 +350,23 @@ def run_ours(args):
     ms3, n3 = prof["site_deriv_3b"]
     ach3 = flops3 / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
     naive3 = clusters3 * cluster_flops(blk3) / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
-    r_mom = {"kernel": "moments3b_kernel (3-body basis values + derivatives per ordered pair)", "bound": "fp64",
-             "achieved": ach3, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach3 / fp64_peak, "traffic": None,
+    traffic = {}
+    tf = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tf):
+        traffic = json.load(open(tf))
+    r_mom = {"kernel": "moments3b_kernel<11, unit 0..7> (3-body basis values + derivatives per ordered pair; 8 unit launches per batch)",
+             "bound": "fp64", "achieved": ach3, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach3 / fp64_peak,
+             "traffic": traffic.get("moments3b", {}).get("dram_bytes_per_pair", 0) * pairs3 / max(1, n3) or None,
              "launches": n3, "avg_launch_ms": ms3 / max(1, n3), "algorithmic_flops_per_launch": flops3 / max(1, n3),
              "naive_algorithm_equivalent_tflops": naive3, "total_ms": ms3}
     # (b) gather kernel: HBM bytes = own + reverse scratch entry (32 B each) per (pair, function) + the rows written
     msg, ng = prof["gather_3b"]
-    bytes_g = pairs3 * blk3.nb * 64.0 + float(nrows) * blk3.nb * 8.0 * args.steps
+    bytes_g = pairs3 * blk3.nb * 24.0 + float(nrows) * blk3.nb * 8.0 * args.steps
     achg = bytes_g / (msg * 1e-3) * 1e-9 if msg > 0 else 0.0
     r_gat = {"kernel": "gather3b_kernel (scratch -> E/F/V rows)", "bound": "hbm", "achieved": achg, "peak": hbm_peak,
-             "unit": "GB/s", "frac": achg / hbm_peak, "traffic": None, "launches": ng, "avg_launch_ms": msg / max(1, ng),
-             "algorithmic_bytes_per_launch": bytes_g / max(1, ng), "total_ms": msg}
+             "unit": "GB/s", "frac": achg / hbm_peak, "traffic": traffic.get("gather3b", {}).get("dram_bytes_per_config", 0) * len(configs) * args.steps / max(1, ng) or None, "launches": ng, "avg_launch_ms": msg / max(1, ng),
+             "algorithmic_bytes_per_launch": bytes_g / max(1, ng), "total_ms": msg,
+             "note": "reads only the reverse entries (24 B); own sums come pre-reduced from the producer"}
     # (c) Gram kernel: algorithmic flops M n (n+1) (symmetric half) on the FP64 tensor pipe
     gram_ms, gram_n = prof["gram"]
     M = len(Irows)

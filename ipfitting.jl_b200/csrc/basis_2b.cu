@@ -48,8 +48,10 @@ __global__ void __launch_bounds__(P2_THREADS) pair2b_kernel(Pair2Args A) {
             double f0 = 0.0, f1 = 0.0, f2 = 0.0, e = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
             if (at < nat && blive) {
                 const int64_t s = a0 + at;
-                for (int64_t p = A.site_off[s]; p < A.site_off[s + 1]; ++p) {
-                    const double* r = A.rec + (int64_t)A.rs * p;
+                const int64_t pe = A.site_off[s + 1];
+#pragma unroll 4
+                for (int64_t p = A.site_off[s]; p < pe; ++p) {
+                    const double* __restrict__ r = A.rec + (int64_t)A.rs * p;
                     const double xb = r[REC + b + 1], xbm1 = r[REC + b];
                     const double radial = r[7] * xb + r[6] * (double)(b + 1) * xbm1 * r[5];
                     const double g0 = radial * r[0], g1 = radial * r[1], g2 = radial * r[2];

@@ -223,7 +223,7 @@ struct CombArgs {
 };
 
 constexpr int C_THREADS = 256;
-constexpr int C_NV = 8;            // visits (moment rows) staged per batch
+constexpr int C_NV = 32;           // visits (moment rows) staged per batch
 constexpr int C_CST = 32;          // doubles of per-visit constants
 constexpr int C_NFT = 2;           // basis functions per thread (nb <= 512)
 
@@ -231,8 +231,9 @@ template <int D>
 __global__ void __launch_bounds__(C_THREADS) combine3b_kernel(CombArgs A) {
     constexpr int NM = Lay<D>::NM;
     constexpr int NZ = Lay<D>::NZ;
-    __shared__ __align__(16) double rows[C_NV][NM];
-    __shared__ double cst[C_NV][C_CST];     // 0-2 Rhat, 3 fc'(r), 4 fc*x', 5 fc/r, 6-8 e1, 9-11 e2, 12 own(1)/rev(0),
+    extern __shared__ __align__(16) double c_smem[];
+    double (*rows)[NM] = reinterpret_cast<double (*)[NM]>(c_smem);
+    double (*cst)[C_CST] = reinterpret_cast<double (*)[C_CST]>(c_smem + C_NV * NM);     // 0-2 Rhat, 3 fc'(r), 4 fc*x', 5 fc/r, 6-8 e1, 9-11 e2, 12 own(1)/rev(0),
                                             // 13 fc/2, 14-16 R_p, 17.. x^0..x^D
     const int cfg = (int)(A.c0 + blockIdx.x);
     const int tid = threadIdx.x;
@@ -384,7 +385,13 @@ void launch_pair(ipf_ctx* ctx, const RawArgs& R, const CombArgs& C, int ncfg, cu
     cudaEventDestroy(produced);
     {
         ProfScope prof_(ctx, "gather_3b", st2);
-        combine3b_kernel<D><<<(unsigned)ncfg, C_THREADS, 0, st2>>>(C);
+        constexpr size_t csmem = sizeof(double) * (size_t)C_NV * (Lay<D>::NM + C_CST);
+        static bool cattr = false;
+        if (!cattr) {
+            cudaFuncSetAttribute(combine3b_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem);
+            cattr = true;
+        }
+        combine3b_kernel<D><<<(unsigned)ncfg, C_THREADS, csmem, st2>>>(C);
         ctx->launches++;
     }
 }
