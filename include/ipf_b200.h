@@ -85,7 +85,9 @@ void* ipf_stream(ipf_ctx* ctx);
 /* per-kernel device timing (CUDA events on the ctx stream), used by bench.py for the
  * roofline numbers.  Names: "neighbour_list", "pair_record", "site_deriv_2b|3b|4b|5b",
  * "k4_build", "gram", "cholesky", "trsm", "residual". */
-/* on = 1: use only the table-driven kernels (the specialised 3-body path is then bypassed) */
+/* kernel-path selection for tests and profiling.  on = 0: automatic (default); 1: only the table-driven kernels;
+ * 2: specialised kernels, but the 3-body block always takes the HBM-scratch + gather path (basis_3b.cu) instead of the
+ * configuration-resident kernel (basis_3b_cfg.cu) */
 int32_t ipf_set_force_generic(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_reset(ipf_ctx* ctx);

@@ -132,8 +132,10 @@ class Context:
             msg = self.lib.ipf_last_error(self.h).decode()
             raise IPFError(rc, _REF_MESSAGES.get(rc, msg) if rc in _REF_MESSAGES else msg)
 
-    def force_generic(self, on: bool = True):
-        self.lib.ipf_set_force_generic(self.h, 1 if on else 0)
+    def force_generic(self, on=True):
+        """Kernel-path selection (tests / profiling): False/0 automatic, True/1 table-driven kernels only,
+        2 = 3-body block through the HBM-scratch + gather path instead of the configuration-resident kernel."""
+        self.lib.ipf_set_force_generic(self.h, int(on))
 
     def profile(self, on: bool = True):
         self.lib.ipf_profile_enable(self.h, 1 if on else 0)

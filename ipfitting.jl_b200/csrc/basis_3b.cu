@@ -25,15 +25,15 @@
 // -- everything in a fixed order, no atomics, 768-byte coalesced reads per (pair, 32 columns).
 #include <cstdlib>
 
-#include "ipf_common.cuh"
+#include "basis_3b_shared.cuh"
 
 int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, const double** rec, int* rs);
+int ipf_assemble_block_3b_cfg(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                              ipf_matrix* Psi, int D, const double* rec, const int16_t* s2c, bool* handled);
 
 namespace {
 
-constexpr int REC = 8;
 constexpr int A_THREADS = 128;
-constexpr int MAXD = 14;
 
 struct Fast3Args {
     int64_t p0, np;                // batch pair range [p0, p0 + np)
@@ -50,40 +50,6 @@ struct Fast3Args {
     int nslot;                     // slot = (batch row / 32) - (site's first batch row / 32): warp-local piece sums
 };
 
-// number of basis functions with w-exponent c (degree-D basis): pairs a <= b, a + b <= D - c, minus the constant
-__host__ __device__ constexpr int nfun_c(int D, int c) {
-    int n = 0;
-    for (int a = 0; a <= (D - c) / 2; ++a) n += (D - c - a) - a + 1;
-    return n - (c == 0 ? 1 : 0);
-}
-__host__ __device__ constexpr int scol_base(int D, int C0) {
-    int n = 0;
-    for (int c = 0; c < C0; ++c) n += nfun_c(D, c);
-    return n;
-}
-
-__host__ __device__ constexpr int cmidx(int c, int a, int b) { return (c * (MAXD + 1) + a) * (MAXD + 1) + b; }
-
-__device__ __forceinline__ double4 ld4(const double* p) {
-    const double2 a = __ldg(reinterpret_cast<const double2*>(p));
-    const double2 b = __ldg(reinterpret_cast<const double2*>(p) + 1);
-    return make_double4(a.x, a.y, b.x, b.y);
-}
-
-template <int E>
-__device__ __forceinline__ double ipow_c(double w) {
-    if constexpr (E <= 0) return 1.0;
-    else if constexpr (E == 1) return w;
-    else {
-        const double h = ipow_c<E / 2>(w);
-        if constexpr (E % 2 == 0) return h * h;
-        else return h * h * w;
-    }
-}
-
-template <int D>
-struct RecStride { static constexpr int value = (REC + D + 2) & ~1; };
-
 constexpr int A_MAXREC = 224;              // pair records staged in shared memory per CTA
 constexpr int A_OUTG = 8;                  // functions per staged output group
 constexpr int A_OUTLD = 4 * A_OUTG + 2;    // doubles per staged row (+2: conflict-free 16-byte columns)
@@ -93,61 +59,6 @@ __host__ __device__ constexpr size_t moments_smem_bytes() {
     constexpr size_t a = sizeof(double) * (size_t)A_MAXREC * RecStride<D>::value;
     constexpr size_t b = sizeof(double) * (size_t)A_THREADS * A_OUTLD;
     return a + b;
-}
-
-// moment accumulation over the neighbours of the thread's centre atom; RK points at the record of
-// the first neighbour (shared or global memory: the caller instantiates one copy per address space)
-template <int D, int C0, int C1, int NC, int EMAX>
-__device__ __forceinline__ void moment_loop(const double* __restrict__ rk, int n, int jself, double Rj0, double Rj1,
-                                            double Rj2, const double (&E1)[3], const double (&E2)[3],
-                                            double (&Z)[NC][EMAX + 1], double (&U)[NC][EMAX + 1][2]) {
-    constexpr int RS = RecStride<D>::value;
-    for (int kk = 0; kk < n; ++kk, rk += RS) {
-        const double2 r01 = *reinterpret_cast<const double2*>(rk);
-        const double2 r23 = *reinterpret_cast<const double2*>(rk + 2);
-        const double2 a1 = *reinterpret_cast<const double2*>(rk + 6);      // fc, dfc
-        double xe[EMAX + 2];
-#pragma unroll
-        for (int e = 0; e <= EMAX; e += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(rk + REC + e);
-            xe[e] = v.x; xe[e + 1] = v.y;
-        }
-        const double w = Rj0 * r01.x + Rj1 * r01.y + Rj2 * r23.x;
-        const double q1 = E1[0] * r01.x + E1[1] * r01.y + E1[2] * r23.x;      // in-plane components of Rhat_k
-        const double q2 = E2[0] * r01.x + E2[1] * r01.y + E2[2] * r23.x;
-        const double fck = (kk == jself) ? 0.0 : a1.x;      // the own leg is not its own partner
-        // wl[ci] = fck w^(c-1), c = C0 + ci  (unused for c = 0)
-        double wl[NC];
-        if constexpr (C0 >= 1) {
-            wl[0] = fck * ipow_c<(C0 >= 1 ? C0 - 1 : 0)>(w);
-#pragma unroll
-            for (int ci = 1; ci < NC; ++ci) wl[ci] = wl[ci - 1] * w;
-        } else {
-            wl[0] = 0.0;
-            if constexpr (NC > 1) {
-                wl[1] = fck;
-#pragma unroll
-                for (int ci = 2; ci < NC; ++ci) wl[ci] = wl[ci - 1] * w;
-            }
-        }
-#pragma unroll
-        for (int e = 0; e <= EMAX; ++e) {
-#pragma unroll
-            for (int ci = 0; ci < NC; ++ci) {
-                const int c = C0 + ci;
-                if (e <= D - c) {
-                    if (c == 0) {
-                        Z[ci][e] = fma(xe[e], fck, Z[ci][e]);
-                    } else {
-                        const double t = xe[e] * wl[ci];          // fck x^e w^(c-1)
-                        U[ci][e][0] = fma(t, q1, U[ci][e][0]);
-                        U[ci][e][1] = fma(t, q2, U[ci][e][1]);
-                        Z[ci][e] = fma(t, w, Z[ci][e]);
-                    }
-                }
-            }
-        }
-    }
 }
 
 constexpr int A_EOFF = 3 * A_OUTG;         // staged row: [g(3) x A_OUTG][e x A_OUTG][pad 2]
@@ -370,34 +281,6 @@ __global__ void __launch_bounds__(A_THREADS) moments3b_kernel(Fast3Args A) {
     else run_all_units<D, 0>(A, T);
 }
 
-// unit tables: consecutive c packed while the accumulators fit (<= 44 doubles)
-template <int D>
-struct UnitTable {
-    int n = 0;
-    int c0[MAXD + 1] = {}, c1[MAXD + 1] = {};
-    int base[MAXD + 2] = {};      // first scratch column of every unit (unit sizes padded to even), [n] = row length
-    constexpr UnitTable() {
-        int c = 0;
-        int b = 0;
-        while (c <= D) {
-            int acc = 0, e = c;
-            while (e <= D) {
-                const int add = (e == 0 ? 1 : 3) * (D - e + 1);
-                if (acc > 0 && acc + add > 36) break;
-                acc += add;
-                ++e;
-            }
-            c0[n] = c; c1[n] = e - 1;
-            base[n] = b;
-            int nf = 0;
-            for (int cc = c; cc < e; ++cc) nf += nfun_c(D, cc);
-            b += (nf + 1) & ~1;
-            ++n;
-            c = e;
-        }
-        base[n] = b;
-    }
-};
 
 template <int D, int U>
 __device__ __forceinline__ void run_unit(const Fast3Args& A, const CtaState& T) {
@@ -628,6 +511,14 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     IPF_CHECK(s2c.alloc(ctx, h_s2c.size()));
     IPF_CUDA(ctx, cudaMemcpyAsync(s2c.p, h_s2c.data(), sizeof(int16_t) * h_s2c.size(), cudaMemcpyHostToDevice, st));
     IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_s2c is a local
+
+    // configuration-resident kernel (no HBM scratch) when every configuration of the chunk fits in shared memory;
+    // IPF_3B_SCRATCH=1 or ipf_set_force_generic(ctx, 2) forces the scratch + gather path below
+    static const bool force_scratch = getenv("IPF_3B_SCRATCH") != nullptr;
+    if (!force_scratch && !ctx->force_scratch3b) {
+        IPF_CHECK(ipf_assemble_block_3b_cfg(ctx, blk, ch, nl, Psi, D, rec, s2c.p, handled));
+        if (*handled) return IPF_OK;
+    }
 
     // batches of whole configurations; S (32 B per pair and function) lives in HBM, double buffered:
     // the gather of batch i (HBM bound, stream2) overlaps the moments of batch i+1 (FP64 bound, stream)

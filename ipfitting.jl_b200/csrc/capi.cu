@@ -123,7 +123,8 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
 // 1: always use the table-driven kernels (tests compare the two paths)
 int32_t ipf_set_force_generic(ipf_ctx* ctx, int32_t on) {
     if (!ctx) return IPF_EINVAL;
-    ctx->force_generic = on != 0;
+    ctx->force_generic = on == 1;
+    ctx->force_scratch3b = on == 2;
     return IPF_OK;
 }
 

@@ -74,16 +74,42 @@ def test_empty(ctx):
     assert db.Psi.shape == (0, 3)
 
 
+@pytest.mark.parametrize("path", ["cfg", "scratch"])
 @pytest.mark.parametrize("D", [2, 3, 5, 8, 11, 14])
-def test_3b_specialised_path(ctx, D):
-    """Canonical nbpolys(3, desc, D) goes through the moment-factorised kernels (basis_3b.cu)."""
+def test_3b_specialised_path(ctx, D, path):
+    """Canonical nbpolys(3, desc, D) goes through the moment-factorised kernels: the configuration-resident
+    kernel (basis_3b_cfg.cu, F accumulators in shared memory) or the HBM-scratch + gather path (basis_3b.cu)."""
     configs = (synth.rattled_configs("Si", 1, 2, seed=30 + D, calc=synth.StillingerWeber())
                + synth.rattled_configs("Si", 2, 1, seed=40 + D, calc=synth.StillingerWeber()))
     B = ipf.nbpolys(3, si_desc(2.5 if D <= 11 else 2.0), D)
     ctx.profile(True); ctx.profile_reset()
-    _check(B, configs, ctx)
-    assert ctx.profile_get("gather_3b")[1] > 0, "specialised 3-body path was not taken"
-    ctx.profile(False)
+    ctx.force_generic(2 if path == "scratch" else 0)
+    try:
+        _check(B, configs, ctx)
+        assert ctx.profile_get("site_deriv_3b")[1] > 0, "specialised 3-body path was not taken"
+        if D <= 11:      # D = 14: 64 atoms x 63 functions of the widest unit do not fit in shared memory -> scratch path
+            assert (ctx.profile_get("gather_3b")[1] > 0) == (path == "scratch")
+    finally:
+        ctx.force_generic(0)
+        ctx.profile(False)
+
+
+def test_3b_paths_agree_and_are_reproducible(ctx):
+    """Config-resident and scratch kernels sum in different (fixed) orders: equal to rounding; each is bit-reproducible.
+    Mixed sizes: single atoms, dimers (one pass, few rows) and 64-atom cells (several passes per configuration)."""
+    configs = (synth.rattled_configs("Si", 2, 3, seed=61, calc=synth.StillingerWeber())
+               + synth.rattled_configs("Si", 1, 2, seed=62, calc=synth.StillingerWeber(), vacancies=3))
+    B = ipf.nbpolys(3, si_desc(), 9)
+    a = LsqDB("", B, configs, ctx=ctx).Psi
+    b = LsqDB("", B, configs, ctx=ctx).Psi
+    assert np.array_equal(a, b)
+    ctx.force_generic(2)
+    try:
+        s = LsqDB("", B, configs, ctx=ctx).Psi
+    finally:
+        ctx.force_generic(0)
+    scale = np.abs(s).max(axis=0)
+    assert np.all(np.abs(a - s) <= 1e-12 * scale)
 
 
 def test_3b_specialised_equals_table_driven(ctx):
