@@ -24,29 +24,15 @@
 namespace {
 
 constexpr int REC = 8;   // head of a pair record: Rh[3], 1/r, x, dx/dr, fc, dfc/dr; then x^0..x^maxdeg (stride rs)
-constexpr double kPi = 3.14159265358979323846;
 
 __global__ void pair_record_kernel(int64_t npairs, const double* __restrict__ pR, int transform, double a,
                                    double r0, double rc1, double rc2, int maxdeg, int rs, double* __restrict__ rec) {
     const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= npairs) return;
     const double Rx = pR[3 * p], Ry = pR[3 * p + 1], Rz = pR[3 * p + 2];
-    const double r = sqrt(__dadd_rn(__dadd_rn(__dmul_rn(Rx, Rx), __dmul_rn(Ry, Ry)), __dmul_rn(Rz, Rz)));
+    const double r = ipf_bond_length(Rx, Ry, Rz);
     double x, dx, fc, dfc;
-    if (transform == 0) {
-        x = exp(-a * (r / r0 - 1.0));
-        dx = -a / r0 * x;
-    } else {
-        x = pow(r0 / r, a);
-        dx = -a * x / r;
-    }
-    if (r <= rc1) { fc = 1.0; dfc = 0.0; }
-    else if (r >= rc2) { fc = 0.0; dfc = 0.0; }
-    else {
-        const double w = rc2 - rc1, s = (r - rc1) / w;
-        fc = 0.5 * (1.0 + cos(kPi * s));
-        dfc = -0.5 * kPi / w * sin(kPi * s);
-    }
+    ipf_descriptor(r, transform, a, r0, rc1, rc2, x, dx, fc, dfc);
     double* o = rec + (int64_t)rs * p;
     o[0] = Rx / r; o[1] = Ry / r; o[2] = Rz / r; o[3] = 1.0 / r;
     o[4] = x; o[5] = dx; o[6] = fc; o[7] = dfc;

@@ -211,6 +211,30 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
                           ipf_matrix* Psi, bool* handled);
 
 // ---- device helpers ---------------------------------------------------------
+// distance transform x(r) and cutoff fc(r) of a descriptor with their r-derivatives (builder-defined maths,
+// basis.py: transform 0 = exp(-a (r/r0 - 1)), 1 = (r0/r)^a;  CosCut(rc1, rc2)); one definition for every kernel
+__device__ __forceinline__ void ipf_descriptor(double r, int transform, double a, double r0, double rc1, double rc2,
+                                               double& x, double& dx, double& fc, double& dfc) {
+    constexpr double kPiD = 3.14159265358979323846;
+    if (transform == 0) {
+        x = exp(-a * (r / r0 - 1.0));
+        dx = -a / r0 * x;
+    } else {
+        x = pow(r0 / r, a);
+        dx = -a * x / r;
+    }
+    if (r <= rc1) { fc = 1.0; dfc = 0.0; }
+    else if (r >= rc2) { fc = 0.0; dfc = 0.0; }
+    else {
+        const double w = rc2 - rc1, s = (r - rc1) / w;
+        fc = 0.5 * (1.0 + cos(kPiD * s));
+        dfc = -0.5 * kPiD / w * sin(kPiD * s);
+    }
+}
+__device__ __forceinline__ double ipf_bond_length(double Rx, double Ry, double Rz) {
+    return sqrt(__dadd_rn(__dadd_rn(__dmul_rn(Rx, Rx), __dmul_rn(Ry, Ry)), __dmul_rn(Rz, Rz)));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

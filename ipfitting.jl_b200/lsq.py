@@ -134,9 +134,11 @@ def collect_observations(db: LsqDB, weights: dict, Vref):
         if onebody:
             esel = (lay["key"] == 0) & live
             if esel.any():
-                e0 = np.array([Vref.energy(db.configs[i].at) for i in lay["cfg"][esel]])
-                Y = Y.copy()
-                Y[lay["first"][esel]] -= e0
+                if isinstance(Vref.E0, dict):
+                    e0 = np.array([Vref.energy(db.configs[i].at) for i in lay["cfg"][esel]])
+                else:                           # E0 * natoms, the same product OneBody.energy forms
+                    e0 = float(Vref.E0) * lay["nat"][esel]
+                Y[lay["first"][esel]] -= e0        # Y is a fresh array (concatenate above)
         W = np.repeat(np.where(live, wobs, 0.0), lay["len"])
         Icfg = np.repeat(np.where(live, lay["cfg"], -1), lay["len"])
         if not live.all():

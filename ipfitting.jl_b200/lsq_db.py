@@ -43,46 +43,67 @@ def _alloc_rows(configs: Sequence[Dat], layout: dict = None) -> int:
     """Row assignment of `_alloc_lsq_matrix` (`src/lsq_db.jl:237-250`): prefix sum of the
     observation lengths in `observations(configs)` order.  Returns nrows.  When `layout` is a dict
     it receives the per-observation arrays (config, okey id, first row, length, natoms, configtype id)
-    that `collect_observations` uses for its vectorised path."""
+    that `collect_observations` and `flatten_configs` use for their vectorised paths."""
     nrows = 0
-    cfg, key, first, length, nat, ctid = [], [], [], [], [], []
+    flat = []            # (config, okey id, first row, length, natoms, configtype id) per E/F/V observation
+    ext = flat.extend
     cts = {}
     plain = True
+    okid = _OKEY_ID.get
     for icfg, d in enumerate(configs):      # observations(configs) order: config-major, then D's key order
         ci = cts.setdefault(d.configtype, len(cts))
-        na = len(d.at)
+        na = d.at.X.shape[0]
+        rows = {}
         for okey, v in d.D.items():
-            n = len(v)
-            d.rows[okey] = (nrows, n)
-            k = _OKEY_ID.get(okey)
+            n = v.shape[0]
+            rows[okey] = (nrows, n)
+            k = okid(okey)
             if k is None:
                 plain = False
             else:
-                cfg.append(icfg); key.append(k); first.append(nrows); length.append(n); nat.append(na); ctid.append(ci)
+                ext((icfg, k, nrows, n, na, ci))
             nrows += n
+        d.rows = rows
     if layout is not None:
+        a = np.asarray(flat, dtype=np.int64).reshape(-1, 6)
         layout.update(nconfigs=len(configs), plain=plain, cts=list(cts.keys()), contiguous=plain,
-                      cfg=np.asarray(cfg, dtype=np.int64), key=np.asarray(key, dtype=np.int64),
-                      first=np.asarray(first, dtype=np.int64), len=np.asarray(length, dtype=np.int64),
-                      nat=np.asarray(nat, dtype=np.float64), ctid=np.asarray(ctid, dtype=np.int64))
+                      cfg=a[:, 0].copy(), key=a[:, 1].copy(), first=a[:, 2].copy(), len=a[:, 3].copy(),
+                      nat=a[:, 4].astype(np.float64), ctid=a[:, 5].copy())
     return nrows
 
 
-def flatten_configs(configs: Sequence[Dat]):
-    """The flat arrays `ipf_assemble` takes."""
+def flatten_configs(configs: Sequence[Dat], layout: dict = None):
+    """The flat arrays `ipf_assemble` takes.  `layout` (from `_alloc_rows` on the same list) gives the
+    1-based row blocks without another pass over the configurations."""
     ncfg = len(configs)
-    nat = np.fromiter((len(d.at) for d in configs), dtype=np.int64, count=ncfg)
+    ats = [d.at for d in configs]
+    nat = np.array([a.X.shape[0] for a in ats], dtype=np.int64)
     off = np.zeros(ncfg + 1, dtype=np.int64)
     np.cumsum(nat, out=off[1:])
     if ncfg:
-        pos = np.ascontiguousarray(np.concatenate([d.at.X for d in configs], axis=0), dtype=np.float64)
-        cell = np.ascontiguousarray(np.stack([d.at.cell for d in configs]), dtype=np.float64)
-        pbc = np.ascontiguousarray(np.stack([d.at.pbc for d in configs]).astype(np.uint8))
-        Z = np.ascontiguousarray(np.concatenate([d.at.Z for d in configs]), dtype=np.int32)
+        pos = np.ascontiguousarray(np.concatenate([a.X for a in ats], axis=0), dtype=np.float64)
+        cell = np.ascontiguousarray(np.concatenate([a.cell for a in ats]), dtype=np.float64).reshape(ncfg, 3, 3)
+        pbc = np.concatenate([a.pbc for a in ats]).astype(np.uint8).reshape(ncfg, 3)
+        Z = np.ascontiguousarray(np.concatenate([a.Z for a in ats]), dtype=np.int32)
     else:
         pos = np.zeros((0, 3)); cell = np.zeros((0, 3, 3)); pbc = np.zeros((0, 3), dtype=np.uint8)
         Z = np.zeros(0, dtype=np.int32)
     rows = {}
+    if layout and layout.get("nconfigs") == ncfg and "cfg" in layout:
+        lc, lk, lf, ll = layout["cfg"], layout["key"], layout["first"], layout["len"]
+        expect = np.where(lk == 0, 1, np.where(lk == 1, 3 * nat[lc], 6))
+        bad = np.nonzero(ll != expect)[0]
+        if bad.size:
+            b = int(bad[0])
+            k = (ENERGY, FORCES, VIRIAL)[int(lk[b])]
+            raise ValueError(f"observation {k} of config {int(lc[b])} has length {int(ll[b])}, "
+                             f"expected {int(expect[b])}")
+        for ki, k in enumerate((ENERGY, FORCES, VIRIAL)):
+            r = np.zeros(ncfg, dtype=np.int64)
+            m = lk == ki
+            r[lc[m]] = lf[m] + 1             # 1-based at the ABI, 0 = absent
+            rows[k] = r
+        return off, pos, cell, pbc, Z, rows
     for k in (ENERGY, FORCES, VIRIAL):
         r = np.zeros(ncfg, dtype=np.int64)
         for c, d in enumerate(configs):
@@ -140,7 +161,7 @@ class LsqDB:
         ctx = self._context()
         self._dev_basis = _capi.DeviceBasis(ctx, self.basis)
         self._Psi_dev = _capi.DeviceMatrix(ctx, self.nrows, len(self.basis))
-        off, pos, cell, pbc, Z, rows = flatten_configs(self.configs)
+        off, pos, cell, pbc, Z, rows = flatten_configs(self.configs, self._obs_layout)
         ctx.check(ctx.lib.ipf_assemble(
             ctx.h, self._dev_basis.h, len(self.configs), _capi.ptr(off, C.c_int64),
             _capi.ptr(pos, C.c_double), _capi.ptr(cell, C.c_double), _capi.ptr(pbc, C.c_uint8),
