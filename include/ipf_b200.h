@@ -89,6 +89,11 @@ void* ipf_stream(ipf_ctx* ctx);
  * 2: specialised kernels, but the 3-body block always takes the HBM-scratch + gather path (basis_3b.cu) instead of the
  * configuration-resident kernel (basis_3b_cfg.cu) */
 int32_t ipf_set_force_generic(ipf_ctx* ctx, int32_t on);
+/* on = 1: ipf_assemble / ipf_assemble_configs return as soon as the last kernels are queued on the ctx stream
+ * (no final synchronisation); every later call on this ctx is ordered behind them, and a device fault is
+ * reported by the next synchronising call.  Lets host-side work of the caller (collect_observations, ...) overlap
+ * the tail of the assembly.  Default 0: synchronous, errors reported by the call itself. */
+int32_t ipf_set_async(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_reset(ipf_ctx* ctx);
 int32_t ipf_profile_get(ipf_ctx* ctx, const char* name, double* ms, int64_t* count);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "ipf_launch_count": (C.c_int64, [_vp]),
     "ipf_stream": (_vp, [_vp]),
     "ipf_set_force_generic": (C.c_int32, [_vp, C.c_int32]),
+    "ipf_set_async": (C.c_int32, [_vp, C.c_int32]),
     "ipf_profile_enable": (C.c_int32, [_vp, C.c_int32]),
     "ipf_profile_reset": (C.c_int32, [_vp]),
     "ipf_profile_get": (C.c_int32, [_vp, C.c_char_p, _dp, _lp]),
@@ -136,6 +137,10 @@ class Context:
         """Kernel-path selection (tests / profiling): False/0 automatic, True/1 table-driven kernels only,
         2 = 3-body block through the HBM-scratch + gather path instead of the configuration-resident kernel."""
         self.lib.ipf_set_force_generic(self.h, int(on))
+
+    def set_async(self, on: bool = True):
+        """`ipf_assemble*` return without the final stream synchronisation (later calls are stream-ordered)."""
+        self.lib.ipf_set_async(self.h, 1 if on else 0)
 
     def profile(self, on: bool = True):
         self.lib.ipf_profile_enable(self.h, 1 if on else 0)

@@ -551,6 +551,7 @@ int ipf_assemble_block_3b_cfg(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev&
     IPF_CHECK(hdr.alloc(ctx, (size_t)npass_tot));
     IPF_CHECK(pblock.alloc(ctx, (size_t)npass_tot * pb_bytes(ngmax)));
     IPF_CUDA(ctx, cudaMemcpyAsync(pass_off.p, h_pass.data(), sizeof(int32_t) * h_pass.size(), cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_pass is a local; nothing long is queued yet
     if (maxpass > 0) {
         ProfScope prof_(ctx, "tsort_3b");
         dim3 grid((unsigned)ch.ncfg, (unsigned)maxpass);
@@ -585,7 +586,6 @@ int ipf_assemble_block_3b_cfg(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev&
         }
     }
     IPF_CUDA(ctx, cudaGetLastError());
-    IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_pass is a local
     *handled = true;
     return IPF_OK;
 }

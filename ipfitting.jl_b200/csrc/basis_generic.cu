@@ -25,20 +25,40 @@ namespace {
 
 constexpr int REC = 8;   // head of a pair record: Rh[3], 1/r, x, dx/dr, fc, dfc/dr; then x^0..x^maxdeg (stride rs)
 
-__global__ void pair_record_kernel(int64_t npairs, const double* __restrict__ pR, int transform, double a,
-                                   double r0, double rc1, double rc2, int maxdeg, int rs, double* __restrict__ rec) {
-    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= npairs) return;
-    const double Rx = pR[3 * p], Ry = pR[3 * p + 1], Rz = pR[3 * p + 2];
-    const double r = ipf_bond_length(Rx, Ry, Rz);
-    double x, dx, fc, dfc;
-    ipf_descriptor(r, transform, a, r0, rc1, rc2, x, dx, fc, dfc);
-    double* o = rec + (int64_t)rs * p;
-    o[0] = Rx / r; o[1] = Ry / r; o[2] = Rz / r; o[3] = 1.0 / r;
-    o[4] = x; o[5] = dx; o[6] = fc; o[7] = dfc;
-    double v = 1.0;
-    for (int e = 0; e <= maxdeg; ++e) { o[REC + e] = v; v *= x; }
-    for (int e = REC + maxdeg + 1; e < rs; ++e) o[e] = 0.0;
+// thread per pair; the 32 records of a warp are staged in shared memory and written as one contiguous run
+// (records are AoS: a per-thread store would touch 32 sectors per instruction)
+constexpr int PR_THREADS = 128;
+constexpr int PR_MAXRS = 32;
+
+__global__ void __launch_bounds__(PR_THREADS)
+pair_record_kernel(int64_t npairs, const double* __restrict__ pR, int transform, double a,
+                   double r0, double rc1, double rc2, int maxdeg, int rs, double* __restrict__ rec) {
+    __shared__ double tile[PR_THREADS / 32][32 * PR_MAXRS + 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t p0 = ((int64_t)blockIdx.x * PR_THREADS) + warp * 32;      // first pair of the warp
+    if (p0 >= npairs) return;
+    const int cnt = (int)min((int64_t)32, npairs - p0);
+    const int rsp = rs | 1;                 // odd stride in shared memory: conflict-free per-lane records
+    if (lane < cnt) {
+        const int64_t p = p0 + lane;
+        const double Rx = pR[3 * p], Ry = pR[3 * p + 1], Rz = pR[3 * p + 2];
+        const double r = ipf_bond_length(Rx, Ry, Rz);
+        double x, dx, fc, dfc;
+        ipf_descriptor(r, transform, a, r0, rc1, rc2, x, dx, fc, dfc);
+        double* o = tile[warp] + lane * rsp;
+        o[0] = Rx / r; o[1] = Ry / r; o[2] = Rz / r; o[3] = 1.0 / r;
+        o[4] = x; o[5] = dx; o[6] = fc; o[7] = dfc;
+        double v = 1.0;
+        for (int e = 0; e <= maxdeg; ++e) { o[REC + e] = v; v *= x; }
+        for (int e = REC + maxdeg + 1; e < rs; ++e) o[e] = 0.0;
+    }
+    __syncwarp();
+    double* out = rec + (int64_t)rs * p0;
+    const double* t = tile[warp];
+    for (int i = lane; i < cnt * rs; i += 32) {
+        const int q = i / rs, e = i - q * rs;
+        out[i] = t[q * rsp + e];
+    }
 }
 
 __device__ __forceinline__ double ipow(double w, int e) {
@@ -287,7 +307,7 @@ int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, con
     IPF_CHECK(ipf_scratch(ctx, 1, sizeof(double) * rs * (size_t)(npairs + 1), &rec));
     if (npairs > 0) {
         ProfScope prof_(ctx, "pair_record");
-        pair_record_kernel<<<(unsigned)((npairs + 255) / 256), 256, 0, ctx->stream>>>(
+        pair_record_kernel<<<(unsigned)((npairs + PR_THREADS - 1) / PR_THREADS), PR_THREADS, 0, ctx->stream>>>(
             npairs, nl.pR.p, blk.transform, blk.a, blk.r0, blk.rc1, blk.rc2, blk.maxdeg, rs, (double*)rec);
         ctx->launches++;
     }

@@ -128,6 +128,12 @@ int32_t ipf_set_force_generic(ipf_ctx* ctx, int32_t on) {
     return IPF_OK;
 }
 
+int32_t ipf_set_async(ipf_ctx* ctx, int32_t on) {
+    if (!ctx) return IPF_EINVAL;
+    ctx->async_assemble = on != 0;
+    return IPF_OK;
+}
+
 int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on) {
     if (!ctx) return IPF_EINVAL;
     ctx->profiling = on != 0;
@@ -496,7 +502,7 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
                 }
         }
     }
-    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!ctx->async_assemble) IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IPF_OK;
 }
 
@@ -509,7 +515,9 @@ int32_t ipf_assemble(ipf_ctx* ctx, const ipf_basis* basis, int64_t ncfg, const i
     IPF_CHECK(ipf_arena_reset_in(ctx, ctx->chunk_arena));
     IPF_CHECK(configs_create_impl(ctx, ncfg, atom_off, pos, cell, pbc, Z, rowE, rowF, rowV, &cf, &ctx->chunk_arena));
     const int rc = ipf_assemble_configs(ctx, basis, cf, Psi);
-    ipf_configs_destroy(ctx, cf);
+    // the chunks live in the recycled arena (stream-ordered reuse): only the host-side descriptors go away
+    if (ctx->async_assemble && rc == IPF_OK) delete cf;
+    else ipf_configs_destroy(ctx, cf);
     return rc;
 }
 

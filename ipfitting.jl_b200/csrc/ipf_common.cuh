@@ -37,6 +37,7 @@ struct ipf_ctx {
     cudaStream_t stream2 = nullptr;     // second stream: gather of batch n overlaps the moments of batch n+1
     bool profiling = false;
     bool force_generic = false;
+    bool async_assemble = false;    // ipf_assemble*: no final stream synchronisation
     bool force_scratch3b = false;   // 3-body: HBM-scratch path even when the configuration-resident kernel applies
     std::map<std::string, ProfEntry> prof;
     int device = 0;

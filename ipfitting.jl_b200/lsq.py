@@ -171,14 +171,18 @@ def collect_observations(db: LsqDB, weights: dict, Vref):
 
 def _select(db: LsqDB, Y, W, Icfg, Ibasis, Itrain):
     """Row/column selection of `get_lsq_system` (`src/lsq.jl:270-283`)."""
-    if np.isnan(Y).any():
+    # a NaN anywhere makes the sum NaN (no temporary); inf - inf can too, hence the exact re-check
+    if np.isnan(Y.sum()) and np.isnan(Y).any():
         raise _capi.IPFError(-4, "NaN detected in observations vector")
-    if np.isnan(W).any():
+    if np.isnan(W.sum()) and np.isnan(W).any():
         raise _capi.IPFError(-5, "NaN detected in weights vector")
-    keep = W != 0
-    if Itrain is not None:
+    if Itrain is None:
+        Irows = np.flatnonzero(W)            # NaN != 0 is excluded above
+    else:
+        keep = W != 0
         keep &= np.isin(Icfg, np.asarray(list(Itrain), dtype=np.int64))
-    Irows = np.nonzero(keep)[0].astype(np.int64)
+        Irows = np.flatnonzero(keep)
+    Irows = Irows.astype(np.int64, copy=False)
     Icols = None if Ibasis is None else np.asarray(list(Ibasis), dtype=np.int64)
     return Irows, Icols
 

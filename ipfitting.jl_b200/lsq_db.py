@@ -162,6 +162,16 @@ class LsqDB:
         self._dev_basis = _capi.DeviceBasis(ctx, self.basis)
         self._Psi_dev = _capi.DeviceMatrix(ctx, self.nrows, len(self.basis))
         off, pos, cell, pbc, Z, rows = flatten_configs(self.configs, self._obs_layout)
+        # no final synchronisation: the solve / download that follows is ordered behind the assembly on the
+        # context's stream, and the host-side work of lsqfit overlaps the last kernels
+        ctx.set_async(True)
+        try:
+            self._assemble_call(ctx, off, pos, cell, pbc, Z, rows)
+        finally:
+            ctx.set_async(False)
+        self._Psi_host = None
+
+    def _assemble_call(self, ctx, off, pos, cell, pbc, Z, rows):
         ctx.check(ctx.lib.ipf_assemble(
             ctx.h, self._dev_basis.h, len(self.configs), _capi.ptr(off, C.c_int64),
             _capi.ptr(pos, C.c_double), _capi.ptr(cell, C.c_double), _capi.ptr(pbc, C.c_uint8),
