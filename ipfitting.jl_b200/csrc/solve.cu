@@ -18,9 +18,13 @@
 // Cholesky triggers a diagonal shift (shifted CholeskyQR3) and one more pass.
 #include <cmath>
 
+#include <cstdlib>
+
 #include "ipf_common.cuh"
 
 int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, int n1, double* G, double* kernel_ms);
+
+int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpad, int ncp, int n, const double* L);
 
 struct ipf_solver {
     int64_t M = 0, Mpad = 0;        // local rows (selected, weight != 0), padded to 16
@@ -854,10 +858,17 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         IPF_CUDA(ctx, cudaEventCreate(&e0));
         IPF_CUDA(ctx, cudaEventCreate(&e1));
         IPF_CUDA(ctx, cudaEventRecord(e0, st));
+        // A <- A L^-T: product with the explicit inverse on the FP64 tensor cores (trmm.cu);
+        // IPF_TRSM_ROWS=1 selects the thread-per-row substitution on the FMA pipe (2.5x slower, kept for A/B runs)
+        static const bool trsm_rows = getenv("IPF_TRSM_ROWS") != nullptr;
         { ProfScope prof_(ctx, "trsm");
-        trsm_rows_kernel<<<(unsigned)((S->Mpad + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, 0, st>>>(S->A, S->Mpad, S->M, S->L, n); }
+        if (trsm_rows) {
+            trsm_rows_kernel<<<(unsigned)((S->Mpad + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, 0, st>>>(S->A, S->Mpad, S->M, S->L, n);
+            ctx->launches++;
+        } else {
+            IPF_CHECK(ipf_apply_inverse_transpose(ctx, S->A, S->Mpad, S->Mpad, S->ncp, n, S->L));
+        } }
         IPF_CUDA(ctx, cudaEventRecord(e1, st));
-        ctx->launches++;
         IPF_CUDA(ctx, cudaStreamSynchronize(st));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
