@@ -295,7 +295,7 @@ int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, con
     const int64_t npairs = nl.npairs;
     // reuse the records of the previous block when it had the same descriptor on the same neighbour list
     // (e.g. nbpolys(2, D, 14) followed by nbpolys(3, D, 11)) and at least this block's degree
-    if (ctx->rec_nl == (const void*)&nl && ctx->rec_npairs == npairs && ctx->rec_transform == blk.transform &&
+    if (ctx->rec_nl == nl.serial && nl.serial >= 0 && ctx->rec_npairs == npairs && ctx->rec_transform == blk.transform &&
         ctx->rec_a == blk.a && ctx->rec_r0 == blk.r0 && ctx->rec_rc1 == blk.rc1 && ctx->rec_rc2 == blk.rc2 &&
         ctx->rec_maxdeg == blk.maxdeg && ctx->rec_ptr) {
         *rec_out = ctx->rec_ptr;
@@ -313,7 +313,7 @@ int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, con
     }
     *rec_out = (const double*)rec;
     *rs_out = rs;
-    ctx->rec_nl = (const void*)&nl; ctx->rec_npairs = npairs; ctx->rec_transform = blk.transform;
+    ctx->rec_nl = nl.serial; ctx->rec_npairs = npairs; ctx->rec_transform = blk.transform;
     ctx->rec_a = blk.a; ctx->rec_r0 = blk.r0; ctx->rec_rc1 = blk.rc1; ctx->rec_rc2 = blk.rc2;
     ctx->rec_maxdeg = blk.maxdeg; ctx->rec_ptr = (const double*)rec; ctx->rec_rs = rs;
     return IPF_OK;

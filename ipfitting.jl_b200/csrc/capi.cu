@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <new>
 
@@ -479,17 +480,24 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
         return ipf_set_error(ctx, IPF_EINVAL, "ipf_assemble: row block out of range (%lld > %lld rows)",
                              (long long)cf->max_row, (long long)Psi->nrows);
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    // distinct cutoffs, largest first: its neighbour list is built from the positions, the lists of the smaller
+    // cutoffs are sub-lists of it (ipf_filter_neighbours; IPF_NL_REBUILD=1 builds every list from scratch)
+    std::vector<double> cutoffs;
+    for (const BlockDev& b : basis->blocks)
+        if (std::find(cutoffs.begin(), cutoffs.end(), b.rc2) == cutoffs.end()) cutoffs.push_back(b.rc2);
+    std::sort(cutoffs.begin(), cutoffs.end(), std::greater<double>());
+    static const bool nl_rebuild = getenv("IPF_NL_REBUILD") != nullptr;
     for (const ChunkDev* ch : cf->chunks) {
-        // one neighbour list per distinct cutoff
-        std::vector<double> done_rcut;
-        for (size_t k = 0; k < basis->blocks.size(); ++k) {
-            const double rc = basis->blocks[k].rc2;
-            if (std::find(done_rcut.begin(), done_rcut.end(), rc) != done_rcut.end()) continue;
-            done_rcut.push_back(rc);
-            NeighList nl;
-            IPF_CHECK(ipf_arena_reset(ctx));
-            IPF_CHECK(ipf_build_neighbours(ctx, *ch, rc, nl));
-            for (size_t k2 = k; k2 < basis->blocks.size(); ++k2)
+        IPF_CHECK(ipf_arena_reset(ctx));
+        NeighList big;
+        for (size_t ic = 0; ic < cutoffs.size(); ++ic) {
+            const double rc = cutoffs[ic];
+            NeighList sub;
+            if (ic == 0) IPF_CHECK(ipf_build_neighbours(ctx, *ch, rc, big));
+            else if (nl_rebuild) IPF_CHECK(ipf_build_neighbours(ctx, *ch, rc, sub));
+            else IPF_CHECK(ipf_filter_neighbours(ctx, *ch, big, rc, sub));
+            const NeighList& nl = ic == 0 ? big : sub;
+            for (size_t k2 = 0; k2 < basis->blocks.size(); ++k2)
                 if (basis->blocks[k2].rc2 == rc) {
                     bool handled = false;
                     if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_2b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));

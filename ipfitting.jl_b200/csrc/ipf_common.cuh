@@ -30,7 +30,8 @@ struct ipf_ctx {
     Arena chunk_arena;                  // configuration chunks of the host-pointer ipf_assemble (transient)
     int active_solvers = 0;
     // pair-record cache key (see ipf_pair_records)
-    const void* rec_nl = nullptr; int64_t rec_npairs = -1; int rec_transform = -1, rec_maxdeg = -1, rec_rs = 0;
+    int64_t nl_serial = 0;           // neighbour lists built so far (identity of a list for the record cache)
+    int64_t rec_nl = -1; int64_t rec_npairs = -1; int rec_transform = -1, rec_maxdeg = -1, rec_rs = 0;
     double rec_a = 0, rec_r0 = 0, rec_rc1 = 0, rec_rc2 = 0; const double* rec_ptr = nullptr;
     double* matrix_cache = nullptr;     // one recycled design-matrix allocation (avoids cudaMalloc/cudaFree per LsqDB)
     size_t matrix_cache_bytes = 0;
@@ -170,6 +171,7 @@ struct FlexBuf {
 
 // ---- neighbour list of a chunk of configurations (device resident, arena backed) -------
 struct NeighList {
+    int64_t serial = -1;      // unique per built list (ipf_ctx::nl_serial)
     int64_t nsites = 0;       // atoms in the chunk
     int64_t npairs = 0;
     int32_t maxpairs_cfg = 0; // max pairs of one config
@@ -202,6 +204,7 @@ struct ChunkDev {
 };
 
 int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighList& nl);
+int ipf_filter_neighbours(ipf_ctx* ctx, const ChunkDev& ch, const NeighList& big, double rcut, NeighList& nl);
 int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
                                const NeighList& nl, ipf_matrix* Psi);
 int ipf_assemble_block_2b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,

@@ -232,10 +232,129 @@ __global__ void nl_reverse_kernel(int64_t npairs, const int64_t* __restrict__ si
     prev[p] = found;
 }
 
+// ---- derive the list of a smaller cutoff from an existing one -------------------------------------------
+__global__ void nlf_flag_kernel(int64_t npairs, const double* __restrict__ pR, double rc2, int32_t* __restrict__ keep) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > npairs) return;
+    if (p == npairs) { keep[p] = 0; return; }
+    const double R0 = pR[3 * p], R1 = pR[3 * p + 1], R2 = pR[3 * p + 2];
+    // same individually rounded sum and comparison as pair_r2() / nl_pairs_kernel
+    const double r2 = __dadd_rn(__dadd_rn(__dmul_rn(R0, R0), __dmul_rn(R1, R1)), __dmul_rn(R2, R2));
+    keep[p] = r2 < rc2 ? 1 : 0;
+}
+
+// new site / config offsets = new index of the old offsets; [ncfg+1] = max neighbours of one site
+__global__ void nlf_offsets_kernel(int64_t nsites, int64_t ncfg, const int64_t* __restrict__ site_off_old,
+                                   const int64_t* __restrict__ cfg_off_old, const int32_t* __restrict__ newidx,
+                                   int64_t* __restrict__ site_off, int64_t* __restrict__ cfg_off) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= nsites) site_off[s] = newidx[site_off_old[s]];
+    if (s <= ncfg) cfg_off[s] = newidx[cfg_off_old[s]];
+    if (s < nsites) {
+        const int64_t cnt = (int64_t)newidx[site_off_old[s + 1]] - newidx[site_off_old[s]];
+        atomicMax((unsigned long long*)(cfg_off + ncfg + 1), (unsigned long long)cnt);
+    }
+}
+
+__global__ void nlf_compact_kernel(int64_t npairs, const int32_t* __restrict__ keep, const int32_t* __restrict__ newidx,
+                                   const int64_t* __restrict__ site_off,
+                                   const int32_t* __restrict__ pi0, const int32_t* __restrict__ pj0,
+                                   const int32_t* __restrict__ psite0, const int32_t* __restrict__ pS0,
+                                   const double* __restrict__ pR0, const int32_t* __restrict__ prev0,
+                                   int32_t* __restrict__ pi, int32_t* __restrict__ pj, int32_t* __restrict__ psite,
+                                   int64_t* __restrict__ pbeg, int32_t* __restrict__ pcnt, int32_t* __restrict__ pS,
+                                   double* __restrict__ pR, int32_t* __restrict__ prev) {
+    const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= npairs || !keep[p]) return;
+    const int64_t q = newidx[p];
+    const int32_t s = psite0[p];
+    pi[q] = pi0[p]; pj[q] = pj0[p]; psite[q] = s;
+    pbeg[q] = site_off[s];
+    pcnt[q] = (int32_t)(site_off[s + 1] - site_off[s]);
+    pS[3 * q] = pS0[3 * p]; pS[3 * q + 1] = pS0[3 * p + 1]; pS[3 * q + 2] = pS0[3 * p + 2];
+    pR[3 * q] = pR0[3 * p]; pR[3 * q + 1] = pR0[3 * p + 1]; pR[3 * q + 2] = pR0[3 * p + 2];
+    const int32_t rv = prev0[p];
+    prev[q] = rv >= 0 ? newidx[rv] : -1;          // the reverse pair has the same length: it is kept too
+}
+
 }  // namespace
+
+// Neighbour list of cutoff rcut <= big.rcut as the sub-list of `big` (same chunk): identical, entry for entry,
+// to ipf_build_neighbours(ctx, ch, rcut, nl) -- the accept test is re-evaluated on the stored bond vectors with
+// the same rounded operations, and the order within a site is inherited -- at a fraction of the cost.
+int ipf_filter_neighbours(ipf_ctx* ctx, const ChunkDev& ch, const NeighList& big, double rcut, NeighList& nl) {
+    const int64_t ncfg = ch.ncfg, nsites = ch.natoms;
+    nl.serial = ctx->nl_serial++;
+    nl.nsites = nsites;
+    nl.rcut = rcut;
+    nl.npairs = 0;
+    nl.maxpairs_cfg = 0;
+    nl.max_nbrs = 0;
+    nl.h_cfg_pair_off.assign(ncfg + 2, 0);
+    nl.h_site_off.clear();
+    cudaStream_t st = ctx->stream;
+    IPF_CHECK(nl.site_off.alloc(ctx, nsites + 1));
+    IPF_CHECK(nl.cfg_pair_off.alloc(ctx, ncfg + 2));
+    if (nsites == 0 || big.npairs == 0) {
+        IPF_CUDA(ctx, cudaMemsetAsync(nl.site_off.p, 0, sizeof(int64_t) * (nsites + 1), st));
+        IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p, 0, sizeof(int64_t) * (ncfg + 2), st));
+        IPF_CHECK(nl.pi.alloc(ctx, 0)); IPF_CHECK(nl.pj.alloc(ctx, 0)); IPF_CHECK(nl.psite.alloc(ctx, 0));
+        IPF_CHECK(nl.pbeg.alloc(ctx, 0)); IPF_CHECK(nl.pcnt.alloc(ctx, 0)); IPF_CHECK(nl.pS.alloc(ctx, 0));
+        IPF_CHECK(nl.pR.alloc(ctx, 0)); IPF_CHECK(nl.prev.alloc(ctx, 0));
+        return IPF_OK;
+    }
+    ProfScope prof_(ctx, "neighbour_list");
+    const int64_t np0 = big.npairs;
+    ABuf<int32_t> keep, newidx;
+    IPF_CHECK(keep.alloc(ctx, np0 + 1));
+    IPF_CHECK(newidx.alloc(ctx, np0 + 1));
+    const unsigned nbp = (unsigned)((np0 + 1 + 255) / 256);
+    nlf_flag_kernel<<<nbp, 256, 0, st>>>(np0, big.pR.p, rcut * rcut, keep.p);
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, keep.p, newidx.p, (int)(np0 + 1), st);
+    void* tmp = nullptr;
+    IPF_CHECK(ipf_arena_alloc(ctx, tmp_bytes, &tmp));
+    IPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, keep.p, newidx.p, (int)(np0 + 1), st));
+    IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p + ncfg + 1, 0, sizeof(int64_t), st));
+    const int64_t nmax = std::max(nsites, ncfg) + 1;
+    nlf_offsets_kernel<<<(unsigned)((nmax + 255) / 256), 256, 0, st>>>(nsites, ncfg, big.site_off.p, big.cfg_pair_off.p,
+                                                                      newidx.p, nl.site_off.p, nl.cfg_pair_off.p);
+    ctx->launches += 3;
+    IPF_CUDA(ctx, cudaMemcpyAsync(nl.h_cfg_pair_off.data(), nl.cfg_pair_off.p, sizeof(int64_t) * (ncfg + 2),
+                                  cudaMemcpyDeviceToHost, st));
+    if (ctx->profiling) {
+        nl.h_site_off.assign(nsites + 1, 0);
+        IPF_CUDA(ctx, cudaMemcpyAsync(nl.h_site_off.data(), nl.site_off.p, sizeof(int64_t) * (nsites + 1),
+                                      cudaMemcpyDeviceToHost, st));
+    }
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    const int64_t npairs = nl.h_cfg_pair_off[ncfg];
+    nl.max_nbrs = (int32_t)nl.h_cfg_pair_off[ncfg + 1];
+    nl.npairs = npairs;
+    int64_t mx = 0;
+    for (int64_t c = 0; c < ncfg; ++c) mx = std::max<int64_t>(mx, nl.h_cfg_pair_off[c + 1] - nl.h_cfg_pair_off[c]);
+    nl.maxpairs_cfg = (int32_t)mx;
+    IPF_CHECK(nl.pi.alloc(ctx, npairs));
+    IPF_CHECK(nl.pj.alloc(ctx, npairs));
+    IPF_CHECK(nl.psite.alloc(ctx, npairs));
+    IPF_CHECK(nl.pbeg.alloc(ctx, npairs));
+    IPF_CHECK(nl.pcnt.alloc(ctx, npairs));
+    IPF_CHECK(nl.pS.alloc(ctx, 3 * npairs));
+    IPF_CHECK(nl.pR.alloc(ctx, 3 * npairs));
+    IPF_CHECK(nl.prev.alloc(ctx, npairs));
+    if (npairs == 0) return IPF_OK;
+    nlf_compact_kernel<<<(unsigned)((np0 + 255) / 256), 256, 0, st>>>(np0, keep.p, newidx.p, nl.site_off.p, big.pi.p, big.pj.p,
+                                                                     big.psite.p, big.pS.p, big.pR.p, big.prev.p, nl.pi.p,
+                                                                     nl.pj.p, nl.psite.p, nl.pbeg.p, nl.pcnt.p, nl.pS.p,
+                                                                     nl.pR.p, nl.prev.p);
+    ctx->launches++;
+    IPF_CUDA(ctx, cudaGetLastError());
+    return IPF_OK;
+}
 
 int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighList& nl) {
     const int64_t ncfg = ch.ncfg, nsites = ch.natoms;
+    nl.serial = ctx->nl_serial++;
     nl.nsites = nsites;
     nl.rcut = rcut;
     nl.npairs = 0;

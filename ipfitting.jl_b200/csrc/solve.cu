@@ -806,8 +806,11 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     if (S->pass >= 1) S->defect = defect;
     if (!final_pass && S->pass >= 6)
         return ipf_set_error(ctx, IPF_ESINGULAR, "CholeskyQR did not reach orthogonality in %d passes (defect %.3e)", S->pass, defect);
-    // Cholesky with escalating shift
-    double shift = 0.0;
+    // Cholesky with escalating shift.  The first pass always carries the smallest shift (1e-15 n on the unit
+    // diagonal of the equilibrated matrix): it only perturbs the intermediate factor -- the later passes
+    // re-orthogonalise, and the accuracy of the solution is set by the last one -- and it saves the failed
+    // attempt that every ill-conditioned system (the common case for these bases) would otherwise pay for.
+    double shift = S->pass == 0 ? 1e-15 * (double)n : 0.0;
     equil_kernel<<<(n + 255) / 256, 256, 0, st>>>(S->G, n1, n, S->dscale);
     ctx->launches++;
     for (int attempt = 0;; ++attempt) {

@@ -147,3 +147,22 @@ def test_2b_specialised_equals_table_driven(ctx):
         ctx.force_generic(False)
     scale = np.abs(slow).max(axis=0)
     assert (np.abs(fast - slow).max(axis=0) <= 1e-13 * scale).all()
+
+
+def test_equal_sized_chunks_do_not_share_pair_records(ctx):
+    """Two device chunks (> 65536 atoms in total) with the SAME pair count but different geometries: the second
+    chunk must get its own pair records (the record cache is keyed on the neighbour-list identity, not its size)."""
+    rng = np.random.Generator(np.random.Philox(key=77))
+    base = synth.repeat(synth.bulk("Si"), 2)                       # 64 atoms
+    X = synth.rattle(base, 0.02, rng)                               # small rattles: neighbour shells stay separated,
+    Y = synth.rattle(base, 0.02, rng)                               # so both have the same number of pairs
+    from ipfitting_jl_b200.prototypes import Dat
+    mk = lambda at: Dat(at, "rand", E=0.0, F=np.zeros((64, 3)), V=np.zeros((3, 3)))
+    B = ipf.nbpolys(2, si_desc(), 4) + ipf.nbpolys(3, si_desc(2.0), 4)
+    ref = LsqDB("", B, [mk(X), mk(Y)], ctx=ctx).Psi
+    assert not np.allclose(ref[:199], ref[199:])
+    big = LsqDB("", B, [mk(X) for _ in range(1024)] + [mk(Y) for _ in range(1024)], ctx=ctx).Psi
+    assert np.array_equal(big[:199], ref[:199])
+    assert np.array_equal(big[1023 * 199:1024 * 199], ref[:199])
+    assert np.array_equal(big[1024 * 199:1025 * 199], ref[199:])
+    assert np.array_equal(big[2047 * 199:], ref[199:])
