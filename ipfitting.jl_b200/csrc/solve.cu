@@ -342,7 +342,7 @@ __global__ void rprod_kernel(const double* __restrict__ L, const double* __restr
 
 // mode 0: solve L w = b (lower, forward);  mode 1: solve R x = b (upper, backward).  x overwrites b.
 // Blocked by 32: warp 0 solves the diagonal block, all threads update the remaining right-hand side.
-__global__ void __launch_bounds__(1024) trsv_kernel(const double* __restrict__ T, int n, double* __restrict__ b, int mode) {
+__global__ void __launch_bounds__(256) trsv_kernel(const double* __restrict__ T, int n, double* __restrict__ b, int mode) {
     extern __shared__ double s_x[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int k = tid; k < n; k += blockDim.x) s_x[k] = b[k];
@@ -352,23 +352,33 @@ __global__ void __launch_bounds__(1024) trsv_kernel(const double* __restrict__ T
         const int J0 = (mode == 0) ? bi * KB : (nblk - 1 - bi) * KB;
         const int nbk = min(KB, n - J0);
         if (warp == 0) {
+            // lane i holds row i of the diagonal block (32 coalesced loads, issued back to back) and its right-hand
+            // side; the recurrence then runs out of registers: x_j by shuffle, reciprocal diagonal by one division
+            double d[KB];
+#pragma unroll
+            for (int j = 0; j < KB; ++j)
+                d[j] = (j < nbk && lane < nbk) ? T[(size_t)(J0 + j) * n + J0 + lane] : (j == lane ? 1.0 : 0.0);
+            double dii = 1.0;
+#pragma unroll
+            for (int j = 0; j < KB; ++j) if (j == lane) dii = d[j];
+            const double rd = 1.0 / dii;
+            double sv = lane < nbk ? s_x[J0 + lane] : 0.0;
             if (mode == 0) {
-                for (int j = 0; j < nbk; ++j) {
-                    const double xj = s_x[J0 + j] / T[(size_t)(J0 + j) * n + J0 + j];
-                    __syncwarp();
-                    if (lane == j) s_x[J0 + j] = xj;
-                    if (lane > j && lane < nbk) s_x[J0 + lane] -= T[(size_t)(J0 + j) * n + J0 + lane] * xj;
-                    __syncwarp();
+#pragma unroll
+                for (int j = 0; j < KB; ++j) {
+                    const double xj = __shfl_sync(0xffffffffu, sv * rd, j);
+                    if (lane == j) sv = xj;
+                    else if (lane > j) sv = fma(-d[j], xj, sv);
                 }
             } else {
-                for (int j = nbk - 1; j >= 0; --j) {
-                    const double xj = s_x[J0 + j] / T[(size_t)(J0 + j) * n + J0 + j];
-                    __syncwarp();
-                    if (lane == j) s_x[J0 + j] = xj;
-                    if (lane < j) s_x[J0 + lane] -= T[(size_t)(J0 + j) * n + J0 + lane] * xj;
-                    __syncwarp();
+#pragma unroll
+                for (int j = KB - 1; j >= 0; --j) {
+                    const double xj = __shfl_sync(0xffffffffu, sv * rd, j);
+                    if (lane == j) sv = xj;
+                    else if (lane < j) sv = fma(-d[j], xj, sv);
                 }
             }
+            if (lane < nbk) s_x[J0 + lane] = sv;
         }
         __syncthreads();
         // update the rest: rows below (mode 0) / above (mode 1) the block
@@ -850,7 +860,7 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     if (final_pass) {
         // c = Rtot^-1 (L^-1 z),  z = G[0:n, n]
         IPF_CUDA(ctx, cudaMemcpyAsync(S->vec, S->G + (size_t)n * n1, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-        trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, S->vec, 0);
+        trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->L, n, S->vec, 0);
         // residual in the orthonormal basis needs c'' = L^-T (L^-1 z): compute it into G's scratch later;
         // here keep w = L^-1 z in vec and the solution in vec[n..): not needed, finish computes both.
         ctx->launches++;
@@ -903,10 +913,10 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     double* g = S->work + S->n1;
     double* cf = S->work + 2 * S->n1;
     IPF_CUDA(ctx, cudaMemcpyAsync(cc, S->vec, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Lt, n, cc, 1);
+    trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->Lt, n, cc, 1);
     normal_residual_kernel<<<nvb, 256, 0, st>>>(S->G, S->n1, n, cc, g);
-    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->L, n, g, 0);
-    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Lt, n, g, 1);
+    trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->L, n, g, 0);
+    trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->Lt, n, g, 1);
     add_vec_kernel<<<nvb, 256, 0, st>>>(cc, g, n);
     const int64_t nb = (S->Mpad + 255) / 256;
     { ProfScope prof_(ctx, "residual");
@@ -915,7 +925,7 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     // solution in the original (scaled) basis: A_p = A_0 Rprev^-1  =>  c = Rprev^-1 cc
     // (Rtmp holds Rprev: factor swapped it out when it formed Rtot = L^T Rprev)
     IPF_CUDA(ctx, cudaMemcpyAsync(cf, cc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    trsv_kernel<<<1, 1024, sizeof(double) * n, st>>>(S->Rtmp, n, cf, 1);
+    trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->Rtmp, n, cf, 1);
     if (S->dinv) scale_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(cf, S->dinv, n);
     ctx->launches += 4;
     ctx->launches += 6;

@@ -150,15 +150,19 @@ __global__ void __launch_bounds__(32 * TI_WARPS) trinv_kernel(const double* __re
         double s = (i == c) ? 1.0 : 0.0;
         if (live)
             for (int k = c; k < b0; ++k) s = fma(-L[(size_t)k * n + i], xs[k], s);
-        // in-block recurrence: x_t = s_t / L[t][t];  s_i -= L[i][t] x_t  (i > t)
+        // in-block recurrence: x_t = s_t / L[t][t];  s_i -= L[i][t] x_t  (i > t).  Lane i preloads row i of the
+        // diagonal block (32 coalesced loads in flight at once); the recurrence runs out of registers.
+        double d[32];
+#pragma unroll
+        for (int t = 0; t < 32; ++t) d[t] = (i < n && b0 + t < n) ? L[(size_t)(b0 + t) * n + i] : 0.0;
+        const double rdi = rdiag[min(i, n - 1)];
+#pragma unroll
         for (int t = 0; t < 32; ++t) {
             const int it = b0 + t;
-            if (it >= n) break;
-            double xt = (lane == t) ? s * rdiag[min(i, n - 1)] : 0.0;
-            xt = __shfl_sync(0xffffffffu, xt, t);
-            if (it < c) continue;
+            const double xt = __shfl_sync(0xffffffffu, s * rdi, t);
+            if (it >= n || it < c) continue;      // uniform
             if (lane == t) s = xt;
-            else if (live && i > it) s = fma(-L[(size_t)it * n + i], xt, s);
+            else if (live && i > it) s = fma(-d[t], xt, s);
         }
         if (live) {
             xs[i] = s;
