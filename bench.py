@@ -293,7 +293,7 @@ def run_ours(args):
     ms_dev = e0.elapsed_time(e1)
     launches = ctx.launches - l0
     prof = {k: ctx.profile_get(k) for k in ("neighbour_list", "pair_record", "site_deriv_2b", "site_deriv_3b", "gather_3b",
-                                             "k4_build", "gram", "cholesky", "trsm", "residual")}
+                                             "tsort_3b", "k4_build", "gram", "cholesky", "trsm", "residual")}
     clusters3 = ctx.profile_get("count:clusters_3b")[0]
     ordered3 = ctx.profile_get("count:ordered_pairs_3b")[0]
     pairs3 = ctx.profile_get("count:pairs_3b")[0]
@@ -346,7 +346,11 @@ def run_ours(args):
     f_k = 15 + D + 7 * (D * (D + 1) // 2) + 2 * (D + 1)         # per ordered neighbour pair (j, k)
     n_single = int(np.sum(np.bincount(blk3.mono_b) == 1)); n_double = blk3.nb - n_single
     f_comb = 36 * n_double + 30 * n_single                      # per own leg: combine moments into all functions
-    flops3 = ordered3 * f_k + pairs3 * f_comb
+    # per own leg and function: F[i] += g, F[j] -= g (6 adds), E += e (1), six Voigt products of the virial (12)
+    f_scatter = 19 * blk3.nb
+    msg, ng = prof["gather_3b"]
+    resident = ng == 0            # configuration-resident kernel: moments + combine + in-SM scatter in one kernel
+    flops3 = ordered3 * f_k + pairs3 * (f_comb + (f_scatter if resident else 0))
     ms3, n3 = prof["site_deriv_3b"]
     ach3 = flops3 / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
     naive3 = clusters3 * cluster_flops(blk3) / (ms3 * 1e-3) * 1e-12 if ms3 > 0 else 0.0
@@ -354,13 +358,19 @@ def run_ours(args):
     tf = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
     if os.path.exists(tf):
         traffic = json.load(open(tf))
-    r_mom = {"kernel": "moments3b_kernel<11, unit 0..7> (3-body basis values + derivatives per ordered pair; 8 unit launches per batch)",
+    tkey = "cfg3b" if resident else "moments3b"
+    kname = (f"cfg3b_kernel<{D}, unit 0..7> (configuration-resident 3-body kernel: moments + combine + scatter into the "
+             "E/F/V rows from shared memory; one launch per unit and chunk)" if resident else
+             f"moments3b_kernel<{D}, unit 0..7> (3-body basis values + derivatives per ordered pair; 8 unit launches per batch)")
+    r_mom = {"kernel": kname,
              "bound": "fp64", "achieved": ach3, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach3 / fp64_peak,
-             "traffic": traffic.get("moments3b", {}).get("dram_bytes_per_pair", 0) * pairs3 / max(1, n3) or None,
+             "traffic": traffic.get(tkey, {}).get("dram_bytes_per_pair", 0) * pairs3 / max(1, n3) or None,
              "launches": n3, "avg_launch_ms": ms3 / max(1, n3), "algorithmic_flops_per_launch": flops3 / max(1, n3),
-             "naive_algorithm_equivalent_tflops": naive3, "total_ms": ms3}
-    # (b) gather kernel: HBM bytes = own + reverse scratch entry (32 B each) per (pair, function) + the rows written
-    msg, ng = prof["gather_3b"]
+             "algorithmic_bytes_per_launch": (pairs3 * 8.0 * (8 + D + 2) + float(nrows) * blk3.nb * 8.0 * args.steps) / max(1, n3),
+             "naive_algorithm_equivalent_tflops": naive3, "total_ms": ms3,
+             "note": "one 'launch' = the 8 unit kernels of a chunk; flops = factorised algorithm (DESIGN.md section 4), "
+                     "FMA = 2; algorithmic bytes = pair records read once + Psi rows written once"}
+    # (b) gather kernel (scratch path only): HBM bytes = reverse scratch entry (24 B) per (pair, function) + the rows written
     bytes_g = pairs3 * blk3.nb * 24.0 + float(nrows) * blk3.nb * 8.0 * args.steps
     achg = bytes_g / (msg * 1e-3) * 1e-9 if msg > 0 else 0.0
     r_gat = {"kernel": "gather3b_kernel (scratch -> E/F/V rows)", "bound": "hbm", "achieved": achg, "peak": hbm_peak,
@@ -376,7 +386,15 @@ def run_ours(args):
               "peak": dmma_peak, "unit": "TFLOP/s", "frac": achd / dmma_peak, "traffic": None, "launches": gram_n,
               "avg_launch_ms": gram_ms / max(1, gram_n), "algorithmic_flops_per_launch": gram_flops / max(1, gram_n),
               "total_ms": gram_ms}
-    cands = sorted([r_mom, r_gat, r_gram], key=lambda r: -r["total_ms"])
+    # (d) re-orthogonalisation update A <- A L^-T (DMMA product with the explicit inverse): M n^2 flops (triangular)
+    trsm_ms, trsm_n = prof["trsm"]
+    trsm_flops = float(M) * ncols * ncols * trsm_n
+    acht = trsm_flops / (trsm_ms * 1e-3) * 1e-12 if trsm_ms > 0 else 0.0
+    r_trsm = {"kernel": "trinv_kernel + applyw_kernel (A <- A L^-T, DMMA m8n8k4 f64, in place)", "bound": "tensor",
+              "achieved": acht, "peak": dmma_peak, "unit": "TFLOP/s", "frac": acht / dmma_peak, "traffic": None,
+              "launches": trsm_n, "avg_launch_ms": trsm_ms / max(1, trsm_n),
+              "algorithmic_flops_per_launch": trsm_flops / max(1, trsm_n), "total_ms": trsm_ms}
+    cands = sorted([r for r in (r_mom, r_gat, r_gram, r_trsm) if r["launches"] > 0], key=lambda r: -r["total_ms"])
     roofline = cands[0]
     roofline["peak_source"] = ("HBM: MEASURED_PEAKS.json (driver); FP64 FMA 33.9 and DMMA 37.1 TFLOP/s: own microbenchmark "
                                "tools/peaks.cu (MEASURED_PEAKS.json has no FP64 entry), cuBLAS DGEMM 8192^3 = 35.5")
