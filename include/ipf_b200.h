@@ -193,6 +193,12 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done);
 /* c [n]; R_out [n*n] column-major upper factor of the scaled system, or NULL;
  * ssr, ssy: LOCAL sums |y - A c'|^2 and |y|^2 (sum across ranks before the ratio) */
 int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, double* ssr, double* ssy);
+/* After the factorisation is complete (done = 1): qty[n] = Q^T y for the factor R that ipf_solve_finish returns
+ * (A0 = Q R), and the residual sums of ANY coefficient vector c[n] given in the scaled basis (before D_inv):
+ * ssr = |y - A0 c|^2, ssy = |y|^2 (local rows).  They carry the `:svd` and `:rrqr` branches of lsqfit
+ * (src/lsq.jl:482-497), whose small dense work (SVD / pivoted QR of the n x n factor) stays on the host. */
+int32_t ipf_solve_qty(ipf_ctx* ctx, ipf_solver* S, double* qty);
+int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double* ssr, double* ssy);
 int32_t ipf_solve_info(const ipf_solver* S, int32_t* npasses, double* defect, double* shift,
                        double* gram_ms, double* trsm_ms);
 int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S);

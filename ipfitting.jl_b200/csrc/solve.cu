@@ -454,6 +454,15 @@ trsm_rows_kernel(double* __restrict__ A, int64_t ld, int64_t M, const double* __
     }
 }
 
+// y = R x, R upper triangular (column-major n x n)
+__global__ void triu_matvec_kernel(const double* __restrict__ R, int n, const double* __restrict__ x, double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (int j = i; j < n; ++j) s = fma(R[(size_t)j * n + i], x[j], s);
+    y[i] = s;
+}
+
 // ---- residual r = y - A c (current A, coefficients in the current basis) -----
 __global__ void residual_kernel(const double* __restrict__ A, int64_t ld, int64_t M, int n,
                                 const double* __restrict__ c, double* __restrict__ partial) {
@@ -933,6 +942,43 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     IPF_CUDA(ctx, cudaMemcpyAsync(c, cf, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
     if (R_out) IPF_CUDA(ctx, cudaMemcpyAsync(R_out, S->Rtot, sizeof(double) * nn, cudaMemcpyDeviceToHost, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    IPF_CUDA(ctx, cudaGetLastError());
+    if (ssr) *ssr = h[0];
+    if (ssy) *ssy = h[1];
+    return IPF_OK;
+}
+
+// Q^T y of the factorisation A0 = Q R (R = the factor ipf_solve_finish returns): the starting point of the
+// solvers that work on the n x n factor on the host (:svd, :rrqr, src/lsq.jl:482-497).
+int32_t ipf_solve_qty(ipf_ctx* ctx, ipf_solver* S, double* qty) {
+    if (!ctx || !S || !qty) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_qty: bad arguments");
+    if (S->state != 2) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_qty: factorisation not complete");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    IPF_CUDA(ctx, cudaMemcpyAsync(qty, S->vec, sizeof(double) * S->n, cudaMemcpyDeviceToHost, ctx->stream));
+    IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return IPF_OK;
+}
+
+// Local residual sums ssr = |y - A0 c|^2, ssy = |y|^2 of the weighted, column-scaled system for ANY coefficient
+// vector c (length n, in the scaled basis, i.e. before the multiplication with D_inv): `rel_rms = norm(Psi*c - Y) /
+// norm(Y)` of the :svd / :rrqr branches.  Evaluated on the current A = A0 Rprev^-1 as y - A (Rprev c).
+int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double* ssr, double* ssy) {
+    if (!ctx || !S || !c) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_residual: bad arguments");
+    if (S->state != 2) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_residual: factorisation not complete");
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = S->n;
+    double* x = S->work + 3 * S->n1;
+    double* cc = S->work;
+    IPF_CUDA(ctx, cudaMemcpyAsync(x, c, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    triu_matvec_kernel<<<(n + 255) / 256, 256, 0, st>>>(S->Rtmp, n, x, cc);
+    const int64_t nb = (S->Mpad + 255) / 256;
+    residual_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, n, cc, S->red + 8);
+    sum_pairs_kernel<<<1, 1024, 0, st>>>(S->red + 8, nb, S->red);
+    ctx->launches += 3;
+    double h[2];
+    IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
     IPF_CUDA(ctx, cudaStreamSynchronize(st));
     IPF_CUDA(ctx, cudaGetLastError());
     if (ssr) *ssr = h[0];

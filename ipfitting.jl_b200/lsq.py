@@ -284,6 +284,20 @@ class _Solver:
             C.byref(ssr), C.byref(ssy)))
         return c, R, ssr.value, ssy.value
 
+    def qty(self) -> np.ndarray:
+        """Q^T y of the factorisation A0 = Q R (after the factorisation is complete)."""
+        q = np.empty(self.n)
+        self.ctx.check(self.ctx.lib.ipf_solve_qty(self.ctx.h, self.h, _capi.ptr(q, C.c_double)))
+        return q
+
+    def residual(self, c):
+        """(ssr, ssy) = (|y - A0 c|^2, |y|^2) over the local rows, c in the scaled basis (before D_inv)."""
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        ssr, ssy = C.c_double(), C.c_double()
+        self.ctx.check(self.ctx.lib.ipf_solve_residual(self.ctx.h, self.h, _capi.ptr(c, C.c_double),
+                                                       C.byref(ssr), C.byref(ssy)))
+        return ssr.value, ssy.value
+
     def info(self) -> dict:
         npass, defect, shift, gms, tms = C.c_int32(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
         self.ctx.lib.ipf_solve_info(self.h, C.byref(npass), C.byref(defect), C.byref(shift), C.byref(gms), C.byref(tms))
@@ -302,10 +316,11 @@ class _Solver:
             pass
 
 
-def run_staged(S, comm=None, device: int = 0, want_R: bool = True):
+def run_staged(S, comm=None, device: int = 0, want_R: bool = True, factor_solver=None, Dinv=None):
     """The staged solve protocol (include/ipf_b200.h): gram -> [all-reduce] -> factor, repeated
     until done; then finish.  `S` is a `_Solver` (device) -- or any object with the same four
-    methods (the gloo tests drive a numpy stand-in through exactly this function)."""
+    methods (the gloo tests drive a numpy stand-in through exactly this function).
+    `factor_solver(R, qty) -> (c_scaled, info)` replaces the triangular solve by a host-side solve on the factor."""
     multi = comm is not None and comm.world_size > 1
     while True:
         g, n1 = S.gram()
@@ -313,22 +328,30 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True):
             comm.allreduce_gram(g, n1 * n1, device)
         if S.factor():
             break
-    c, R, ssr, ssy = S.finish(want_R)
+    c, R, ssr, ssy = S.finish(want_R or factor_solver is not None)
+    extra = {}
+    if factor_solver is not None:
+        # :svd / :rrqr: the solve happens on the n x n factor (host), the residual on the device
+        cs, extra = factor_solver(R, S.qty())
+        ssr, ssy = S.residual(cs)
+        c = cs if Dinv is None else cs * Dinv
     if multi:
         ssr, ssy = comm.allreduce_scalars([ssr, ssy])
     info = S.info()
+    info.update(extra)
     info["rel_rms"] = math.sqrt(ssr) / math.sqrt(ssy) if ssy > 0 else float("nan")
     return c, R, info
 
 
-def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None, precon=None):
+def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None, precon=None,
+                 factor_solver=None):
     """Weighted LSQ solve of the device-resident system.  `comm`: a
     `parallel.Communicator` (rows are sharded over its ranks) or None.  `precon`: (row0, blocks, solver)."""
     S = _Solver(ctx, Psi_dev, Y, W, Irows, Icols, Dinv)
     try:
         if precon is not None and precon[1]:
             S.apply_precon(*precon)
-        return run_staged(S, comm, ctx.device, want_R)
+        return run_staged(S, comm, ctx.device, want_R, factor_solver, Dinv)
     finally:
         S.close()
 
@@ -351,6 +374,37 @@ def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=Non
         return S.system_to_host()
     finally:
         S.close()
+
+
+def _svd_factor_solver(ndiscard: int):
+    """`:svd` (`src/lsq.jl:482-488`): c = V[:, 1:end-k] * (S[1:end-k] \\ (U'Y)[1:end-k]).  With Psi = Q R the SVD of
+    the n x n factor gives the same S, V and U'Y = U_R' (Q'Y)."""
+    def solve(R, qty):
+        n = R.shape[0]
+        if not 0 <= ndiscard < max(n, 1):
+            raise ValueError("svd_ndiscard out of range")
+        U, S, Vt = np.linalg.svd(np.triu(R))
+        k = n - ndiscard
+        c = Vt[:k].T @ ((U.T @ qty)[:k] / S[:k])
+        return c, {"svd_S": S}
+    return solve
+
+
+def _rrqr_factor_solver(rtol: float):
+    """`:rrqr` (`src/lsq.jl:489-496`, `pqrfact(Psi, rtol=...)` of LowRankApprox.jl): column-pivoted QR truncated
+    where |R_kk| <= rtol |R_11|, basic solution (zeros for the discarded columns).  The pivoted QR of the n x n
+    factor selects the same columns as that of Psi = Q R (equal column norms at every step)."""
+    def solve(R, qty):
+        import scipy.linalg as sla
+        n = R.shape[0]
+        Q2, R2, piv = sla.qr(np.triu(R), pivoting=True)
+        d = np.abs(np.diag(R2))
+        k = int(np.sum(d > rtol * d[0])) if n else 0
+        c = np.zeros(n)
+        if k:
+            c[piv[:k]] = sla.solve_triangular(R2[:k, :k], (Q2.T @ qty)[:k])
+        return c, {"rrqr_rank": k}
+    return solve
 
 
 def _diag_of(P, n) -> Optional[np.ndarray]:
@@ -385,9 +439,18 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
         raise NotImplementedError("regularisers are not part of the CUDA path yet (SURVEY.md §8f N4)")
     weights = _fix_weights(weights)
     name = str(solver.get("solver", "qr")).lstrip(":")
-    if name != "qr":
-        raise ValueError("unknown `solver` in `lsqfit`" if name not in ("svd", "rrqr", "lsqr", "brr", "ard", "xgboost")
-                         else f"solver :{name} is not provided by the CUDA path (only :qr)")
+    factor_solver = None
+    if name == "svd":
+        if "svd_ndiscard" not in solver:
+            raise AssertionError('haskey(solver, "svd_ndiscard")')       # `@assert`, src/lsq.jl:483
+        factor_solver = _svd_factor_solver(int(solver["svd_ndiscard"]))
+    elif name == "rrqr":
+        if "rrqr_tol" not in solver:
+            raise AssertionError('haskey(solver, "rrqr_tol")')           # `@assert`, src/lsq.jl:490
+        factor_solver = _rrqr_factor_solver(float(solver["rrqr_tol"]))
+    elif name != "qr":
+        raise ValueError("unknown `solver` in `lsqfit`" if name not in ("lsqr", "brr", "ard", "xgboost")
+                         else f"solver :{name} is not provided by the CUDA path (:qr, :svd, :rrqr)")
     ctx = db._context()
     Y, W, Icfg = collect_observations(db, weights, Vref)
     Irows, Icols = _select(db, Y, W, Icfg, Ibasis, Itrain)
@@ -396,7 +459,8 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     if "P" in solver:
         del solver["P"]          # `src/lsq.jl:460-462`
     precon = _precon_blocks(db, weights, Irows)
-    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm, precon=precon)
+    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm, precon=precon,
+                              factor_solver=factor_solver)
     kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
     if isinstance(saveqr, dict):
         saveqr["R"] = R

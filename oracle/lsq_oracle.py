@@ -103,6 +103,37 @@ def lsqfit_qr(Psi, configs, weights=None, E0=None, Ibasis=None, Itrain=None, P=N
     return Dinv * c, kappa, rel_rms, R
 
 
+def lsqfit_svd(Psi, configs, svd_ndiscard, weights=None, E0=None, Ibasis=None, Itrain=None, P=None):
+    """The :svd branch (`src/lsq.jl:482-488`): F = svd(Psi);
+    c = F.V[:, 1:end-k] * (Diagonal(F.S[1:end-k]) \\ (F.U' * Y)[1:end-k]); rel_rms = norm(Psi*c - Y) / norm(Y)."""
+    A, Y = get_lsq_system(Psi, configs, weights, E0, Ibasis, Itrain)
+    n = A.shape[1]
+    Dinv = np.ones(n) if P is None else np.where(np.asarray(P) != 0, 1.0 / np.asarray(P, dtype=float), 0.0)
+    A = A * Dinv[None, :]
+    U, S, Vt = np.linalg.svd(A, full_matrices=False)
+    k = n - svd_ndiscard
+    c = Vt[:k].T @ ((U.T @ Y)[:k] / S[:k])
+    rel_rms = np.linalg.norm(A @ c - Y) / np.linalg.norm(Y)
+    return Dinv * c, rel_rms, S
+
+
+def lsqfit_rrqr(Psi, configs, rrqr_tol, weights=None, E0=None, Ibasis=None, Itrain=None, P=None):
+    """The :rrqr branch (`src/lsq.jl:489-496`): qrPsi = pqrfact(Psi, rtol=rrqr_tol); c = qrPsi \\ Y.  pqrfact
+    (LowRankApprox.jl, not vendored) = column-pivoted Householder QR stopped where |R_kk| <= rtol |R_11|; `\\`
+    gives the basic solution on the selected columns.  Returns c, rel_rms, rank."""
+    A, Y = get_lsq_system(Psi, configs, weights, E0, Ibasis, Itrain)
+    n = A.shape[1]
+    Dinv = np.ones(n) if P is None else np.where(np.asarray(P) != 0, 1.0 / np.asarray(P, dtype=float), 0.0)
+    A = A * Dinv[None, :]
+    Q, R, piv = sla.qr(A, mode="economic", pivoting=True)
+    d = np.abs(np.diag(R))
+    k = int(np.sum(d > rrqr_tol * d[0]))
+    c = np.zeros(n)
+    c[piv[:k]] = sla.solve_triangular(R[:k, :k], (Q.T @ Y)[:k])
+    rel_rms = np.linalg.norm(A @ c - Y) / np.linalg.norm(Y)
+    return Dinv * c, rel_rms, k
+
+
 def rmse_table(Psi, configs, cfull, E0=None):
     """_fiterrs with fit values Psi*c + Vref observations; raw observations, err_weighthook."""
     yhat = Psi @ cfull

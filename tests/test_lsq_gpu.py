@@ -173,3 +173,37 @@ def test_bench_basis_fit_matches_householder(ctx):
     assert abs(r_gpu - rel_rms) <= 1e-6 * rel_rms                     # the returned c reproduces the minimum
     assert np.linalg.norm(A @ (info["c"] - c_ref)) <= 2e-3 * np.linalg.norm(y) * rel_rms
     assert abs(np.log10(info["cond_R"]) - np.log10(kappa)) < 0.5
+
+
+@pytest.mark.parametrize("ndiscard", [0, 2])
+def test_lsqfit_svd_matches_reference(fitcase, ndiscard):
+    """`:svd` (`src/lsq.jl:482-488`): SVD of the n x n factor on the host, Q'y and the residual from the device."""
+    db, ref = fitcase
+    w = {"default": {"E": 30.0, "F": 1.0, "V": 0.5}}
+    E0 = -4.0
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=E0, Vref=ipf.OneBody(E0),
+                          solver={"solver": "svd", "svd_ndiscard": ndiscard})
+    c_ref, rel_rms, S = LO.lsqfit_svd(ref, db.configs, ndiscard, w, E0=E0)
+    assert np.linalg.norm(info["c"] - c_ref) <= C_RTOL * np.linalg.norm(c_ref)
+    assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
+    assert np.allclose(info["solve_info"]["svd_S"], S, rtol=1e-9, atol=0)
+    if ndiscard == 0:            # full rank: the same minimiser as :qr
+        c_qr = LO.lsqfit_qr(ref, db.configs, w, E0=E0)[0]
+        assert np.linalg.norm(info["c"] - c_qr) <= 1e-7 * np.linalg.norm(c_qr)
+    with pytest.raises(AssertionError):
+        ipf.lsqfit(db, weights=dict(w), solver={"solver": "svd"})
+
+
+@pytest.mark.parametrize("tol", [1e-14, 3e-3])
+def test_lsqfit_rrqr_matches_reference(fitcase, tol):
+    """`:rrqr` (`src/lsq.jl:489-496`): column-pivoted QR of the n x n factor selects the same columns as that of Psi."""
+    db, ref = fitcase
+    w = {"default": {"E": 30.0, "F": 1.0, "V": 0.5}}
+    P = np.linspace(0.7, 2.0, len(db.basis))
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=0.0, solver={"solver": "rrqr", "rrqr_tol": tol, "P": P.copy()})
+    c_ref, rel_rms, rank = LO.lsqfit_rrqr(ref, db.configs, tol, w, E0=0.0, P=P)
+    assert info["solve_info"]["rrqr_rank"] == rank
+    assert (rank < len(db.basis)) == (tol > 1e-6)
+    assert np.array_equal(info["c"] == 0, c_ref == 0)            # the same columns were discarded
+    assert np.linalg.norm(info["c"] - c_ref) <= C_RTOL * np.linalg.norm(c_ref)
+    assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
