@@ -193,6 +193,11 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done);
 /* c [n]; R_out [n*n] column-major upper factor of the scaled system, or NULL;
  * ssr, ssy: LOCAL sums |y - A c'|^2 and |y|^2 (sum across ranks before the ratio) */
 int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, double* ssr, double* ssy);
+/* Regulariser rows (`_regularise!`, src/lsq.jl:163-181): append nextra rows [P | q] to the weighted system (after
+ * the row weighting, before the first ipf_solve_gram).  P: column-major nextra x n (ldP), columns = the selected
+ * basis functions, unscaled (the solver applies Dinv); q: nextra targets or NULL (zeros).  In a multi-GPU solve
+ * exactly one rank appends them. */
+int32_t ipf_solve_append_rows(ipf_ctx* ctx, ipf_solver* S, int64_t nextra, const double* P, int64_t ldP, const double* q);
 /* After the factorisation is complete (done = 1): qty[n] = Q^T y for the factor R that ipf_solve_finish returns
  * (A0 = Q R), and the residual sums of ANY coefficient vector c[n] given in the scaled basis (before D_inv):
  * ssr = |y - A0 c|^2, ssy = |y|^2 (local rows).  They carry the `:svd` and `:rrqr` branches of lsqfit

@@ -78,6 +78,7 @@ SIGNATURES = {
     "ipf_solve_gram": (C.c_int32, [_vp, _vp, C.POINTER(_vp), _lp]),
     "ipf_solve_factor": (C.c_int32, [_vp, _vp, _ip]),
     "ipf_solve_finish": (C.c_int32, [_vp, _vp, _dp, _dp, _dp, _dp]),
+    "ipf_solve_append_rows": (C.c_int32, [_vp, _vp, C.c_int64, _dp, C.c_int64, _dp]),
     "ipf_solve_qty": (C.c_int32, [_vp, _vp, _dp]),
     "ipf_solve_residual": (C.c_int32, [_vp, _vp, _dp, _dp, _dp]),
     "ipf_solve_info": (C.c_int32, [_vp, _ip, _dp, _dp, _dp, _dp]),

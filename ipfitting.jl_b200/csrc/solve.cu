@@ -949,6 +949,66 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     return IPF_OK;
 }
 
+// A[(c) * ld + M + r] = P[c * ldP + r] * dinv[c]  (c < n),  A[n * ld + M + r] = q[r]
+__global__ void append_rows_kernel(double* __restrict__ A, int64_t ld, int64_t M, int n, int64_t nextra,
+                                   const double* __restrict__ P, int64_t ldP, const double* __restrict__ q,
+                                   const double* __restrict__ dinv) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int c = blockIdx.y;
+    if (r >= nextra) return;
+    A[(int64_t)c * ld + M + r] = c < n ? P[(int64_t)c * ldP + r] * (dinv ? dinv[c] : 1.0) : (q ? q[r] : 0.0);
+}
+
+// Regulariser rows (`_regularise!`, src/lsq.jl:163-181: vcat(Psi, Psi_reg), vcat(Y, Y_reg) AFTER the weighting):
+// appends nextra rows [P | q] to the weighted system of a solver that has not been factorised yet.  P is column-major
+// nextra x n (leading dimension ldP) in the unscaled basis of the selected columns; q may be NULL (zeros).
+int32_t ipf_solve_append_rows(ipf_ctx* ctx, ipf_solver* S, int64_t nextra, const double* P, int64_t ldP, const double* q) {
+    if (!ctx || !S || nextra < 0 || (nextra && (!P || ldP < nextra)))
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_append_rows: bad arguments");
+    if (S->state != 0 || S->pass != 0) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_append_rows: the factorisation has started");
+    if (nextra == 0) return IPF_OK;
+    IPF_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int n = S->n;
+    for (int64_t k = 0; k < nextra; ++k) {
+        if (q && std::isnan(q[k])) return ipf_set_error(ctx, IPF_ENAN_Y, "NaN detected in observations vector");
+        for (int c = 0; c < n; ++c)
+            if (std::isnan(P[(size_t)c * ldP + k])) return ipf_set_error(ctx, IPF_ENAN_PSI, "discovered NaNs in LSQ system matrix");
+    }
+    const int64_t newM = S->M + nextra;
+    const int64_t newMpad = ((newM + 15) / 16) * 16;
+    const size_t abytes = sizeof(double) * (size_t)newMpad * S->ncp;
+    const size_t rbytes = sizeof(double) * (2 * (size_t)(newMpad / 256 + 2) + 8);
+    double *newA = nullptr, *newRed = nullptr;
+    if (S->pooled) {
+        IPF_CHECK(ipf_arena_alloc_in(ctx, ctx->solve_arena, abytes, (void**)&newA));
+        IPF_CHECK(ipf_arena_alloc_in(ctx, ctx->solve_arena, rbytes, (void**)&newRed));
+    } else {
+        if (cudaMalloc((void**)&newA, abytes) != cudaSuccess || cudaMalloc((void**)&newRed, rbytes) != cudaSuccess) {
+            if (newA) cudaFree(newA);
+            return ipf_set_error(ctx, IPF_ENOMEM, "ipf_solve_append_rows: %zu bytes", abytes);
+        }
+    }
+    IPF_CUDA(ctx, cudaMemsetAsync(newA, 0, abytes, st));
+    if (S->M > 0)
+        IPF_CUDA(ctx, cudaMemcpy2DAsync(newA, sizeof(double) * newMpad, S->A, sizeof(double) * S->Mpad, sizeof(double) * S->M,
+                                        S->n1, cudaMemcpyDeviceToDevice, st));
+    // staging copies from the assembly arena (idle during a solve)
+    ABuf<double> dP, dq;
+    IPF_CHECK(dP.alloc(ctx, (size_t)ldP * n));
+    IPF_CHECK(dq.alloc(ctx, nextra));
+    IPF_CUDA(ctx, cudaMemcpyAsync(dP.p, P, sizeof(double) * (size_t)ldP * n, cudaMemcpyHostToDevice, st));
+    if (q) IPF_CUDA(ctx, cudaMemcpyAsync(dq.p, q, sizeof(double) * nextra, cudaMemcpyHostToDevice, st));
+    append_rows_kernel<<<dim3((unsigned)((nextra + 255) / 256), (unsigned)S->n1), 256, 0, st>>>(
+        newA, newMpad, S->M, n, nextra, dP.p, ldP, q ? dq.p : nullptr, S->dinv);
+    ctx->launches++;
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));
+    IPF_CUDA(ctx, cudaGetLastError());
+    if (!S->pooled) { cudaFree(S->A); cudaFree(S->red); }
+    S->A = newA; S->red = newRed; S->M = newM; S->Mpad = newMpad;
+    return IPF_OK;
+}
+
 // Q^T y of the factorisation A0 = Q R (R = the factor ipf_solve_finish returns): the starting point of the
 // solvers that work on the n x n factor on the host (:svd, :rrqr, src/lsq.jl:482-497).
 int32_t ipf_solve_qty(ipf_ctx* ctx, ipf_solver* S, double* qty) {

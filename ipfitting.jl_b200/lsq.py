@@ -258,6 +258,21 @@ class _Solver:
             self.ctx.h, self.h, len(blocks), _capi.ptr(r0, C.c_int64), _capi.ptr(m, C.c_int32), _capi.ptr(off, C.c_int64),
             _capi.ptr(P, C.c_double), len(P), 0 if solver == "chol" else 1))
 
+    def append_rows(self, P, q=None):
+        """Regulariser rows [P | q] below the weighted system (`_regularise!`, `src/lsq.jl:163-181`)."""
+        P = np.asfortranarray(P, dtype=np.float64)
+        if P.ndim != 2 or P.shape[1] != self.n:
+            raise ValueError("regulariser has the wrong number of columns")
+        if P.shape[0] == 0:
+            return
+        qq = None if q is None else np.ascontiguousarray(q, dtype=np.float64)
+        if qq is not None and qq.shape != (P.shape[0],):
+            raise ValueError("regulariser target has the wrong length")
+        self.ctx.check(self.ctx.lib.ipf_solve_append_rows(
+            self.ctx.h, self.h, P.shape[0], _capi.ptr(P, C.c_double), P.shape[0],
+            None if qq is None else _capi.ptr(qq, C.c_double)))
+        self.M += P.shape[0]
+
     def system_to_host(self):
         A = np.empty((self.M, self.n), order="F")
         y = np.empty(self.M)
@@ -344,13 +359,15 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True, factor_solver
 
 
 def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None, precon=None,
-                 factor_solver=None):
+                 factor_solver=None, reg=None):
     """Weighted LSQ solve of the device-resident system.  `comm`: a
     `parallel.Communicator` (rows are sharded over its ranks) or None.  `precon`: (row0, blocks, solver)."""
     S = _Solver(ctx, Psi_dev, Y, W, Irows, Icols, Dinv)
     try:
         if precon is not None and precon[1]:
             S.apply_precon(*precon)
+        if reg is not None and reg[0] is not None and (comm is None or comm.rank == 0):
+            S.append_rows(*reg)          # one rank carries the regulariser rows
         return run_staged(S, comm, ctx.device, want_R, factor_solver, Dinv)
     finally:
         S.close()
@@ -360,8 +377,6 @@ def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=Non
                    weights=None, regularisers=()):
     """`get_lsq_system(db; ...) -> Psi_W, Y_W` on the host (`src/lsq.jl:245-311`); default
     `Vref = OneBody(E0)` as there."""
-    if regularisers:
-        raise NotImplementedError("regularisers are not part of the CUDA path yet (SURVEY.md §8f N4)")
     if isinstance(Vref, str) and Vref == "default":
         Vref = OneBody(E0 if E0 is not None else 0.0)
     weights = _fix_weights(weights)
@@ -371,6 +386,8 @@ def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=Non
     try:
         row0, blocks, psolver = _precon_blocks(db, weights, Irows)
         S.apply_precon(row0, blocks, psolver)
+        if regularisers:
+            S.append_rows(*_regulariser_rows(regularisers, db.basis, Icols))
         return S.system_to_host()
     finally:
         S.close()
@@ -407,6 +424,30 @@ def _rrqr_factor_solver(rtol: float):
     return solve
 
 
+def _regulariser_rows(regularisers, basis, Icols):
+    """`_regularise!` (`src/lsq.jl:163-181`): every regulariser is a matrix P (target 0), a pair (P, q), or an object
+    with `.matrix(basis) -> (P, q)` (the reference's `Matrix(reg, basis)`); all are stacked.  With `Ibasis` the
+    selected columns are taken (the reference leaves that case as a TODO)."""
+    Ps, qs = [], []
+    for reg in regularisers:
+        if hasattr(reg, "matrix") and not isinstance(reg, np.ndarray):
+            P, q = reg.matrix(basis)
+        elif isinstance(reg, (tuple, list)) and len(reg) == 2 and np.ndim(reg[0]) == 2:
+            P, q = reg
+        else:
+            P, q = reg, None
+        P = np.asarray(P, dtype=np.float64)
+        if P.ndim != 2 or P.shape[1] != len(basis):
+            raise ValueError("regulariser matrix must have one column per basis function")
+        q = np.zeros(P.shape[0]) if q is None else np.asarray(q, dtype=np.float64).reshape(-1)
+        if q.shape[0] != P.shape[0]:
+            raise ValueError("regulariser target has the wrong length")
+        Ps.append(P if Icols is None else P[:, Icols]); qs.append(q)
+    if not Ps:
+        return None, None
+    return np.vstack(Ps), np.concatenate(qs)
+
+
 def _diag_of(P, n) -> Optional[np.ndarray]:
     if P is None:
         return None
@@ -435,8 +476,6 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
             if isinstance(cw, dict):
                 for k in cw:
                     cw[k] = 1.0 / cw[k]
-    if regularisers:
-        raise NotImplementedError("regularisers are not part of the CUDA path yet (SURVEY.md §8f N4)")
     weights = _fix_weights(weights)
     name = str(solver.get("solver", "qr")).lstrip(":")
     factor_solver = None
@@ -459,8 +498,9 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     if "P" in solver:
         del solver["P"]          # `src/lsq.jl:460-462`
     precon = _precon_blocks(db, weights, Irows)
+    reg = _regulariser_rows(regularisers, db.basis, Icols) if regularisers else None
     c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm, precon=precon,
-                              factor_solver=factor_solver)
+                              factor_solver=factor_solver, reg=reg)
     kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
     if isinstance(saveqr, dict):
         saveqr["R"] = R

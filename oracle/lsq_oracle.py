@@ -75,7 +75,7 @@ def fix_weights(weights):
     return weights
 
 
-def get_lsq_system(Psi, configs, weights=None, E0=0.0, Ibasis=None, Itrain=None):
+def get_lsq_system(Psi, configs, weights=None, E0=0.0, Ibasis=None, Itrain=None, regularisers=()):
     weights = fix_weights(weights)
     Y, W, Icfg = collect_observations(configs, Psi.shape[0], weights, E0)
     assert not np.isnan(Y).any() and not np.isnan(W).any()
@@ -87,12 +87,20 @@ def get_lsq_system(Psi, configs, weights=None, E0=0.0, Ibasis=None, Itrain=None)
     A = np.array(A, order="F", copy=True)
     Y = Y[Irows]; W = W[Irows]
     assert not np.isnan(A).any()
-    return W[:, None] * A, W * Y
+    A, Y = W[:, None] * A, W * Y
+    # `_regularise!` (`src/lsq.jl:163-181`): vcat below the weighted system; a bare matrix has target zero
+    for reg in regularisers:
+        P, q = reg if isinstance(reg, tuple) else (reg, None)
+        P = np.asarray(P, dtype=float)
+        if Ibasis is not None:
+            P = P[:, np.asarray(list(Ibasis))]
+        A = np.vstack([A, P]); Y = np.concatenate([Y, np.zeros(P.shape[0]) if q is None else np.asarray(q, dtype=float)])
+    return A, Y
 
 
-def lsqfit_qr(Psi, configs, weights=None, E0=None, Ibasis=None, Itrain=None, P=None):
+def lsqfit_qr(Psi, configs, weights=None, E0=None, Ibasis=None, Itrain=None, P=None, regularisers=()):
     """Returns c, cond(R), rel_rms, R exactly as the :qr branch computes them."""
-    A, Y = get_lsq_system(Psi, configs, weights, E0, Ibasis, Itrain)
+    A, Y = get_lsq_system(Psi, configs, weights, E0, Ibasis, Itrain, regularisers)
     n = A.shape[1]
     Dinv = np.ones(n) if P is None else np.where(np.asarray(P) != 0, 1.0 / np.asarray(P, dtype=float), 0.0)
     A = A * Dinv[None, :]

@@ -207,3 +207,23 @@ def test_lsqfit_rrqr_matches_reference(fitcase, tol):
     assert np.array_equal(info["c"] == 0, c_ref == 0)            # the same columns were discarded
     assert np.linalg.norm(info["c"] - c_ref) <= C_RTOL * np.linalg.norm(c_ref)
     assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
+
+
+def test_regularisers_append_rows(fitcase):
+    """`_regularise!` (`src/lsq.jl:163-181`): matrices (target 0) and (P, q) pairs are stacked below the weighted
+    system; the solve sees them as ordinary rows (also after the column scaling `solver["P"]`)."""
+    db, ref = fitcase
+    n = len(db.basis)
+    rng = np.random.default_rng(5)
+    w = {"default": {"E": 30.0, "F": 1.0, "V": 0.5}}
+    regs = [0.3 * np.eye(n), (rng.normal(size=(3, n)), rng.normal(size=3))]
+    A, Y = ipf.get_lsq_system(db, Vref=ipf.OneBody(0.0), weights=dict(w), regularisers=regs)
+    A2, Y2 = LO.get_lsq_system(ref, db.configs, weights=w, E0=0.0, regularisers=regs)
+    assert A.shape == A2.shape and np.array_equal(A[-(n + 3):], A2[-(n + 3):]) and np.array_equal(Y[-(n + 3):], Y2[-(n + 3):])
+    P = np.linspace(0.7, 2.0, n)
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=0.0, regularisers=regs, solver={"solver": "qr", "P": P.copy()})
+    c_ref, kappa, rel_rms, _ = LO.lsqfit_qr(ref, db.configs, w, E0=0.0, P=P, regularisers=regs)
+    assert np.linalg.norm(info["c"] - c_ref) <= C_RTOL * np.linalg.norm(c_ref)
+    assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
+    c_plain = LO.lsqfit_qr(ref, db.configs, w, E0=0.0, P=P)[0]
+    assert np.linalg.norm(c_ref - c_plain) > 1e-3 * np.linalg.norm(c_plain)      # the regularisers do act
