@@ -11,5 +11,6 @@ from .potentials import OneBody, NBodyIP, SumIP
 from .lsq_db import LsqDB, matrows, filter_basis, filter_configs, dbpath
 from .lsq import lsqfit, get_lsq_system, collect_observations
 from .lsqerrors import add_fits, rmse, mae
-from . import synth, parallel
+from . import synth, parallel, data
+from .data import read_xyz, write_xyz, load_data
 from .preconditioners import AdjacancyPrecon

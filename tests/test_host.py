@@ -153,3 +153,24 @@ def test_lpt_sharding():
     assert max(loads) == 512 and min(loads) >= 256
     assert parallel.shard_configs(costs, 1) == [list(range(len(costs)))]
     assert parallel.shard_configs([], 2) == [[], []]
+
+
+def test_read_xyz_round_trip(tmp_path):
+    """`read_xyz` (`src/data.jl:129-243`): keys are matched case-insensitively, `config_type` drives include / exclude,
+    missing observations stay missing; an extended-xyz round trip through `write_xyz` is exact."""
+    from ipfitting_jl_b200 import data
+    cfgs = (synth.rattled_configs("Si", 1, 3, seed=3, calc=synth.StillingerWeber(), configtype="bulk")
+            + synth.rattled_configs("Si", 1, 2, seed=4, calc=synth.StillingerWeber(), configtype="liq", virial=False))
+    fn = str(tmp_path / "train.xyz")
+    data.write_xyz(fn, cfgs, energy_key="DFT_Energy")
+    back = data.read_xyz(fn, verbose=False)                      # default key "dft_energy" matches "DFT_Energy"
+    assert len(back) == 5 and all(a == b for a, b in zip(cfgs, back))
+    assert list(back[0].D) == ["E", "F", "V"] and list(back[3].D) == ["E", "F"]
+    assert [d.configtype for d in data.read_xyz(fn, verbose=False, exclude=["liq"])] == ["bulk"] * 3
+    assert [d.configtype for d in data.read_xyz(fn, verbose=False, include=["liq"])] == ["liq"] * 2
+    assert len(data.read_xyz(fn, verbose=False, index="1:4")) == 3
+    assert "E" not in data.read_xyz(fn, verbose=False, energy_key="energy")[0].D
+    assert "E" in data.read_xyz(fn, verbose=False, energy_key="energy", auto=True)[0].D     # closest key
+    assert len(data.load_data(fn, verbose=False)) == 5
+    with pytest.raises(ValueError):
+        data.load_data(str(tmp_path / "train.jld2"))
