@@ -157,7 +157,7 @@ struct SRecStride { static constexpr int value = RecStride<D>::value + ((RecStri
 // dynamic shared memory of one CTA
 template <int D, int NF>
 __host__ __device__ constexpr size_t cfg_smem_bytes(int ga, int maxrec, int ngmax) {
-    return sizeof(double) * ((size_t)maxrec * SRecStride<D>::value + (size_t)(C_T + 1) * C_SLD + (size_t)ga * NF * 3 +
+    return sizeof(double) * ((size_t)maxrec * SRecStride<D>::value + (size_t)(C_T + 1) * C_SLD + (((size_t)ga * NF * 3 + 1) & ~(size_t)1) +
                              2 * (size_t)C_T * 4) +
            2 * (size_t)pb_bytes(ngmax) + sizeof(uint16_t) * (2 * (size_t)ga + 8) + 16;
 }
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A) {
     {
         double* q = sm + (size_t)A.maxrec * SRS;
         M.stage = q; q += (size_t)(C_T + 1) * C_SLD;
-        M.F = q; q += (size_t)A.ga * NF * 3;
+        M.F = q; q += ((size_t)A.ga * NF * 3 + 1) & ~(size_t)1;      // even: everything behind stays 16-byte aligned
         B0.R = q; q += 2 * (size_t)C_T * 4;
         B0.pb = reinterpret_cast<unsigned char*>(q);
         B0.ngmax = A.ngmax;

@@ -54,24 +54,26 @@ __device__ __forceinline__ void load_tile(double* __restrict__ dst, const double
     }
 }
 
-__global__ void __launch_bounds__(GRAM_THREADS, 1)
-gram_kernel(const double* __restrict__ A, int64_t ld, int64_t Mpad, int nt, int nchunk, int64_t chunk_rows,
-            const int2* __restrict__ tiles, double* __restrict__ part) {
-    extern __shared__ __align__(128) double smem[];
+// One tile of the Gram matrix for one chunk of rows.  The 8 warps are laid out 2 x 4 over a (16 NA) x (32 NB) sub-tile
+// (NA = 8, NB = 4: the full 128 x 128 tile); the last block row / column of G only needs the sub-tile that covers
+// n1 - 128 (nt - 1) columns, which saves the MMAs on the zero padding (n1 = 217: 23 % of all MMAs).
+template <int NA, int NB>
+__device__ __forceinline__ void gram_tile(const double* __restrict__ A, int64_t ld, int64_t Mpad, int nchunk,
+                                          int64_t chunk_rows, int ti, int tj, int tile, double* __restrict__ part,
+                                          double* smem) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, chunk = blockIdx.y;
-    const int ti = tiles[tile].x, tj = tiles[tile].y;
+    const int chunk = blockIdx.y;
     const int64_t kbeg = (int64_t)chunk * chunk_rows;
     const int64_t kend = min(Mpad, kbeg + chunk_rows);
     const int nk = kend > kbeg ? (int)((kend - kbeg) / BK) : 0;
 
-    const int wr = warp >> 2, wc = warp & 3;     // warp tile: rows 64*wr.., cols 32*wc..
+    const int wr = warp >> 2, wc = warp & 3;     // warp tile: rows 8 NA wr.., cols 8 NB wc..
     const int fi = lane >> 2, ft = lane & 3;
-    double acc[8][4][2];
+    double acc[NA][NB][2];
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
+        for (int b = 0; b < NB; ++b) { acc[a][b][0] = 0.0; acc[a][b][1] = 0.0; }
 
     // prologue
 #pragma unroll
@@ -95,39 +97,53 @@ gram_kernel(const double* __restrict__ A, int64_t ld, int64_t Mpad, int nt, int 
             }
             cp_async_commit();
         }
-        const double* sA = smem + (k % STAGES) * STAGE_DOUBLES + (wr * 64) * BK;
-        const double* sB = smem + (k % STAGES) * STAGE_DOUBLES + TILE_DOUBLES + (wc * 32) * BK;
+        const double* sA = smem + (k % STAGES) * STAGE_DOUBLES + (wr * 8 * NA) * BK;
+        const double* sB = smem + (k % STAGES) * STAGE_DOUBLES + TILE_DOUBLES + (wc * 8 * NB) * BK;
 #pragma unroll
         for (int s = 0; s < 4; ++s) {
             // logical k = 4s + ft -> 32-byte group s, slot ft; physical group s ^ (row & 3)
             const int off = ((s ^ (fi & 3)) << 2) + ft;
-            double af[8], bf[4];
+            double af[NA], bf[NB];
 #pragma unroll
-            for (int a = 0; a < 8; ++a) af[a] = sA[(a * 8 + fi) * BK + off];
+            for (int a = 0; a < NA; ++a) af[a] = sA[(a * 8 + fi) * BK + off];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) bf[b] = sB[(b * 8 + fi) * BK + off];
+            for (int b = 0; b < NB; ++b) bf[b] = sB[(b * 8 + fi) * BK + off];
 #pragma unroll
-            for (int a = 0; a < 8; ++a)
+            for (int a = 0; a < NA; ++a)
 #pragma unroll
-                for (int b = 0; b < 4; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+                for (int b = 0; b < NB; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
         }
     }
     cp_async_wait<0>();
     // partial tile: part[chunk][tile][i][j], i = row in tile (column of A in block ti)
     double* P = part + ((size_t)chunk * gridDim.x + tile) * (BT * BT);
 #pragma unroll
-    for (int a = 0; a < 8; ++a)
+    for (int a = 0; a < NA; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-            const int i = wr * 64 + a * 8 + fi;
-            const int j = wc * 32 + b * 8 + ft * 2;
+        for (int b = 0; b < NB; ++b) {
+            const int i = wr * 8 * NA + a * 8 + fi;
+            const int j = wc * 8 * NB + b * 8 + ft * 2;
             *reinterpret_cast<double2*>(P + i * BT + j) = make_double2(acc[a][b][0], acc[a][b][1]);
         }
 }
 
+// tiles[t] = (block row ti, block column tj, NA, NB)
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_kernel(const double* __restrict__ A, int64_t ld, int64_t Mpad, int nt, int nchunk, int64_t chunk_rows,
+            const int4* __restrict__ tiles, double* __restrict__ part) {
+    extern __shared__ __align__(128) double smem[];
+    const int tile = blockIdx.x;
+    const int4 T = tiles[tile];
+#define IPF_GRAM_CASE(NA_, NB_)                                                                             \
+    if (T.z == NA_ && T.w == NB_) { gram_tile<NA_, NB_>(A, ld, Mpad, nchunk, chunk_rows, T.x, T.y, tile, part, smem); return; }
+    IPF_GRAM_CASE(8, 4) IPF_GRAM_CASE(8, 3) IPF_GRAM_CASE(8, 2) IPF_GRAM_CASE(8, 1)
+    IPF_GRAM_CASE(6, 3) IPF_GRAM_CASE(4, 2) IPF_GRAM_CASE(2, 1)
+#undef IPF_GRAM_CASE
+}
+
 // G[i][j] (n1 x n1, ld n1, both triangles) = sum over chunks, fixed order
 __global__ void gram_reduce_kernel(const double* __restrict__ part, int ntiles, int nchunk,
-                                   const int2* __restrict__ tiles, double* __restrict__ G, int n1) {
+                                   const int4* __restrict__ tiles, double* __restrict__ G, int n1) {
     const int tile = blockIdx.x;
     const int ti = tiles[tile].x, tj = tiles[tile].y;
     // blockIdx.y selects a band of BT / gridDim.y rows of the tile
@@ -153,9 +169,12 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
     if (ncp % BT != 0 || ld % BK != 0 || Mpad % BK != 0 || n1 > ncp)
         return ipf_set_error(ctx, IPF_EINVAL, "ipf_gram: bad padding");
     const int nt = (n1 + BT - 1) / BT;
-    std::vector<int2> h_tiles;
+    // last block row / column: only the sub-tile that covers the remaining columns (in steps of 32)
+    const int rem = n1 - BT * (nt - 1);
+    const int q = (rem + 31) / 32;                      // 1..4
+    std::vector<int4> h_tiles;
     for (int i = 0; i < nt; ++i)
-        for (int j = i; j < nt; ++j) h_tiles.push_back(make_int2(i, j));
+        for (int j = i; j < nt; ++j) h_tiles.push_back(make_int4(i, j, i == nt - 1 ? 2 * q : 8, j == nt - 1 ? q : 4));
     const int T = (int)h_tiles.size();
     // split-K: fill whole waves of SMs (one CTA per SM)
     int nchunk = std::max(1, ctx->sm_count / T);
@@ -168,9 +187,9 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
     }
     const int64_t chunk_rows = ((ksteps + nchunk - 1) / nchunk) * BK;
     void *d_tiles = nullptr, *part = nullptr;
-    IPF_CHECK(ipf_scratch(ctx, 6, sizeof(int2) * T, &d_tiles));
+    IPF_CHECK(ipf_scratch(ctx, 6, sizeof(int4) * T, &d_tiles));
     IPF_CHECK(ipf_scratch(ctx, 7, sizeof(double) * (size_t)nchunk * T * BT * BT, &part));
-    IPF_CUDA(ctx, cudaMemcpyAsync(d_tiles, h_tiles.data(), sizeof(int2) * T, cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaMemcpyAsync(d_tiles, h_tiles.data(), sizeof(int4) * T, cudaMemcpyHostToDevice, st));
     static bool attr_set = false;
     if (!attr_set) {
         IPF_CUDA(ctx, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
@@ -185,10 +204,10 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
     {
         ProfScope prof_(ctx, "gram");
         gram_kernel<<<dim3(T, nchunk), GRAM_THREADS, GRAM_SMEM, st>>>(A, ld, Mpad, nt, nchunk, chunk_rows,
-                                                                      (const int2*)d_tiles, (double*)part);
+                                                                      (const int4*)d_tiles, (double*)part);
     }
     if (kernel_ms) IPF_CUDA(ctx, cudaEventRecord(e1, st));
-    gram_reduce_kernel<<<dim3(T, 32), 256, 0, st>>>((const double*)part, T, nchunk, (const int2*)d_tiles, G, n1);
+    gram_reduce_kernel<<<dim3(T, 32), 256, 0, st>>>((const double*)part, T, nchunk, (const int4*)d_tiles, G, n1);
     ctx->launches += 2;
     IPF_CUDA(ctx, cudaGetLastError());
     IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_tiles must outlive the copy

@@ -166,3 +166,20 @@ def test_equal_sized_chunks_do_not_share_pair_records(ctx):
     assert np.array_equal(big[1023 * 199:1024 * 199], ref[:199])
     assert np.array_equal(big[1024 * 199:1025 * 199], ref[199:])
     assert np.array_equal(big[2047 * 199:], ref[199:])
+
+
+def test_3b_odd_sized_configurations_only(ctx):
+    """A chunk whose largest configuration has an odd atom count (shared-memory carve-up of the resident kernel) and
+    a cell that is periodic along one axis only."""
+    configs = synth.rattled_configs("Si", 2, 2, seed=71, calc=synth.StillingerWeber(), vacancies=3)
+    for d in configs:
+        while len(d.at) % 2 == 0:                      # force odd sizes
+            keep = np.arange(len(d.at) - 1)
+            d.at = ipf.Atoms(d.at.X[keep], d.at.cell, d.at.pbc, d.at.Z[keep])
+            d.D["F"] = d.D["F"][:3 * len(keep)]
+    iso = synth.rattled_configs("Si", 1, 1, seed=72, calc=synth.StillingerWeber())[0]
+    iso.at = ipf.Atoms(iso.at.X[:7] + 50.0, iso.at.cell * 40.0, (False, True, False), iso.at.Z[:7])
+    iso.D["F"] = iso.D["F"][:21]
+    B = ipf.nbpolys(3, si_desc(2.0), 6)
+    assert all(len(d.at) % 2 == 1 for d in configs + [iso])
+    _check(B, configs + [iso], ctx)
