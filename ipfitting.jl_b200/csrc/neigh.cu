@@ -109,7 +109,10 @@ __device__ __forceinline__ double bond(const double* __restrict__ Xi, const doub
     return __dadd_rn(__dadd_rn(__dmul_rn(R[0], R[0]), __dmul_rn(R[1], R[1])), __dmul_rn(R[2], R[2]));
 }
 
-// thread per centre atom.  FILL = false: count; true: write (key, S, R) in discovery order.
+// NL_SUB threads per centre atom (they split the (x, y) columns of neighbouring cells: four times the threads, the
+// kernel is latency bound).  FILL = false: count per (atom, sub-thread); true: write (key, S, R) at the sub-thread's
+// offset, in discovery order (nl_sort_kernel puts every list into its canonical order afterwards).
+constexpr int NL_SUB = 4;
 template <bool FILL>
 __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site_cfg,
                                 const int64_t* __restrict__ atom_off, const double* __restrict__ pos,
@@ -119,7 +122,9 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
                                 const int32_t* __restrict__ atom_wrap, int64_t* __restrict__ counts,
                                 const int64_t* __restrict__ site_off, unsigned long long* __restrict__ keys,
                                 double* __restrict__ Rtmp, unsigned long long* __restrict__ maxn) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gt = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t s = gt / NL_SUB;
+    const int sub = (int)(gt - s * NL_SUB);
     if (s >= nsites) return;
     const int c = site_cfg[s];
     const int64_t a0 = atom_off[c];
@@ -134,10 +139,12 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
     const int cx = cid / g.ncell[1];
     const int nix = atom_wrap[3 * s], niy = atom_wrap[3 * s + 1], niz = atom_wrap[3 * s + 2];
     int64_t n = 0;
-    const int64_t o0 = FILL ? site_off[s] : 0;
-    for (int ox = -g.m[0]; ox <= g.m[0]; ++ox) {
+    const int64_t o0 = FILL ? site_off[NL_SUB * s + sub] : 0;      // site_off = offsets of the (atom, sub-thread) pieces here
+    const int ny = 2 * g.m[1] + 1, nxy = (2 * g.m[0] + 1) * ny;
+    for (int oxy = sub; oxy < nxy; oxy += NL_SUB) {
+        const int ox = oxy / ny - g.m[0], oy = oxy % ny - g.m[1];
         const int tx = cx + ox, sx = floordiv(tx, g.ncell[0]), ccx = tx - sx * g.ncell[0];
-        for (int oy = -g.m[1]; oy <= g.m[1]; ++oy) {
+        {
             const int ty = cy + oy, sy = floordiv(ty, g.ncell[1]), ccy = ty - sy * g.ncell[1];
             for (int oz = -g.m[2]; oz <= g.m[2]; ++oz) {
                 const int tz = cz + oz, sz = floordiv(tz, g.ncell[2]), ccz = tz - sz * g.ncell[2];
@@ -164,7 +171,16 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
             }
         }
     }
-    if (!FILL) { counts[s] = n; atomicMax(maxn, (unsigned long long)n); }
+    if (!FILL) counts[NL_SUB * s + sub] = n;
+}
+
+// site offsets from the offsets of the (atom, sub-thread) pieces; maxn = longest list
+__global__ void nl_site_off_kernel(int64_t nsites, const int64_t* __restrict__ sub_off, int64_t* __restrict__ site_off,
+                                   unsigned long long* __restrict__ maxn) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s > nsites) return;
+    site_off[s] = sub_off[NL_SUB * s];
+    if (s < nsites) atomicMax(maxn, (unsigned long long)(sub_off[NL_SUB * (s + 1)] - sub_off[NL_SUB * s]));
 }
 
 __global__ void cfg_offsets_kernel(int64_t ncfg, const int64_t* __restrict__ atom_off,
@@ -373,32 +389,34 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     ProfScope prof_(ctx, "neighbour_list");
     ABuf<int32_t> cell_start, cell_atoms, atom_cell, atom_wrap;
     ABuf<GridInfo> grid;
-    ABuf<int64_t> counts;
+    ABuf<int64_t> counts, sub_off;
     IPF_CHECK(cell_start.alloc(ctx, (size_t)ncfg * (NCELL_MAX + 1)));
     IPF_CHECK(cell_atoms.alloc(ctx, nsites));
     IPF_CHECK(atom_cell.alloc(ctx, nsites));
     IPF_CHECK(atom_wrap.alloc(ctx, 3 * nsites));
     IPF_CHECK(grid.alloc(ctx, ncfg));
-    IPF_CHECK(counts.alloc(ctx, nsites + 1));
+    IPF_CHECK(counts.alloc(ctx, NL_SUB * nsites + 1));
+    IPF_CHECK(sub_off.alloc(ctx, NL_SUB * nsites + 1));
     const int32_t* site_cfg = ch.site_cfg.p;
     nl_bin_kernel<<<(unsigned)ncfg, 128, 0, st>>>(ch.atom_off.p, ch.pos.p, ch.cell.p, ch.pbc.p, rcut,
                                                   grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p);
     ctx->launches++;
     const double rc2 = rcut * rcut;
-    const unsigned nb_sites = (unsigned)((nsites + 127) / 128);
-    IPF_CUDA(ctx, cudaMemsetAsync(counts.p + nsites, 0, sizeof(int64_t), st));
+    const unsigned nb_sites = (unsigned)((NL_SUB * nsites + 127) / 128);
+    IPF_CUDA(ctx, cudaMemsetAsync(counts.p + NL_SUB * nsites, 0, sizeof(int64_t), st));
     IPF_CUDA(ctx, cudaMemsetAsync(nl.cfg_pair_off.p + ncfg + 1, 0, sizeof(int64_t), st));
     nl_pairs_kernel<false><<<nb_sites, 128, 0, st>>>(nsites, site_cfg, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
                                                      grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
-                                                     counts.p, nullptr, nullptr, nullptr,
-                                                     (unsigned long long*)(nl.cfg_pair_off.p + ncfg + 1));
+                                                     counts.p, nullptr, nullptr, nullptr, nullptr);
     ctx->launches++;
     size_t tmp_bytes = 0;
-    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, counts.p, sub_off.p, (int)(NL_SUB * nsites + 1), st);
     void* tmp = nullptr;
     IPF_CHECK(ipf_arena_alloc(ctx, tmp_bytes, &tmp));
-    IPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts.p, nl.site_off.p, (int)(nsites + 1), st));
-    ctx->launches++;
+    IPF_CUDA(ctx, cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, counts.p, sub_off.p, (int)(NL_SUB * nsites + 1), st));
+    nl_site_off_kernel<<<(unsigned)((nsites + 256) / 256), 256, 0, st>>>(nsites, sub_off.p, nl.site_off.p,
+                                                                        (unsigned long long*)(nl.cfg_pair_off.p + ncfg + 1));
+    ctx->launches += 2;
     // per-config pair offsets (ncfg+1 values) to the host; gives the total too
     cfg_offsets_kernel<<<(unsigned)((ncfg + 256) / 256), 256, 0, st>>>(ncfg, ch.atom_off.p, nl.site_off.p, nl.cfg_pair_off.p);
     ctx->launches++;
@@ -432,7 +450,7 @@ int ipf_build_neighbours(ipf_ctx* ctx, const ChunkDev& ch, double rcut, NeighLis
     IPF_CHECK(Rtmp.alloc(ctx, 3 * npairs));
     nl_pairs_kernel<true><<<nb_sites, 128, 0, st>>>(nsites, site_cfg, ch.atom_off.p, ch.pos.p, ch.cell.p, rc2,
                                                     grid.p, cell_start.p, cell_atoms.p, atom_cell.p, atom_wrap.p,
-                                                    nullptr, nl.site_off.p, keys.p, Rtmp.p, nullptr);
+                                                    nullptr, sub_off.p, keys.p, Rtmp.p, nullptr);
     const unsigned nb_pairs = (unsigned)((npairs + 255) / 256);
     nl_sort_kernel<<<nb_pairs, 256, 0, st>>>(npairs, nsites, nl.site_off.p, site_cfg, ch.atom_off.p, keys.p,
                                              Rtmp.p, nl.pi.p, nl.pj.p, nl.psite.p, nl.pbeg.p, nl.pcnt.p, nl.pS.p, nl.pR.p, keys_sorted.p);
