@@ -407,7 +407,7 @@ def run_ours(args):
         import ipf_oracle as O
         nth = O.num_threads()
         ent, ta, ts = cpu_reference_step(basis, configs[:2], nth)
-        S = int(max(2, min(len(configs), 15.0 / ((ta + ts) / 2))))
+        S = int(max(2, min(len(configs), 60.0 / ((ta + ts) / 2))))      # ~15-20 s of CPU work (threads scale with the task count)
         ent, ta, ts = cpu_reference_step(basis, configs[:S], nth)
         cpu = {"value": ent / (ta + ts), "unit": "entries/s", "cores": nth, "kind": "port",
                "sample": f"first {S} of {len(configs)} configurations: assembly {ta:.2f} s (1 task per (config,okey), E/F/V separately) "
