@@ -23,7 +23,7 @@ from . import _capi, parallel
 from .datatypes import weighthook
 from .lsq_db import LsqDB, matrows
 from .obsiter import observations
-from .potentials import NBodyIP, OneBody, SumIP, vref_observation
+from .potentials import linear_part, NBodyIP, OneBody, SumIP, vref_observation
 from .prototypes import ENERGY, FORCES, VIRIAL
 
 _QR = ("qr", ":qr")
@@ -110,7 +110,11 @@ def collect_observations(db: LsqDB, weights: dict, Vref):
     ignore = weights["ignore"]
     onebody = isinstance(Vref, OneBody)
     lay = _observation_layout(db)
-    simple = (lay["plain"] and lay["contiguous"] and (Vref is None or onebody) and int(lay["len"].sum()) == nrows
+    # a reference potential that is linear in one of OUR bases (a previous fit, possibly + OneBody terms) is evaluated
+    # for all configurations at once: assemble its design matrix on the device, multiply by its coefficients
+    lin, others = (None, []) if (Vref is None or onebody) else linear_part(Vref)
+    batched = lin is not None and all(isinstance(o, OneBody) and not isinstance(o.E0, dict) for o in others)
+    simple = (lay["plain"] and lay["contiguous"] and (Vref is None or onebody or batched) and int(lay["len"].sum()) == nrows
               and not any(("W" in d.info) or ("Vref" in d.info) for d in db.configs))
     if simple:
         Y = (np.concatenate([v for d in db.configs for v in d.D.values()]) if nrows else np.zeros(0)).astype(np.float64, copy=False)
@@ -139,6 +143,18 @@ def collect_observations(db: LsqDB, weights: dict, Vref):
                 else:                           # E0 * natoms, the same product OneBody.energy forms
                     e0 = float(Vref.E0) * lay["nat"][esel]
                 Y[lay["first"][esel]] -= e0        # Y is a fresh array (concatenate above)
+        if batched and nrows:
+            from .lsq_db import LsqDB as _LsqDB
+            dbr = _LsqDB("", lin.basis, db.configs, ctx=getattr(db, "ctx", None))      # same configs => same rows
+            cx = dbr._context()
+            cr = np.ascontiguousarray(lin.c, dtype=np.float64)
+            yref = np.empty(dbr.nrows)
+            cx.check(cx.lib.ipf_predict(cx.h, dbr.Psi_dev.h, _capi.ptr(cr, C.c_double), _capi.ptr(yref, C.c_double)))
+            dbr.delete()
+            esel = lay["key"] == 0
+            for o in others:
+                yref[lay["first"][esel]] += float(o.E0) * lay["nat"][esel]
+            Y -= yref
         W = np.repeat(np.where(live, wobs, 0.0), lay["len"])
         Icfg = np.repeat(np.where(live, lay["cfg"], -1), lay["len"])
         if not live.all():

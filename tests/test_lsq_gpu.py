@@ -227,3 +227,34 @@ def test_regularisers_append_rows(fitcase):
     assert abs(info["rel_rms"] - rel_rms) <= 1e-8 * rel_rms
     c_plain = LO.lsqfit_qr(ref, db.configs, w, E0=0.0, P=P)[0]
     assert np.linalg.norm(c_ref - c_plain) > 1e-3 * np.linalg.norm(c_plain)      # the regularisers do act
+
+
+def test_vref_from_a_previous_fit_is_evaluated_on_the_device(fitcase, ctx):
+    """`Vref` = a fitted potential (`eval_obs(okey, Vref, dat)`, `src/lsq.jl:96-99`): the 2-body fit is subtracted from
+    every observation before the 3-body fit; evaluated as Psi_ref c_ref for all configurations at once."""
+    db, ref = fitcase
+    w = {"default": {"E": 30.0, "F": 1.0, "V": 0.5}}
+    B2 = ipf.nbpolys(2, si_desc(2.0), 4)
+    db2 = LsqDB("", B2, db.configs, ctx=ctx)
+    IP2, info2 = ipf.lsqfit(db2, weights=dict(w), E0=-4.0, Vref=ipf.OneBody(-4.0))       # SumIP(OneBody, NBodyIP)
+    from ipfitting_jl_b200.lsq import collect_observations, _fix_weights
+    Y, W, Icfg = collect_observations(db, _fix_weights(dict(w)), IP2)
+    # by hand: data - (Psi_2 c_2 + E0 N on the energy rows)
+    yref = db2.Psi @ info2["c"]
+    Ydata = np.zeros(db.nrows)
+    for d in db.configs:
+        for okey, v in d.D.items():
+            f, n = d.rows[okey]
+            Ydata[f:f + n] = v
+            if okey == "E":
+                yref[f] += -4.0 * len(d.at)
+    assert np.allclose(Y, Ydata - yref, rtol=1e-12, atol=1e-9 * np.abs(Ydata).max())
+    # and the observation-by-observation path of the reference gives the same numbers
+    db.configs[0].info["W"] = {"E": 30.0, "F": 1.0, "V": 0.5}      # forces the loop
+    try:
+        Yl, Wl, _ = collect_observations(db, _fix_weights(dict(w)), IP2)
+    finally:
+        del db.configs[0].info["W"]
+    assert np.allclose(Yl, Y, rtol=1e-10, atol=1e-9 * np.abs(Ydata).max())
+    IP3, info3 = ipf.lsqfit(db, weights=dict(w), Vref=IP2)
+    assert info3["rel_rms"] < 1.0 and np.isfinite(info3["c"]).all()
