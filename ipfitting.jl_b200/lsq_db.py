@@ -72,9 +72,8 @@ def _alloc_rows(configs: Sequence[Dat], layout: dict = None) -> int:
     return nrows
 
 
-def flatten_configs(configs: Sequence[Dat], layout: dict = None):
-    """The flat arrays `ipf_assemble` takes.  `layout` (from `_alloc_rows` on the same list) gives the
-    1-based row blocks without another pass over the configurations."""
+def _flatten_atoms(configs: Sequence[Dat]):
+    """Atom data of a configuration list as the flat arrays `ipf_assemble` takes: (atom_off, pos, cell, pbc, Z)."""
     ncfg = len(configs)
     ats = [d.at for d in configs]
     nat = np.array([a.X.shape[0] for a in ats], dtype=np.int64)
@@ -88,22 +87,40 @@ def flatten_configs(configs: Sequence[Dat], layout: dict = None):
     else:
         pos = np.zeros((0, 3)); cell = np.zeros((0, 3, 3)); pbc = np.zeros((0, 3), dtype=np.uint8)
         Z = np.zeros(0, dtype=np.int32)
+    return off, pos, cell, pbc, Z
+
+
+def _rows_from_layout(layout: dict, ncfg: int):
+    """1-based first rows (0 = absent) per observation type from the arrays `_alloc_rows` recorded, with the length
+    check of every E / F / V block; None when the layout does not describe this list."""
+    if not (layout and layout.get("nconfigs") == ncfg and "cfg" in layout):
+        return None
+    lc, lk, lf, ll = layout["cfg"], layout["key"], layout["first"], layout["len"]
+    expect = np.where(lk == 0, 1, np.where(lk == 1, 3 * layout["nat"].astype(np.int64), 6))
+    bad = np.nonzero(ll != expect)[0]
+    if bad.size:
+        b = int(bad[0])
+        k = (ENERGY, FORCES, VIRIAL)[int(lk[b])]
+        raise ValueError(f"observation {k} of config {int(lc[b])} has length {int(ll[b])}, "
+                         f"expected {int(expect[b])}")
     rows = {}
-    if layout and layout.get("nconfigs") == ncfg and "cfg" in layout:
-        lc, lk, lf, ll = layout["cfg"], layout["key"], layout["first"], layout["len"]
-        expect = np.where(lk == 0, 1, np.where(lk == 1, 3 * nat[lc], 6))
-        bad = np.nonzero(ll != expect)[0]
-        if bad.size:
-            b = int(bad[0])
-            k = (ENERGY, FORCES, VIRIAL)[int(lk[b])]
-            raise ValueError(f"observation {k} of config {int(lc[b])} has length {int(ll[b])}, "
-                             f"expected {int(expect[b])}")
-        for ki, k in enumerate((ENERGY, FORCES, VIRIAL)):
-            r = np.zeros(ncfg, dtype=np.int64)
-            m = lk == ki
-            r[lc[m]] = lf[m] + 1             # 1-based at the ABI, 0 = absent
-            rows[k] = r
+    for ki, k in enumerate((ENERGY, FORCES, VIRIAL)):
+        r = np.zeros(ncfg, dtype=np.int64)
+        m = lk == ki
+        r[lc[m]] = lf[m] + 1             # 1-based at the ABI, 0 = absent
+        rows[k] = r
+    return rows
+
+
+def flatten_configs(configs: Sequence[Dat], layout: dict = None):
+    """The flat arrays `ipf_assemble` takes.  `layout` (from `_alloc_rows` on the same list) gives the
+    1-based row blocks without another pass over the configurations."""
+    ncfg = len(configs)
+    off, pos, cell, pbc, Z = _flatten_atoms(configs)
+    rows = _rows_from_layout(layout, ncfg)
+    if rows is not None:
         return off, pos, cell, pbc, Z, rows
+    rows = {}
     for k in (ENERGY, FORCES, VIRIAL):
         r = np.zeros(ncfg, dtype=np.int64)
         for c, d in enumerate(configs):
@@ -161,23 +178,31 @@ class LsqDB:
         ctx = self._context()
         self._dev_basis = _capi.DeviceBasis(ctx, self.basis)
         self._Psi_dev = _capi.DeviceMatrix(ctx, self.nrows, len(self.basis))
-        off, pos, cell, pbc, Z, rows = flatten_configs(self.configs, self._obs_layout)
         # no final synchronisation: the solve / download that follows is ordered behind the assembly on the
-        # context's stream, and the host-side work of lsqfit overlaps the last kernels
+        # context's stream, and the host-side work of lsqfit overlaps the last kernels.  Large sets go down in two
+        # calls so that flattening the second half overlaps the kernels of the first.
+        ncfg = len(self.configs)
+        rows = _rows_from_layout(self._obs_layout, ncfg)
+        parts = [(0, ncfg)] if (rows is None or ncfg < 256) else [(0, ncfg // 2), (ncfg // 2, ncfg)]
         ctx.set_async(True)
         try:
-            self._assemble_call(ctx, off, pos, cell, pbc, Z, rows)
+            for a, b in parts:
+                if rows is None:
+                    off, pos, cell, pbc, Z, r = flatten_configs(self.configs, self._obs_layout)
+                else:
+                    off, pos, cell, pbc, Z = _flatten_atoms(self.configs[a:b])
+                    r = {k: np.ascontiguousarray(v[a:b]) for k, v in rows.items()}
+                self._assemble_call(ctx, b - a, off, pos, cell, pbc, Z, r)
         finally:
             ctx.set_async(False)
         self._Psi_host = None
 
-    def _assemble_call(self, ctx, off, pos, cell, pbc, Z, rows):
+    def _assemble_call(self, ctx, ncfg, off, pos, cell, pbc, Z, rows):
         ctx.check(ctx.lib.ipf_assemble(
-            ctx.h, self._dev_basis.h, len(self.configs), _capi.ptr(off, C.c_int64),
+            ctx.h, self._dev_basis.h, ncfg, _capi.ptr(off, C.c_int64),
             _capi.ptr(pos, C.c_double), _capi.ptr(cell, C.c_double), _capi.ptr(pbc, C.c_uint8),
             _capi.ptr(Z, C.c_int32), _capi.ptr(rows[ENERGY], C.c_int64), _capi.ptr(rows[FORCES], C.c_int64),
             _capi.ptr(rows[VIRIAL], C.c_int64), self._Psi_dev.h))
-        self._Psi_host = None
 
     @property
     def Psi_dev(self) -> _capi.DeviceMatrix:
