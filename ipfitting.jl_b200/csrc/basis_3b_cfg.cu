@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(C_T) tsort_kernel(const int64_t* __restrict__ 
                                                     const int64_t* __restrict__ pbeg, const int32_t* __restrict__ pcnt,
                                                     int ngmax, PassHdr* __restrict__ hdr,
                                                     unsigned char* __restrict__ pblock) {
-    __shared__ int tg[C_T];
     __shared__ int cntA[C_MAXATOMS], gstart[C_MAXATOMS];
+    __shared__ unsigned rowmask[C_MAXATOMS][C_NW];      // bit r of word w: row 32 w + r targets the atom
     __shared__ int wo[C_NW + 1];
     const int c = blockIdx.x, q = blockIdx.y, tid = threadIdx.x;
     const int64_t pc0 = cfg_pair_off[c];
@@ -99,18 +99,22 @@ __global__ void __launch_bounds__(C_T) tsort_kernel(const int64_t* __restrict__ 
     uint16_t* k0s = reinterpret_cast<uint16_t*>(pb + pb_k0(ngmax));
     uint16_t* ns = reinterpret_cast<uint16_t*>(pb + pb_n(ngmax));
     const int tgt = tid < nrow ? pj[P0 + tid] : -1;
-    tg[tid] = tgt;
-    for (int a = tid; a < nat; a += C_T) cntA[a] = 0;
+    for (int i = tid; i < nat * C_NW; i += C_T) (&rowmask[0][0])[i] = 0u;
     __syncthreads();
-    // k = rows before this one with the same target; the last of them records the atom's count
-    int k = 0, later = 0;
+    if (tid < nrow) atomicOr(&rowmask[tgt][tid >> 5], 1u << (tid & 31));      // the final masks do not depend on the order
+    __syncthreads();
+    // k = rows before this one with the same target; cntA = rows of the atom (both from the bit masks)
+    int k = 0;
     if (tid < nrow) {
-        for (int r = 0; r < nrow; ++r) {
-            const bool same = tg[r] == tgt;
-            k += (same && r < tid) ? 1 : 0;
-            later += (same && r > tid) ? 1 : 0;
-        }
-        if (later == 0) cntA[tgt] = k + 1;
+        const int w = tid >> 5;
+        for (int u = 0; u < w; ++u) k += __popc(rowmask[tgt][u]);
+        k += __popc(rowmask[tgt][w] & ((1u << (tid & 31)) - 1u));
+    }
+    for (int a = tid; a < nat; a += C_T) {
+        int n = 0;
+#pragma unroll
+        for (int u = 0; u < C_NW; ++u) n += __popc(rowmask[a][u]);
+        cntA[a] = n;
     }
     __syncthreads();
     if (tid == 0) {      // first group of every atom, atoms in (owner warp, atom) order

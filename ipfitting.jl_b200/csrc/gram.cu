@@ -153,8 +153,16 @@ __global__ void gram_reduce_kernel(const double* __restrict__ part, int ntiles, 
         const int gi = ti * BT + i, gj = tj * BT + j;
         if (gi >= n1 || gj >= n1) continue;
         if (ti == tj && gj < gi) continue;
-        double s = 0.0;
-        for (int c = 0; c < nchunk; ++c) s += part[((size_t)c * ntiles + tile) * (BT * BT) + e];
+        // four interleaved partial sums (fixed order): the loads of four chunks are in flight together
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        const double* pe = part + (size_t)tile * (BT * BT) + e;
+        const size_t cs = (size_t)ntiles * (BT * BT);
+        int c = 0;
+        for (; c + 3 < nchunk; c += 4) {
+            s0 += pe[(size_t)c * cs]; s1 += pe[(size_t)(c + 1) * cs]; s2 += pe[(size_t)(c + 2) * cs]; s3 += pe[(size_t)(c + 3) * cs];
+        }
+        for (; c < nchunk; ++c) s0 += pe[(size_t)c * cs];
+        const double s = (s0 + s1) + (s2 + s3);
         G[(size_t)gj * n1 + gi] = s;
         G[(size_t)gi * n1 + gj] = s;
     }
@@ -207,7 +215,7 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
                                                                       (const int4*)d_tiles, (double*)part);
     }
     if (kernel_ms) IPF_CUDA(ctx, cudaEventRecord(e1, st));
-    gram_reduce_kernel<<<dim3(T, 32), 256, 0, st>>>((const double*)part, T, nchunk, (const int4*)d_tiles, G, n1);
+    gram_reduce_kernel<<<dim3(T, 64), 256, 0, st>>>((const double*)part, T, nchunk, (const int4*)d_tiles, G, n1);
     ctx->launches += 2;
     IPF_CUDA(ctx, cudaGetLastError());
     IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_tiles must outlive the copy

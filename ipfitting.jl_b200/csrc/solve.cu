@@ -89,8 +89,11 @@ constexpr int KB = 32;
 // lower Cholesky, column-major, in place on L (copy of D G D + shift I).  Per block column:
 // warp 0 factors the 32x32 diagonal block in shared memory, every thread solves panel rows against it,
 // then the trailing matrix gets a rank-32 update -- 3 barriers per 32 columns instead of 3 per column.
-__device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, int* __restrict__ flag) {
+// `sP` (pcap rows x KB, k-major) stages the solved panel for the trailing update when the rows below the block fit.
+__device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, int* __restrict__ flag,
+                                                double* __restrict__ sP = nullptr, int pcap = 0) {
     __shared__ double sD[KB][KB + 1];
+    __shared__ double sR[KB];          // reciprocal diagonal of the factored block
     __shared__ int s_fail;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_fail = -1;
@@ -103,20 +106,22 @@ __device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, i
         }
         __syncthreads();
         if (warp == 0) {
+            // left-looking (Cholesky-Crout) on the 32 x 32 block: column j = one dot product per lane (row), the
+            // pivot comes by shuffle; 32 steps of j pipelined shared-memory loads instead of 32 x 31 dependent updates
             for (int j = 0; j < nbk; ++j) {
-                const double d = sD[j][j];
+                double sv = 0.0;
+                if (lane >= j && lane < nbk) {
+                    sv = sD[lane][j];
+                    for (int k = 0; k < j; ++k) sv = fma(-sD[lane][k], sD[j][k], sv);
+                }
+                const double d = __shfl_sync(0xffffffffu, sv, j);
                 if (!(d > 0.0) || !isfinite(d)) { if (lane == 0) s_fail = J0 + j; break; }
                 const double ljj = sqrt(d);
-                __syncwarp();
-                if (lane == j) sD[j][j] = ljj;
-                if (lane > j && lane < nbk) sD[lane][j] = sD[lane][j] / ljj;
-                __syncwarp();
-                if (lane > j && lane < nbk) {
-                    const double lij = sD[lane][j];
-                    for (int k = j + 1; k <= lane; ++k) sD[lane][k] -= lij * sD[k][j];
-                }
+                if (lane == j) { sD[j][j] = ljj; sR[j] = 1.0 / ljj; }
+                else if (lane > j && lane < nbk) sD[lane][j] = sv / ljj;
                 __syncwarp();
             }
+            for (int j = nbk + lane; j < KB; j += 32) sR[j] = 1.0;
         }
         __syncthreads();
         if (s_fail >= 0) {
@@ -139,7 +144,7 @@ __device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, i
                 double v = x[k];
 #pragma unroll
                 for (int m = 0; m < k; ++m) v -= x[m] * sD[k][m];
-                x[k] = v / sD[k][k];
+                x[k] = v * sR[k];
             }
 #pragma unroll
             for (int k = 0; k < KB; ++k) if (k < nbk) L[(size_t)(J0 + k) * n + r] = x[k];
@@ -147,6 +152,31 @@ __device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, i
         __syncthreads();
         // trailing update: L[r][c] -= sum_k L[r][J0+k] L[c][J0+k],  c >= r0, r >= c
         const int nt = n - r0;
+        if (sP != nullptr && nt <= pcap) {
+            // panel from shared memory (sP[k][r - r0]): the single CTA is latency bound on global loads otherwise
+            for (int e = tid; e < KB * nt; e += blockDim.x) {
+                const int k = e / nt, r = e - k * nt;
+                sP[k * pcap + r] = (k < nbk) ? L[(size_t)(J0 + k) * n + r0 + r] : 0.0;
+            }
+            __syncthreads();
+            for (int c = warp; c < nt; c += (int)(blockDim.x >> 5)) {
+                double lc[KB];
+#pragma unroll
+                for (int k = 0; k < KB; ++k) lc[k] = sP[k * pcap + c];
+                double* col = L + (size_t)(r0 + c) * n + r0;
+                for (int r = c + lane; r < nt; r += 32) {
+                    double a0 = col[r], a1 = 0.0;
+#pragma unroll
+                    for (int k = 0; k < KB; k += 2) {
+                        a0 = fma(-sP[k * pcap + r], lc[k], a0);
+                        a1 = fma(-sP[(k + 1) * pcap + r], lc[k + 1], a1);
+                    }
+                    col[r] = a0 + a1;
+                }
+            }
+            __syncthreads();
+            continue;
+        }
         for (int c = warp; c < nt; c += (int)(blockDim.x >> 5)) {
             double lc[KB];
 #pragma unroll
@@ -173,8 +203,9 @@ __device__ __forceinline__ void chol_lower_body(double* __restrict__ L, int n, i
     }
 }
 
-__global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag) {
-    chol_lower_body(L, n, flag);
+__global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L, int n, int* __restrict__ flag, int pcap) {
+    extern __shared__ double chol_panel[];
+    chol_lower_body(L, n, flag, pcap > 0 ? chol_panel : nullptr, pcap);
 }
 
 // ---- K8: force preconditioner (src/lsq.jl:184-234): batched per-configuration blocks --------------
@@ -836,7 +867,17 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, S->dscale, shift);
         IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
         { ProfScope prof_(ctx, "cholesky");
-        chol_lower_kernel<<<1, 256, 0, st>>>(S->L, n, S->flag); }
+        {
+            // shared-memory panel for the trailing update: all rows below the first block, if they fit in 200 KB
+            const int pcap = (n - KB > 0 && (size_t)(n - KB) * KB * sizeof(double) <= (size_t)200 * 1024) ? ((n - KB + 1) & ~1) : 0;
+            const size_t pbytes = sizeof(double) * (size_t)pcap * KB;
+            static size_t attr_bytes = 0;
+            if (pbytes > attr_bytes) {
+                IPF_CUDA(ctx, cudaFuncSetAttribute(chol_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbytes));
+                attr_bytes = pbytes;
+            }
+            chol_lower_kernel<<<1, 256, pbytes, st>>>(S->L, n, S->flag, pcap);
+        } }
         ctx->launches += 2;
         int hf[4];
         IPF_CUDA(ctx, cudaMemcpyAsync(hf, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
