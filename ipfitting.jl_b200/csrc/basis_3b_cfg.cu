@@ -38,12 +38,14 @@ constexpr int C_ZROW = C_T * C_SLD;       // offset of the all-zero stage row th
 //   [16] u16  first group of every owner warp (C_NW + 1 used)
 //   [C_T] u16 offset of the row's centre-atom list in the record window
 //   [C_T] u16 length of that list
+//   [C_T] u16 centre atom of the row (config-local)
 constexpr int C_GROWS = 3;
 constexpr int C_MAXATOMS = 1024;          // atoms per configuration the kernel accepts (tsort_kernel tables)
-__host__ __device__ constexpr int pb_bytes(int ngmax) { return 16 * ngmax + 32 + 4 * C_T; }
+__host__ __device__ constexpr int pb_bytes(int ngmax) { return 16 * ngmax + 32 + 6 * C_T; }
 __host__ __device__ constexpr int pb_woff(int ngmax) { return 16 * ngmax; }
 __host__ __device__ constexpr int pb_k0(int ngmax) { return 16 * ngmax + 32; }
 __host__ __device__ constexpr int pb_n(int ngmax) { return 16 * ngmax + 32 + 2 * C_T; }
+__host__ __device__ constexpr int pb_atom(int ngmax) { return 16 * ngmax + 32 + 4 * C_T; }
 
 // per-pass header written by tsort_kernel
 struct PassHdr {
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(C_T) tsort_kernel(const int64_t* __restrict__ 
     uint16_t* woff = reinterpret_cast<uint16_t*>(pb + pb_woff(ngmax));
     uint16_t* k0s = reinterpret_cast<uint16_t*>(pb + pb_k0(ngmax));
     uint16_t* ns = reinterpret_cast<uint16_t*>(pb + pb_n(ngmax));
+    uint16_t* ctr = reinterpret_cast<uint16_t*>(pb + pb_atom(ngmax));
     const int tgt = tid < nrow ? pj[P0 + tid] : -1;
     for (int i = tid; i < nat * C_NW; i += C_T) (&rowmask[0][0])[i] = 0u;
     __syncthreads();
@@ -137,9 +140,11 @@ __global__ void __launch_bounds__(C_T) tsort_kernel(const int64_t* __restrict__ 
         }
         k0s[tid] = (uint16_t)(pbeg[P0 + tid] - kbeg);
         ns[tid] = (uint16_t)pcnt[P0 + tid];
+        ctr[tid] = (uint16_t)pi[P0 + tid];
     } else {
         k0s[tid] = 0;
         ns[tid] = 0;
+        ctr[tid] = 0xffff;
     }
     if (tid < 16) woff[tid] = (uint16_t)(tid <= C_NW ? wo[tid] : 0);
     if (tid == 0) {
@@ -320,6 +325,7 @@ __global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A) {
 
     for (int i = tid; i < nat * NF * 3; i += C_T) M.F[i] = 0.0;
     for (int i = tid; i < C_SLD; i += C_T) M.stage[C_ZROW + i] = 0.0;
+    for (int i = tid; i < nat; i += C_T) { M.own0[i] = 0; M.own1[i] = 0; }
     double vE[NGRP][3];
 #pragma unroll
     for (int g = 0; g < NGRP; ++g) vE[g][0] = vE[g][1] = vE[g][2] = 0.0;
@@ -340,16 +346,20 @@ __global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A) {
         const int nrow = (int)min((int64_t)C_T, npc - (int64_t)q * C_T);
         const bool live = tid < nrow;
         const bool staged = h.nrec <= A.maxrec;
-        // own-row ranges of the centre atoms of this pass (read in the scatters, after >= 1 barrier)
-        for (int a = h.sf + tid; a <= h.sl; a += C_T) {
-            const int64_t o0 = A.site_off[a0 + a] - P0, o1 = A.site_off[a0 + a + 1] - P0;
-            M.own0[a] = (uint16_t)max((int64_t)0, min((int64_t)nrow, o0));
-            M.own1[a] = (uint16_t)max((int64_t)0, min((int64_t)nrow, o1));
-        }
         cp_async_wait_all();
         __syncthreads();          // records and inputs of this pass have landed; the previous pass is finished
         if (q + 1 < npass) { fetch_inputs(q + 1, b ^ 1); cp_async_commit(); }
         const PassBuf B = pass_buf(b);
+        {   // own-row ranges of the centre atoms of this pass, from the per-row centre atoms (read in the scatters,
+            // after >= 1 barrier; atoms without rows are never visited: sf..sl are consecutive atoms WITH rows or
+            // atoms without any pair, whose entries keep their initial 0 / 0)
+            const uint16_t* ctr = reinterpret_cast<const uint16_t*>(B.pb + pb_atom(A.ngmax));
+            if (live) {
+                const int at = ctr[tid];
+                if (tid == 0 || ctr[tid - 1] != at) M.own0[at] = (uint16_t)tid;
+                if (tid == nrow - 1 || ctr[tid + 1] != at) M.own1[at] = (uint16_t)(tid + 1);
+            }
+        }
         const int k0off = reinterpret_cast<const uint16_t*>(B.pb + pb_k0(A.ngmax))[tid];
         const int n = live ? (int)reinterpret_cast<const uint16_t*>(B.pb + pb_n(A.ngmax))[tid] : 0;
         const int rowoff = (int)(P0 - h.kbeg) + (live ? tid : 0);      // own record in the window
