@@ -257,9 +257,9 @@ __device__ __forceinline__ void scatter_group(const CfgSmem& M, const PassBuf& B
     __syncthreads();
 }
 
-// CTA = (configuration, unit U of w-exponents)
+// CTA = (configuration, unit U of w-exponents): body of one unit
 template <int D, int U>
-__global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A) {
+__device__ __forceinline__ void cfg3b_unit(const Cfg3Args& A) {
     constexpr UnitTable<D> UT{};
     constexpr int C0 = UT.c0[U], C1 = UT.c1[U], SCB = UT.base[U];
     constexpr int NC = C1 - C0 + 1;
@@ -493,20 +493,37 @@ __global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A) {
 }
 
 template <int D, int U>
-int launch_cfg_from(ipf_ctx* ctx, const Cfg3Args& A, int ncfg) {
+__device__ __forceinline__ void cfg3b_dispatch(const Cfg3Args& A, int unit) {
     constexpr UnitTable<D> UT{};
     if constexpr (U < UT.n) {
-        constexpr int NF = scol_base(D, UT.c1[U] + 1) - scol_base(D, UT.c0[U]);
-        const size_t smem = cfg_smem_bytes<D, NF>(A.ga, A.maxrec, A.ngmax);
-        auto kern = cfg3b_kernel<D, U>;
-        static size_t attr_smem = 0;
-        if (smem > attr_smem) {
-            IPF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_smem = smem;
-        }
-        kern<<<(unsigned)ncfg, C_T, smem, ctx->stream>>>(A);
+        if (unit == U) cfg3b_unit<D, U>(A);
+        else cfg3b_dispatch<D, U + 1>(A, unit);
+    }
+}
+
+// One launch per chunk: blockIdx.x = configuration, blockIdx.y = unit (all units in one grid: the tail of every
+// unit's last wave is filled by the next unit's CTAs; one CTA per SM either way, so the register count of the
+// heaviest unit costs nothing).  IPF_3B_UNIT_LAUNCHES=1 launches unit by unit instead.
+template <int D>
+__global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A, int unit0) {
+    cfg3b_dispatch<D, 0>(A, unit0 + (int)blockIdx.y);
+}
+
+template <int D>
+int launch_cfg(ipf_ctx* ctx, const Cfg3Args& A, int ncfg, size_t smem) {
+    constexpr UnitTable<D> UT{};
+    auto kern = cfg3b_kernel<D>;
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        IPF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
+    static const bool unit_launches = getenv("IPF_3B_UNIT_LAUNCHES") != nullptr;
+    if (unit_launches) {
+        for (int u = 0; u < UT.n; ++u) { kern<<<dim3((unsigned)ncfg, 1), C_T, smem, ctx->stream>>>(A, u); ctx->launches++; }
+    } else {
+        kern<<<dim3((unsigned)ncfg, (unsigned)UT.n), C_T, smem, ctx->stream>>>(A, 0);
         ctx->launches++;
-        return launch_cfg_from<D, U + 1>(ctx, A, ncfg);
     }
     return IPF_OK;
 }
@@ -592,7 +609,7 @@ int ipf_assemble_block_3b_cfg(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev&
     {
         ProfScope prof_(ctx, "site_deriv_3b");
         switch (D) {
-#define IPF_CASE(DD) case DD: IPF_CHECK((launch_cfg_from<DD, 0>(ctx, A, (int)ch.ncfg))); break;
+#define IPF_CASE(DD) case DD: IPF_CHECK((launch_cfg<DD>(ctx, A, (int)ch.ncfg, need))); break;
             IPF_CASE(2) IPF_CASE(3) IPF_CASE(4) IPF_CASE(5) IPF_CASE(6) IPF_CASE(7) IPF_CASE(8)
             IPF_CASE(9) IPF_CASE(10) IPF_CASE(11) IPF_CASE(12) IPF_CASE(13) IPF_CASE(14)
 #undef IPF_CASE
