@@ -360,7 +360,7 @@ def run_ours(args):
         traffic = json.load(open(tf))
     tkey = "cfg3b" if resident else "moments3b"
     kname = (f"cfg3b_kernel<{D}, unit 0..7> (configuration-resident 3-body kernel: moments + combine + scatter into the "
-             "E/F/V rows from shared memory; one launch per unit and chunk)" if resident else
+             "E/F/V rows from shared memory; all units of a chunk in one launch, blockIdx.y = unit)" if resident else
              f"moments3b_kernel<{D}, unit 0..7> (3-body basis values + derivatives per ordered pair; 8 unit launches per batch)")
     r_mom = {"kernel": kname,
              "bound": "fp64", "achieved": ach3, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach3 / fp64_peak,
@@ -368,7 +368,7 @@ def run_ours(args):
              "launches": n3, "avg_launch_ms": ms3 / max(1, n3), "algorithmic_flops_per_launch": flops3 / max(1, n3),
              "algorithmic_bytes_per_launch": (pairs3 * 8.0 * (8 + D + 2) + float(nrows) * blk3.nb * 8.0 * args.steps) / max(1, n3),
              "naive_algorithm_equivalent_tflops": naive3, "total_ms": ms3,
-             "note": "one 'launch' = the 8 unit kernels of a chunk; flops = factorised algorithm (DESIGN.md section 4), "
+             "note": "one launch = all units of one chunk of configurations; flops = factorised algorithm (DESIGN.md section 4), "
                      "FMA = 2; algorithmic bytes = pair records read once + Psi rows written once"}
     # (b) gather kernel (scratch path only): HBM bytes = reverse scratch entry (24 B) per (pair, function) + the rows written
     bytes_g = pairs3 * blk3.nb * 24.0 + float(nrows) * blk3.nb * 8.0 * args.steps

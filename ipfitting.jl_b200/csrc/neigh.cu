@@ -109,6 +109,21 @@ __device__ __forceinline__ double bond(const double* __restrict__ Xi, const doub
     return __dadd_rn(__dadd_rn(__dmul_rn(R[0], R[0]), __dmul_rn(R[1], R[1])), __dmul_rn(R[2], R[2]));
 }
 
+// the lattice shift of bond() alone, and the bond for a given shift: the same rounded operations in the same order,
+// so that the shift of a neighbouring cell can be computed once and reused for every atom in it
+__device__ __forceinline__ void bond_shift(const double* __restrict__ C, int sx, int sy, int sz, double* sh) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+        sh[d] = __dadd_rn(__dadd_rn(__dmul_rn((double)sx, C[d]), __dmul_rn((double)sy, C[3 + d])),
+                          __dmul_rn((double)sz, C[6 + d]));
+}
+__device__ __forceinline__ double bond_with_shift(const double* __restrict__ Xi, const double* __restrict__ Xj,
+                                                  const double* __restrict__ sh, double* R) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) R[d] = __dadd_rn(__dsub_rn(Xj[d], Xi[d]), sh[d]);
+    return __dadd_rn(__dadd_rn(__dmul_rn(R[0], R[0]), __dmul_rn(R[1], R[1])), __dmul_rn(R[2], R[2]));
+}
+
 // NL_SUB threads per centre atom (they split the (x, y) columns of neighbouring cells: four times the threads, the
 // kernel is latency bound).  FILL = false: count per (atom, sub-thread); true: write (key, S, R) at the sub-thread's
 // offset, in discovery order (nl_sort_kernel puts every list into its canonical order afterwards).
@@ -149,14 +164,21 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
             for (int oz = -g.m[2]; oz <= g.m[2]; ++oz) {
                 const int tz = cz + oz, sz = floordiv(tz, g.ncell[2]), ccz = tz - sz * g.ncell[2];
                 const int cc = (ccx * g.ncell[1] + ccy) * g.ncell[2] + ccz;
-                for (int q = cs[cc]; q < cs[cc + 1]; ++q) {
+                const int q0 = cs[cc], q1 = cs[cc + 1];
+                if (q0 == q1) continue;
+                // shift of this cell image for atoms wrapped like the centre atom (the common case)
+                double sh0[3];
+                bond_shift(C, sx, sy, sz, sh0);
+                for (int q = q0; q < q1; ++q) {
                     const int j = cell_atoms[a0 + q];
                     const int Sx = sx - atom_wrap[3 * (a0 + j)] + nix;
                     const int Sy = sy - atom_wrap[3 * (a0 + j) + 1] + niy;
                     const int Sz = sz - atom_wrap[3 * (a0 + j) + 2] + niz;
                     if (j == i && Sx == 0 && Sy == 0 && Sz == 0) continue;
                     double R[3];
-                    const double r2 = bond(Xi, pos + 3 * (a0 + j), C, Sx, Sy, Sz, R);
+                    double r2;
+                    if (Sx == sx && Sy == sy && Sz == sz) r2 = bond_with_shift(Xi, pos + 3 * (a0 + j), sh0, R);
+                    else r2 = bond(Xi, pos + 3 * (a0 + j), C, Sx, Sy, Sz, R);
                     if (r2 < rc2) {
                         if (FILL) {
                             keys[o0 + n] = ((unsigned long long)(unsigned)j << 32) |
@@ -178,9 +200,13 @@ __global__ void nl_pairs_kernel(int64_t nsites, const int32_t* __restrict__ site
 __global__ void nl_site_off_kernel(int64_t nsites, const int64_t* __restrict__ sub_off, int64_t* __restrict__ site_off,
                                    unsigned long long* __restrict__ maxn) {
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > nsites) return;
-    site_off[s] = sub_off[NL_SUB * s];
-    if (s < nsites) atomicMax(maxn, (unsigned long long)(sub_off[NL_SUB * (s + 1)] - sub_off[NL_SUB * s]));
+    unsigned cnt = 0;
+    if (s <= nsites) {
+        site_off[s] = sub_off[NL_SUB * s];
+        if (s < nsites) cnt = (unsigned)(sub_off[NL_SUB * (s + 1)] - sub_off[NL_SUB * s]);
+    }
+    cnt = __reduce_max_sync(0xffffffffu, cnt);          // one atomic per warp
+    if ((threadIdx.x & 31) == 0 && cnt) atomicMax(maxn, (unsigned long long)cnt);
 }
 
 __global__ void cfg_offsets_kernel(int64_t ncfg, const int64_t* __restrict__ atom_off,
