@@ -183,3 +183,21 @@ def test_3b_odd_sized_configurations_only(ctx):
     B = ipf.nbpolys(3, si_desc(2.0), 6)
     assert all(len(d.at) % 2 == 1 for d in configs + [iso])
     _check(B, configs + [iso], ctx)
+
+
+@pytest.mark.parametrize("species, transform", [("W", "(2.74/r)^3"), ("Cu", "exp(- 2.0 * (r/2.55 - 1.0))"), ("C", (1, 2.5, 1.54))])
+def test_other_transforms_and_lattices(ctx, species, transform):
+    """Inverse-power and scaled Morse transforms (`README.md:34-37`), bcc / fcc / diamond neighbourhoods, through the
+    fused 2-body and the resident 3-body kernels."""
+    r0 = ipf.rnn(species)
+    d2 = ipf.BondAngleDesc(transform, ipf.CosCut(2.2 * r0 - 0.7, 2.2 * r0))
+    d3 = ipf.BondAngleDesc(transform, ipf.CosCut(1.8 * r0 - 0.5, 1.8 * r0))
+    configs = (synth.rattled_configs(species, 2, 2, seed=81, calc=synth.PairPotential(r0), vacancies=1)
+               + synth.rattled_configs(species, 1, 2, seed=82, calc=synth.PairPotential(r0)))
+    B = ipf.nbpolys(2, d2, 9) + ipf.nbpolys(3, d3, 6)
+    ctx.profile(True); ctx.profile_reset()
+    try:
+        _check(B, configs, ctx)
+        assert ctx.profile_get("site_deriv_2b")[1] > 0 and ctx.profile_get("site_deriv_3b")[1] > 0
+    finally:
+        ctx.profile(False)
