@@ -259,7 +259,7 @@ __device__ __forceinline__ void scatter_group(const CfgSmem& M, const PassBuf& B
 
 // CTA = (configuration, unit U of w-exponents): body of one unit
 template <int D, int U>
-__device__ __forceinline__ void cfg3b_unit(const Cfg3Args& A) {
+__device__ __forceinline__ void cfg3b_unit(const Cfg3Args& A, const int c) {
     constexpr UnitTable<D> UT{};
     constexpr int C0 = UT.c0[U], C1 = UT.c1[U], SCB = UT.base[U];
     constexpr int NC = C1 - C0 + 1;
@@ -271,7 +271,6 @@ __device__ __forceinline__ void cfg3b_unit(const Cfg3Args& A) {
     constexpr int PPR = RS / 2;               // 16-byte pieces per record
     extern __shared__ __align__(16) double sm[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c = blockIdx.x;
     const int64_t a0 = A.atom_off[c];
     const int nat = (int)(A.atom_off[c + 1] - a0);
     const int64_t pc0 = A.cfg_pair_off[c];
@@ -493,20 +492,28 @@ __device__ __forceinline__ void cfg3b_unit(const Cfg3Args& A) {
 }
 
 template <int D, int U>
-__device__ __forceinline__ void cfg3b_dispatch(const Cfg3Args& A, int unit) {
+__device__ __forceinline__ void cfg3b_dispatch(const Cfg3Args& A, int unit, int c) {
     constexpr UnitTable<D> UT{};
     if constexpr (U < UT.n) {
-        if (unit == U) cfg3b_unit<D, U>(A);
-        else cfg3b_dispatch<D, U + 1>(A, unit);
+        if (unit == U) cfg3b_unit<D, U>(A, c);
+        else cfg3b_dispatch<D, U + 1>(A, unit, c);
     }
 }
 
-// One launch per chunk: blockIdx.x = configuration, blockIdx.y = unit (all units in one grid: the tail of every
-// unit's last wave is filled by the next unit's CTAs; one CTA per SM either way, so the register count of the
-// heaviest unit costs nothing).  IPF_3B_UNIT_LAUNCHES=1 launches unit by unit instead.
+// One launch per chunk, all units in one grid.  Block order: groups of `gsz` configurations (one wave of SMs); within
+// a group the units follow each other, each over the same gsz configurations.  So an SM keeps running the same unit
+// body for a whole wave (instruction cache), the eight waves of a group re-read the group's pair records from L2
+// instead of HBM (gsz x ~0.4 MB), and the tail of the grid is one CTA deep instead of one per unit.  One CTA per SM
+// either way, so the register count of the heaviest unit costs nothing.  IPF_3B_UNIT_LAUNCHES=1: unit by unit.
 template <int D>
-__global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A, int unit0) {
-    cfg3b_dispatch<D, 0>(A, unit0 + (int)blockIdx.y);
+__global__ void __launch_bounds__(C_T, 1) cfg3b_kernel(Cfg3Args A, int unit0, int nunits, int ncfg, int gsz) {
+    const int per_group = gsz * nunits;
+    const int g = (int)blockIdx.x / per_group, r = (int)blockIdx.x - g * per_group;
+    const int c0 = g * gsz;
+    const int gn = min(gsz, ncfg - c0);             // configurations of this (possibly last, shorter) group
+    const int unit = r / gn, c = c0 + r - unit * gn;
+    if (unit >= nunits) return;
+    cfg3b_dispatch<D, 0>(A, unit0 + unit, c);
 }
 
 template <int D>
@@ -520,9 +527,9 @@ int launch_cfg(ipf_ctx* ctx, const Cfg3Args& A, int ncfg, size_t smem) {
     }
     static const bool unit_launches = getenv("IPF_3B_UNIT_LAUNCHES") != nullptr;
     if (unit_launches) {
-        for (int u = 0; u < UT.n; ++u) { kern<<<dim3((unsigned)ncfg, 1), C_T, smem, ctx->stream>>>(A, u); ctx->launches++; }
+        for (int u = 0; u < UT.n; ++u) { kern<<<(unsigned)ncfg, C_T, smem, ctx->stream>>>(A, u, 1, ncfg, ncfg); ctx->launches++; }
     } else {
-        kern<<<dim3((unsigned)ncfg, (unsigned)UT.n), C_T, smem, ctx->stream>>>(A, 0);
+        kern<<<(unsigned)ncfg * (unsigned)UT.n, C_T, smem, ctx->stream>>>(A, 0, UT.n, ncfg, std::max(1, ctx->sm_count));
         ctx->launches++;
     }
     return IPF_OK;
