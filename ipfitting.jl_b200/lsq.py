@@ -515,7 +515,9 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
         del solver["P"]          # `src/lsq.jl:460-462`
     precon = _precon_blocks(db, weights, Irows)
     reg = _regulariser_rows(regularisers, db.basis, Icols) if regularisers else None
-    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows, Icols, Dinv, want_R=True, comm=comm, precon=precon,
+    # every row selected (`_select` returns sorted unique indices): no index upload, no gather on the device
+    Irows_dev = None if len(Irows) == len(W) else Irows
+    c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows_dev, Icols, Dinv, want_R=True, comm=comm, precon=precon,
                               factor_solver=factor_solver, reg=reg)
     kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
     if isinstance(saveqr, dict):
