@@ -159,7 +159,17 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import ipf_oracle as O
     basis = make_basis()
-    nthreads = O.num_threads()
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to its workers)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    nthreads = max(O.num_threads(), ncpu)
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=nthreads)        # LAPACK QR of the reference solve
+    except Exception:
+        pass
     cal = make_configs(2, 999)
     ent, ta, ts = cpu_reference_step(basis, cal, nthreads)
     per_cfg = (ta + ts) / 2
