@@ -24,9 +24,10 @@
  * host pointer past return.  Device objects are opaque handles with explicit
  * destroy calls.  Threading: one ipf_ctx = one GPU = one host thread at a time
  * (entry points are not re-entrant on the same ctx; distinct ctxs are independent).
- * Multi-GPU: one process (ctx) per GPU; the only exchange step is the sum of the
- * Gram blocks between ipf_solve_gram and ipf_solve_factor, done by the host
- * (torch.distributed/NCCL all-reduce on the device pointer the library exposes).
+ * Multi-GPU: one ctx per GPU (one process per GPU, or several ctxs in one process, each driven by its own
+ * host thread); the only exchange step is the sum of the Gram blocks of a CholeskyQR pass.  With a communicator
+ * attached (ipf_comm_init) ipf_solve_gram performs it itself: ncclAllReduce on the ctx stream, no host
+ * synchronisation.  Without one the caller may sum the exposed device buffer by any other means.
  */
 #ifndef IPF_B200_H
 #define IPF_B200_H
@@ -46,6 +47,7 @@ extern "C" {
 #define IPF_ENAN_PSI (-6)    /* "discovered NaNs in LSQ system matrix"  src/lsq.jl:285-292 */
 #define IPF_ESINGULAR (-7)   /* factorisation broke down (rank deficient beyond repair) */
 #define IPF_ESTATE (-8)      /* entry points called out of order */
+#define IPF_ENCCL (-9)       /* NCCL error / libnccl.so.2 not loadable (see ipf_last_error) */
 
 #define IPF_MAX_VARS 10      /* (N-1) + (N-1)(N-2)/2 for N = 5 */
 #define IPF_MAX_DEGREE 20
@@ -97,6 +99,23 @@ int32_t ipf_set_async(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_enable(ipf_ctx* ctx, int32_t on);
 int32_t ipf_profile_reset(ipf_ctx* ctx);
 int32_t ipf_profile_get(ipf_ctx* ctx, const char* name, double* ms, int64_t* count);
+
+/* ---- multi-GPU communicator (comm.cu) -----------------------------------
+ * The reference has no distributed path (only a commented-out DistributedArrays stub, src/lsq_db.jl:202-228); this is
+ * the exchange step SURVEY.md section 8(e) defines.  Rank 0 calls ipf_comm_unique_id and hands the 128 bytes to the
+ * other ranks by any transport (Julia: Distributed / MPI / a file); every rank then calls ipf_comm_init (collective).
+ * From then on, on this ctx:
+ *   ipf_solve_gram    returns the Gram block SUMMED over the ranks (identical bits on every rank),
+ *   ipf_solve_finish  returns ssr, ssy summed over the ranks,
+ *   ipf_comm_allreduce_f64 sums a small host vector (error-table sums) over the ranks.
+ * NCCL is loaded at run time (libnccl.so.2); IPF_ENCCL if it is missing. */
+#define IPF_UNIQUE_ID_BYTES 128
+int32_t ipf_comm_unique_id(ipf_ctx* ctx, uint8_t* id /* [IPF_UNIQUE_ID_BYTES] */);
+int32_t ipf_comm_init(ipf_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id);
+int32_t ipf_comm_destroy(ipf_ctx* ctx);
+int32_t ipf_comm_size(const ipf_ctx* ctx);
+int32_t ipf_comm_rank(const ipf_ctx* ctx);
+int32_t ipf_comm_allreduce_f64(ipf_ctx* ctx, double* x, int64_t n);
 
 /* ---- basis ------------------------------------------------------------ */
 int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* blocks,
@@ -188,10 +207,13 @@ int32_t ipf_solve_precon(ipf_ctx* ctx, ipf_solver* S, int64_t nblocks, const int
 int32_t ipf_solve_shape(const ipf_solver* S, int64_t* M, int64_t* n);
 /* the weighted system itself (get_lsq_system, src/lsq.jl:245-311): Aw [M x n] column-major, yw [M] */
 int32_t ipf_solve_system_to_host(ipf_ctx* ctx, const ipf_solver* S, double* Aw, int64_t ld, double* yw);
+/* G_dev: device pointer to the (n+1) x (n+1) Gram block of [A | y] (summed over the ranks when a communicator is
+ * attached; the call returns without waiting for the device) */
 int32_t ipf_solve_gram(ipf_ctx* ctx, ipf_solver* S, void** G_dev, int64_t* n1);
 int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done);
 /* c [n]; R_out [n*n] column-major upper factor of the scaled system, or NULL;
- * ssr, ssy: LOCAL sums |y - A c'|^2 and |y|^2 (sum across ranks before the ratio) */
+ * ssr, ssy: sums |y - A c'|^2 and |y|^2 over the rows of this ctx -- over ALL ranks when a communicator is attached
+ * (otherwise sum them across ranks before taking the ratio) */
 int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, double* ssr, double* ssy);
 /* Regulariser rows (`_regularise!`, src/lsq.jl:163-181): append nextra rows [P | q] to the weighted system (after
  * the row weighting, before the first ipf_solve_gram).  P: column-major nextra x n (ldP), columns = the selected

@@ -15,7 +15,7 @@ IPF_OK = 0
 IPF_MAX_VARS = 10
 
 _ERRNAMES = {-1: "IPF_EINVAL", -2: "IPF_ECUDA", -3: "IPF_ENOMEM", -4: "IPF_ENAN_Y", -5: "IPF_ENAN_W",
-             -6: "IPF_ENAN_PSI", -7: "IPF_ESINGULAR", -8: "IPF_ESTATE"}
+             -6: "IPF_ENAN_PSI", -7: "IPF_ESINGULAR", -8: "IPF_ESTATE", -9: "IPF_ENCCL"}
 # messages the reference raises for the three NaN checks (src/lsq.jl:261-262,291)
 _REF_MESSAGES = {-4: "NaN detected in observations vector", -5: "NaN detected in weights vector",
                  -6: "discovered NaNs in LSQ system matrix"}
@@ -54,6 +54,12 @@ SIGNATURES = {
     "ipf_profile_enable": (C.c_int32, [_vp, C.c_int32]),
     "ipf_profile_reset": (C.c_int32, [_vp]),
     "ipf_profile_get": (C.c_int32, [_vp, C.c_char_p, _dp, _lp]),
+    "ipf_comm_unique_id": (C.c_int32, [_vp, _bp]),
+    "ipf_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
+    "ipf_comm_destroy": (C.c_int32, [_vp]),
+    "ipf_comm_size": (C.c_int32, [_vp]),
+    "ipf_comm_rank": (C.c_int32, [_vp]),
+    "ipf_comm_allreduce_f64": (C.c_int32, [_vp, _dp, C.c_int64]),
     "ipf_basis_create": (C.c_int32, [_vp, C.c_int32, C.POINTER(BlockSpec), C.POINTER(_vp)]),
     "ipf_basis_destroy": (C.c_int32, [_vp, _vp]),
     "ipf_basis_length": (C.c_int64, [_vp]),
@@ -163,6 +169,27 @@ class Context:
     @property
     def launches(self) -> int:
         return int(self.lib.ipf_launch_count(self.h))
+
+    # ---- multi-GPU communicator inside the library (include/ipf_b200.h: ipf_comm_*)
+    def comm_unique_id(self) -> bytes:
+        buf = np.zeros(128, dtype=np.uint8)
+        self.check(self.lib.ipf_comm_unique_id(self.h, ptr(buf, C.c_uint8)))
+        return buf.tobytes()
+
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes):
+        buf = np.frombuffer(unique_id, dtype=np.uint8).copy()
+        if buf.size != 128:
+            raise ValueError("the NCCL unique id has 128 bytes")
+        self.check(self.lib.ipf_comm_init(self.h, int(nranks), int(rank), ptr(buf, C.c_uint8)))
+
+    def comm_size(self) -> int:
+        return int(self.lib.ipf_comm_size(self.h))
+
+    def comm_allreduce(self, x) -> np.ndarray:
+        """Sum of a small host vector over the ranks of the attached communicator."""
+        a = np.ascontiguousarray(x, dtype=np.float64).copy()
+        self.check(self.lib.ipf_comm_allreduce_f64(self.h, ptr(a, C.c_double), a.size))
+        return a
 
     def close(self):
         if self.h:

@@ -520,11 +520,8 @@ template <int D>
 int launch_cfg(ipf_ctx* ctx, const Cfg3Args& A, int ncfg, size_t smem) {
     constexpr UnitTable<D> UT{};
     auto kern = cfg3b_kernel<D>;
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        IPF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
+    // the attribute is per device (several ctxs of one process may sit on different GPUs): set it on every launch
+    IPF_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     static const bool unit_launches = getenv("IPF_3B_UNIT_LAUNCHES") != nullptr;
     if (unit_launches) {
         for (int u = 0; u < UT.n; ++u) { kern<<<(unsigned)ncfg, C_T, smem, ctx->stream>>>(A, u, 1, ncfg, ncfg); ctx->launches++; }

@@ -132,4 +132,104 @@ struct UnitTable {
     }
 };
 
+// The gather pass is shared by the 3-body scratch path (basis_3b.cu) and the 4-body path (basis_4b.cu): both producers
+// write g_p to S[pair][scol][3] and the per-centre-atom own sums to O[site][slot][scol][4].
+// ---- gather: S (reverse entries) + O (own sums) -> E / F / V rows ------------------
+struct Gather3Args {
+    int64_t p0;               // first pair of the batch
+    int64_t c0;               // first config (chunk-local) of the batch
+    int64_t s0;               // first site of the batch
+    int nb;
+    const double* S;          // [np][nb][3]
+    const double* O;          // [nsites][nslot][nb][4]
+    int nslot;
+    const int16_t* scol2col;  // [nb] scratch column -> local basis column
+    const int64_t* atom_off;
+    const int64_t* site_off;
+    const int32_t* prev;
+    const double* pR;
+    const int64_t* rowE;
+    const int64_t* rowF;
+    const int64_t* rowV;
+    double* Psi;
+    int64_t ld, col0;
+};
+
+constexpr int G_THREADS = 256;
+constexpr int G_WARPS = G_THREADS / 32;
+constexpr int G_ACH = 64;         // atoms per shared-memory tile
+constexpr int G_LDT = 3 * G_ACH + 1;
+
+// CTA = (config, 32 scratch columns); lanes = columns, warps split the atoms.
+__global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
+    extern __shared__ double g_smem[];
+    double* Fs = g_smem;                                            // [32][G_LDT]
+    double (*part)[7][32] = reinterpret_cast<double (*)[7][32]>(g_smem + 32 * G_LDT);   // [G_WARPS][7][32]
+    const int c = (int)(A.c0 + blockIdx.x);
+    const int sc = blockIdx.y * 32 + (threadIdx.x & 31);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = sc < A.nb && A.scol2col[sc] >= 0;
+    const int scl = sc < A.nb ? sc : 0;
+    const int64_t a0 = A.atom_off[c];
+    const int nat = (int)(A.atom_off[c + 1] - a0);
+    const int64_t rE = A.rowE[c], rF = A.rowF[c], rV = A.rowV[c];
+    const double* S3 = A.S + 3 * scl;
+    const double4* O4 = reinterpret_cast<const double4*>(A.O) + scl;
+    double e = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
+    for (int ab = 0; ab < nat; ab += G_ACH) {
+        const int na = min(G_ACH, nat - ab);
+        for (int al = warp; al < na; al += G_WARPS) {
+            const int64_t s = a0 + ab + al;
+            const int64_t q0 = A.site_off[s], q1 = A.site_off[s + 1];
+            double f0 = 0.0, f1 = 0.0, f2 = 0.0;
+            if (q1 > q0) {
+                // own sums: one slot per 32-row block of the producer that holds pairs of this atom
+                const int ns = (int)(((q1 - 1 - A.p0) >> 5) - ((q0 - A.p0) >> 5)) + 1;
+                for (int sl = 0; sl < ns; ++sl) {
+                    const double4 o = O4[((s - A.s0) * A.nslot + sl) * A.nb];
+                    f0 += o.x; f1 += o.y; f2 += o.z; e += o.w;
+                }
+            }
+#pragma unroll 4
+            for (int64_t p = q0; p < q1; ++p) {
+                const double* h = S3 + ((int64_t)A.prev[p] - A.p0) * A.nb * 3;
+                const double hx = __ldg(h), hy = __ldg(h + 1), hz = __ldg(h + 2);
+                const double r0 = A.pR[3 * p], r1 = A.pR[3 * p + 1], r2 = A.pR[3 * p + 2];
+                f0 -= hx; f1 -= hy; f2 -= hz;
+                v0 += hx * r0; v1 += hy * r1; v2 += hz * r2;      // xx, yy, zz
+                v3 += hz * r1; v4 += hz * r0; v5 += hy * r0;      // zy, zx, yx
+            }
+            Fs[lane * G_LDT + 3 * al] = f0;
+            Fs[lane * G_LDT + 3 * al + 1] = f1;
+            Fs[lane * G_LDT + 3 * al + 2] = f2;
+        }
+        __syncthreads();
+        if (rF) {
+            const int nrow = 3 * na;
+            for (int cl = 0; cl < 32; ++cl) {
+                const int scc = blockIdx.y * 32 + cl;
+                if (scc >= A.nb) break;
+                if (A.scol2col[scc] < 0) continue;
+                double* colp = A.Psi + (size_t)(A.col0 + A.scol2col[scc]) * A.ld + (rF - 1) + 3 * ab;
+                for (int r = threadIdx.x; r < nrow; r += G_THREADS) colp[r] = Fs[cl * G_LDT + r];
+            }
+        }
+        __syncthreads();
+    }
+    part[warp][0][lane] = e; part[warp][1][lane] = v0; part[warp][2][lane] = v1; part[warp][3][lane] = v2;
+    part[warp][4][lane] = v3; part[warp][5][lane] = v4; part[warp][6][lane] = v5;
+    __syncthreads();
+    if (warp == 0 && live) {
+        double* colp = A.Psi + (size_t)(A.col0 + A.scol2col[sc]) * A.ld;
+#pragma unroll
+        for (int comp = 0; comp < 7; ++comp) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < G_WARPS; ++w) t += part[w][comp][lane];
+            if (comp == 0) { if (rE) colp[rE - 1] = t; }
+            else if (rV) colp[rV - 1 + comp - 1] = t;
+        }
+    }
+}
+
 }  // namespace

@@ -106,8 +106,10 @@ int32_t ipf_destroy(ipf_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     if (ctx->stream2) cudaStreamSynchronize(ctx->stream2);
-    for (int k = 0; k < 8; ++k)
+    for (int k = 0; k < ipf_ctx::kScratchSlots; ++k)
         if (ctx->scratch[k]) cudaFree(ctx->scratch[k]);
+    ipf_basis4b_forget_ctx(ctx);
+    ipf_comm_destroy(ctx);
     for (void* p : ctx->arena.spill) cudaFree(p);
     if (ctx->arena.base) cudaFree(ctx->arena.base);
     if (ctx->matrix_cache) cudaFree(ctx->matrix_cache);
@@ -246,7 +248,7 @@ int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* bl
 
 int32_t ipf_basis_destroy(ipf_ctx* ctx, ipf_basis* B) {
     if (!B) return IPF_OK;
-    if (ctx) cudaSetDevice(ctx->device);
+    if (ctx) { cudaSetDevice(ctx->device); ipf_basis4b_forget(ctx, B); }
     for (auto& b : B->blocks) {
         if (b.mono_start) cudaFree(b.mono_start);
         if (b.mono_exp) cudaFree(b.mono_exp);
@@ -501,11 +503,8 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
                 if (basis->blocks[k2].rc2 == rc) {
                     bool handled = false;
                     if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_2b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
-                    // IPF_3B_MOM=1 selects the "raw moments in HBM + combine" variant (basis_3b_mom.cu): parity-green,
-                    // producer 1.6x faster, consumer still latency-bound (50 vs 34 ms/step in round 1) -> off by default
-                    static const bool mom3b = getenv("IPF_3B_MOM") != nullptr;
-                    if (!ctx->force_generic && !handled && mom3b) IPF_CHECK(ipf_assemble_block_3b_mom(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!ctx->force_generic && !handled) IPF_CHECK(ipf_assemble_block_3b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
+                    if (!ctx->force_generic && !handled) IPF_CHECK(ipf_assemble_block_4b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!handled) IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
                 }
         }

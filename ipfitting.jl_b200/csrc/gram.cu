@@ -197,34 +197,22 @@ int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, i
     void *d_tiles = nullptr, *part = nullptr;
     IPF_CHECK(ipf_scratch(ctx, 6, sizeof(int4) * T, &d_tiles));
     IPF_CHECK(ipf_scratch(ctx, 7, sizeof(double) * (size_t)nchunk * T * BT * BT, &part));
-    IPF_CUDA(ctx, cudaMemcpyAsync(d_tiles, h_tiles.data(), sizeof(int4) * T, cudaMemcpyHostToDevice, st));
-    static bool attr_set = false;
-    if (!attr_set) {
-        IPF_CUDA(ctx, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
-        attr_set = true;
+    // the tile table stays on the device between calls (it depends on n1 only): no upload and no host
+    // synchronisation in the steady state
+    if (ctx->gram_tiles_n1 != n1 || ctx->gram_tiles_ptr != d_tiles) {
+        IPF_CUDA(ctx, cudaMemcpyAsync(d_tiles, h_tiles.data(), sizeof(int4) * T, cudaMemcpyHostToDevice, st));
+        IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_tiles must outlive the copy
+        ctx->gram_tiles_n1 = n1; ctx->gram_tiles_ptr = d_tiles;
     }
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    if (kernel_ms) {
-        IPF_CUDA(ctx, cudaEventCreate(&e0));
-        IPF_CUDA(ctx, cudaEventCreate(&e1));
-        IPF_CUDA(ctx, cudaEventRecord(e0, st));
-    }
+    IPF_CUDA(ctx, cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GRAM_SMEM));
+    (void)kernel_ms;
     {
         ProfScope prof_(ctx, "gram");
         gram_kernel<<<dim3(T, nchunk), GRAM_THREADS, GRAM_SMEM, st>>>(A, ld, Mpad, nt, nchunk, chunk_rows,
                                                                       (const int4*)d_tiles, (double*)part);
     }
-    if (kernel_ms) IPF_CUDA(ctx, cudaEventRecord(e1, st));
     gram_reduce_kernel<<<dim3(T, 64), 256, 0, st>>>((const double*)part, T, nchunk, (const int4*)d_tiles, G, n1);
     ctx->launches += 2;
     IPF_CUDA(ctx, cudaGetLastError());
-    IPF_CUDA(ctx, cudaStreamSynchronize(st));     // h_tiles must outlive the copy
-    if (kernel_ms) {
-        float ms = 0.f;
-        IPF_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
-        *kernel_ms = ms;
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-    }
     return IPF_OK;
 }

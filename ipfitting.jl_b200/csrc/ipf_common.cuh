@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
 #include <map>
 #include <string>
 #include <utility>
@@ -47,8 +48,16 @@ struct ipf_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     // reusable device scratch (grown on demand, freed with the ctx)
-    void* scratch[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-    size_t scratch_bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    static constexpr int kScratchSlots = 12;
+    void* scratch[kScratchSlots] = {};
+    size_t scratch_bytes[kScratchSlots] = {};
+    // combine tables of the 4-body fast path, keyed by the BlockDev they were built for (basis_4b.cu)
+    std::map<const void*, void*> tabs4b;
+    // multi-GPU: NCCL communicator attached by ipf_comm_init (comm.cu); nranks == 1: no exchange
+    int gram_tiles_n1 = -1;             // Gram tile table currently on the device (gram.cu)
+    const void* gram_tiles_ptr = nullptr;
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
 };
 
 struct ipf_matrix {
@@ -209,8 +218,11 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
                                const NeighList& nl, ipf_matrix* Psi);
 int ipf_assemble_block_2b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
                           ipf_matrix* Psi, bool* handled);
-int ipf_assemble_block_3b_mom(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
-                              ipf_matrix* Psi, bool* handled);
+int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
+                          ipf_matrix* Psi, bool* handled);
+void ipf_basis4b_forget(ipf_ctx* ctx, const ipf_basis* B);      // drop the tables of a basis that is being destroyed
+void ipf_basis4b_forget_ctx(ipf_ctx* ctx);
+int ipf_comm_allreduce_dev(ipf_ctx* ctx, double* buf, size_t n);    // in-place sum over the ranks on the ctx stream
 int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch, const NeighList& nl,
                           ipf_matrix* Psi, bool* handled);
 

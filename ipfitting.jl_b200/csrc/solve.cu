@@ -333,6 +333,26 @@ __global__ void unscale_rows_kernel(double* __restrict__ L, int n, const double*
 }
 
 // |G[0:n,0:n] - I|_F^2 and max diagonal; out[0] = frob^2, out[1] = maxdiag (single CTA, deterministic)
+// out[0] = min, out[1] = max of the diagonal of the n x n factor L
+__global__ void diag_minmax_kernel(const double* __restrict__ L, int n, double* __restrict__ out) {
+    __shared__ double s_lo[8], s_hi[8];
+    double lo = 1e300, hi = -1e300;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = L[(size_t)i * n + i];
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, s_lo[w]); hi = fmax(hi, s_hi[w]); }
+        out[0] = lo; out[1] = hi;
+    }
+}
+
 __global__ void defect_kernel(const double* __restrict__ G, int n1, int n, double* __restrict__ out) {
     __shared__ double s_a[32], s_b[32];
     double fro = 0.0, md = 0.0;
@@ -827,9 +847,9 @@ int32_t ipf_solve_gram(ipf_ctx* ctx, ipf_solver* S, void** G_dev, int64_t* n1) {
     if (!ctx || !S) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_gram: bad arguments");
     if (S->state != 0) return ipf_set_error(ctx, IPF_ESTATE, "ipf_solve_gram: called out of order");
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
-    double ms = 0.0;
-    IPF_CHECK(ipf_gram(ctx, S->A, S->Mpad, S->Mpad, S->ncp, S->n1, S->G, &ms));
-    S->gram_ms += ms;
+    IPF_CHECK(ipf_gram(ctx, S->A, S->Mpad, S->Mpad, S->ncp, S->n1, S->G, nullptr));
+    // multi-GPU: sum of the per-rank blocks, on the same stream (comm.cu); every rank then factors the same matrix
+    IPF_CHECK(ipf_comm_allreduce_dev(ctx, S->G, (size_t)S->n1 * S->n1));
     S->state = 1;
     if (G_dev) *G_dev = S->G;
     if (n1) *n1 = S->n1;
@@ -844,45 +864,44 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     const int n = S->n, n1 = S->n1;
     const size_t nn = (size_t)n * n;
     const unsigned nblk = (unsigned)((nn + 255) / 256);
+    // One host round trip per pass: the orthogonality defect of this Gram matrix, the status of the first Cholesky
+    // attempt and the extreme diagonal entries of its factor come back together.
     defect_kernel<<<1, 1024, 0, st>>>(S->G, n1, n, S->red);
-    ctx->launches++;
-    double h[2];
-    IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
-    IPF_CUDA(ctx, cudaStreamSynchronize(st));
-    if (!std::isfinite(h[0]) || !std::isfinite(h[1]))
-        return ipf_set_error(ctx, IPF_ESINGULAR, "ipf_solve_factor: non-finite Gram matrix");
-    const double defect = std::sqrt(h[0]);
-    bool final_pass = S->pass >= 1 && defect <= 0.1;
-    if (S->pass >= 1) S->defect = defect;
-    if (!final_pass && S->pass >= 6)
-        return ipf_set_error(ctx, IPF_ESINGULAR, "CholeskyQR did not reach orthogonality in %d passes (defect %.3e)", S->pass, defect);
     // Cholesky with escalating shift.  The first pass always carries the smallest shift (1e-15 n on the unit
     // diagonal of the equilibrated matrix): it only perturbs the intermediate factor -- the later passes
     // re-orthogonalise, and the accuracy of the solution is set by the last one -- and it saves the failed
     // attempt that every ill-conditioned system (the common case for these bases) would otherwise pay for.
     double shift = S->pass == 0 ? 1e-15 * (double)n : 0.0;
     equil_kernel<<<(n + 255) / 256, 256, 0, st>>>(S->G, n1, n, S->dscale);
-    ctx->launches++;
+    ctx->launches += 2;
+    // shared-memory panel for the trailing update: all rows below the first block, if they fit in 200 KB
+    const int pcap = (n - KB > 0 && (size_t)(n - KB) * KB * sizeof(double) <= (size_t)200 * 1024) ? ((n - KB + 1) & ~1) : 0;
+    const size_t pbytes = sizeof(double) * (size_t)pcap * KB;
+    if (pbytes > 48 * 1024)
+        IPF_CUDA(ctx, cudaFuncSetAttribute(chol_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbytes));
+    double h[4] = {0.0, 0.0, 0.0, 0.0};
+    bool final_pass = false;
     for (int attempt = 0;; ++attempt) {
         copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, S->dscale, shift);
         IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
         { ProfScope prof_(ctx, "cholesky");
-        {
-            // shared-memory panel for the trailing update: all rows below the first block, if they fit in 200 KB
-            const int pcap = (n - KB > 0 && (size_t)(n - KB) * KB * sizeof(double) <= (size_t)200 * 1024) ? ((n - KB + 1) & ~1) : 0;
-            const size_t pbytes = sizeof(double) * (size_t)pcap * KB;
-            static size_t attr_bytes = 0;
-            if (pbytes > attr_bytes) {
-                IPF_CUDA(ctx, cudaFuncSetAttribute(chol_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbytes));
-                attr_bytes = pbytes;
-            }
-            chol_lower_kernel<<<1, 256, pbytes, st>>>(S->L, n, S->flag, pcap);
-        } }
-        ctx->launches += 2;
+          chol_lower_kernel<<<1, 256, pbytes, st>>>(S->L, n, S->flag, pcap); }
+        diag_minmax_kernel<<<1, 256, 0, st>>>(S->L, n, S->red + 2);
+        ctx->launches += 3;
         int hf[4];
         IPF_CUDA(ctx, cudaMemcpyAsync(hf, S->flag, sizeof(int) * 4, cudaMemcpyDeviceToHost, st));
+        IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 4, cudaMemcpyDeviceToHost, st));
         IPF_CUDA(ctx, cudaStreamSynchronize(st));
         IPF_CUDA(ctx, cudaGetLastError());
+        if (attempt == 0) {
+            if (!std::isfinite(h[0]) || !std::isfinite(h[1]))
+                return ipf_set_error(ctx, IPF_ESINGULAR, "ipf_solve_factor: non-finite Gram matrix");
+            const double defect = std::sqrt(h[0]);
+            final_pass = S->pass >= 1 && defect <= 0.1;
+            if (S->pass >= 1) S->defect = defect;
+            if (!final_pass && S->pass >= 6)
+                return ipf_set_error(ctx, IPF_ESINGULAR, "CholeskyQR did not reach orthogonality in %d passes (defect %.3e)", S->pass, defect);
+        }
         if (!hf[1]) break;
         if (attempt >= 12)
             return ipf_set_error(ctx, IPF_ESINGULAR, "Cholesky of the Gram matrix failed at column %d even with shift %.3e", hf[2], shift);
@@ -891,13 +910,8 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     if (!final_pass && S->pass >= 1 && shift == 0.0) {
         // A is not orthonormal yet, but if the EQUILIBRATED Gram matrix is well conditioned the normal
         // equations of this pass (plus one refinement step in finish) are as accurate as another pass:
-        // estimate cond(D G D) from the diagonal of its Cholesky factor
-        std::vector<double> hd((size_t)n);
-        IPF_CUDA(ctx, cudaMemcpy2DAsync(hd.data(), sizeof(double), S->L, sizeof(double) * (size_t)(n + 1), sizeof(double), n,
-                                        cudaMemcpyDeviceToHost, st));
-        IPF_CUDA(ctx, cudaStreamSynchronize(st));
-        double lo = hd[0], hi = hd[0];
-        for (double v : hd) { lo = std::min(lo, v); hi = std::max(hi, v); }
+        // estimate cond(D G D) from the diagonal of its Cholesky factor (h[2] = min, h[3] = max)
+        const double lo = h[2], hi = h[3];
         if (lo > 0.0 && (hi / lo) * (hi / lo) <= 1e3) final_pass = true;
     }
     unscale_rows_kernel<<<nblk, 256, 0, st>>>(S->L, n, S->dscale);
@@ -917,10 +931,6 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         S->state = 2;
         *done = 1;
     } else {
-        cudaEvent_t e0, e1;
-        IPF_CUDA(ctx, cudaEventCreate(&e0));
-        IPF_CUDA(ctx, cudaEventCreate(&e1));
-        IPF_CUDA(ctx, cudaEventRecord(e0, st));
         // A <- A L^-T: product with the explicit inverse on the FP64 tensor cores (trmm.cu);
         // IPF_TRSM_ROWS=1 selects the thread-per-row substitution on the FMA pipe (2.5x slower, kept for A/B runs)
         static const bool trsm_rows = getenv("IPF_TRSM_ROWS") != nullptr;
@@ -931,12 +941,6 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         } else {
             IPF_CHECK(ipf_apply_inverse_transpose(ctx, S->A, S->Mpad, S->Mpad, S->ncp, n, S->L));
         } }
-        IPF_CUDA(ctx, cudaEventRecord(e1, st));
-        IPF_CUDA(ctx, cudaStreamSynchronize(st));
-        float ms = 0.f;
-        cudaEventElapsedTime(&ms, e0, e1);
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
-        S->trsm_ms += ms;
         S->pass++;
         S->state = 0;
         *done = 0;
@@ -979,6 +983,7 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     if (S->dinv) scale_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(cf, S->dinv, n);
     ctx->launches += 4;
     ctx->launches += 6;
+    IPF_CHECK(ipf_comm_allreduce_dev(ctx, S->red, 2));      // residual sums over all ranks (no-op without a communicator)
     double h[2];
     IPF_CUDA(ctx, cudaMemcpyAsync(c, cf, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
     IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
@@ -1079,6 +1084,7 @@ int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double*
     sum_pairs_kernel<<<1, 1024, 0, st>>>(S->red + 8, nb, S->red);
     ctx->launches += 3;
     double h[2];
+    IPF_CHECK(ipf_comm_allreduce_dev(ctx, S->red, 2));
     IPF_CUDA(ctx, cudaMemcpyAsync(h, S->red, sizeof(double) * 2, cudaMemcpyDeviceToHost, st));
     IPF_CUDA(ctx, cudaStreamSynchronize(st));
     IPF_CUDA(ctx, cudaGetLastError());

@@ -185,11 +185,7 @@ int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpa
     IPF_CUDA(ctx, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)kpad * ncp, st));
     trinv_kernel<<<(n1 + TI_WARPS - 1) / TI_WARPS, 32 * TI_WARPS, sizeof(double) * (size_t)n * (TI_WARPS + 1), st>>>(
         L, n, (double*)W, kpad);
-    static bool attr_set = false;
-    if (!attr_set) {
-        IPF_CUDA(ctx, cudaFuncSetAttribute(applyw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
-        attr_set = true;
-    }
+    IPF_CUDA(ctx, cudaFuncSetAttribute(applyw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
     applyw_kernel<<<(unsigned)((Mpad + BT - 1) / BT), AW_THREADS, AW_SMEM, st>>>(A, ld, Mpad, n1, kpad, (const double*)W);
     ctx->launches += 2;
     IPF_CUDA(ctx, cudaGetLastError());

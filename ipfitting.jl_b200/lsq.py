@@ -366,8 +366,8 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True, factor_solver
         cs, extra = factor_solver(R, S.qty())
         ssr, ssy = S.residual(cs)
         c = cs if Dinv is None else cs * Dinv
-    if multi:
-        ssr, ssy = comm.allreduce_scalars([ssr, ssy])
+    if multi and not (hasattr(comm, "attached") and comm.attached()):
+        ssr, ssy = comm.allreduce_scalars([ssr, ssy])      # (an attached library communicator has summed them already)
     info = S.info()
     info.update(extra)
     info["rel_rms"] = math.sqrt(ssr) / math.sqrt(ssy) if ssy > 0 else float("nan")

@@ -1,5 +1,7 @@
-"""Multi-GPU plumbing: one process per GPU (torch.distributed), configs sharded
-across ranks, ONE exchange step per CholeskyQR pass (sum of the Gram blocks).
+"""Multi-GPU plumbing: one process per GPU, configs sharded across ranks, ONE exchange step per
+CholeskyQR pass (sum of the Gram blocks).  The exchange itself lives in the library (csrc/comm.cu:
+ncclAllReduce on the ctx stream inside ipf_solve_gram); torch.distributed only carries the rendezvous
+(broadcast of the NCCL unique id) and the CPU (gloo) tests.
 
 The reference has no distributed path (only a commented-out DistributedArrays stub,
 `src/lsq_db.jl:202-228,252-265`); its single parallel strategy is the descending-cost
@@ -50,6 +52,19 @@ class Communicator:
         self.rank = dist.get_rank(group)
         self.world_size = dist.get_world_size(group)
         self.backend = dist.get_backend(group)
+        self.ctx = None           # the ipf context whose library-side communicator mirrors this group
+
+    def attach(self, ctx):
+        """Create the library's own NCCL communicator over the ranks of this group (`ipf_comm_init`): from then on
+        `ipf_solve_gram` / `ipf_solve_finish` on `ctx` return sums over all ranks and this object only shards."""
+        uid = [ctx.comm_unique_id() if self.rank == 0 else None]
+        self.dist.broadcast_object_list(uid, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                                        group=self.group)
+        ctx.comm_init(self.world_size, self.rank, uid[0])
+        self.ctx = ctx
+
+    def attached(self, ctx=None) -> bool:
+        return self.ctx is not None and (ctx is None or ctx is self.ctx)
 
     def allreduce_device_f64(self, ptr: int, n: int, device: int):
         """In-place sum of n doubles at device address `ptr` across ranks."""
@@ -63,10 +78,12 @@ class Communicator:
         (CPU stand-in of the tests), reduced in place."""
         if isinstance(g, np.ndarray):
             g[...] = self.allreduce_numpy(g).reshape(g.shape)
-        else:
+        elif not self.attached():          # attached: ipf_solve_gram has already summed the blocks
             self.allreduce_device_f64(g, n, device)
 
     def allreduce_numpy(self, a: np.ndarray) -> np.ndarray:
+        if self.attached():
+            return self.ctx.comm_allreduce(np.asarray(a, dtype=np.float64).ravel()).reshape(np.shape(a))
         import torch
         dev = "cuda" if self.backend == "nccl" else "cpu"
         t = torch.from_numpy(np.ascontiguousarray(a)).to(dev)

@@ -100,6 +100,18 @@ def _pairs(at: Atoms, rcut: float):
     return I, J, R
 
 
+def _min_distance(at: Atoms) -> float:
+    """Smallest interatomic distance (all periodic images)."""
+    X, C = at.X, at.cell
+    S = np.array([[i, j, k] for i in (-1, 0, 1) for j in (-1, 0, 1) for k in (-1, 0, 1)], dtype=np.float64)
+    S = S[[all((s == 0) or p for s, p in zip(row, at.pbc)) for row in S]]
+    D = X[None, :, None, :] - X[:, None, None, :] + (S @ C)[None, None, :, :]
+    r2 = np.einsum("ijsd,ijsd->ijs", D, D)
+    ii = np.arange(len(X))
+    r2[ii, ii, int(np.nonzero(np.all(S == 0, axis=1))[0][0])] = np.inf
+    return float(np.sqrt(r2.min()))
+
+
 class PairPotential:
     """V_i = 1/2 sum_j phi(r_ij); LennardJones(r0,e0) * C2Shift(rcut) by default
     (`test/test_fit2b.jl:29-31`)."""
@@ -194,9 +206,11 @@ class StillingerWeber:
 
 def rattled_configs(species: str, L: int, nconfigs: int, *, rmax: Optional[float] = None,
                     strain: float = 0.02, seed: int = 1, calc=None, configtype: str = "rand",
-                    virial: bool = True, vacancies: int = 0) -> List[Dat]:
+                    virial: bool = True, vacancies: int = 0, min_dist: float = 0.0) -> List[Dat]:
     """`generate_data(species, L, rmax, N, calc)` of the reference tests, with the
-    frozen recipe above.  `vacancies`: remove up to this many random atoms."""
+    frozen recipe above.  `vacancies`: remove up to this many random atoms.
+    `min_dist` (in units of r0): a rattled cell with a pair closer than this is drawn again (same
+    stream), so that a handful of near-collisions cannot dominate the labels."""
     from .basis import rnn
     r0 = rnn(species)
     rmax = 0.33 * r0 if rmax is None else rmax
@@ -205,6 +219,8 @@ def rattled_configs(species: str, L: int, nconfigs: int, *, rmax: Optional[float
     out = []
     for _ in range(nconfigs):
         at = rattle(base, rng.uniform() * rmax, rng, strain)
+        while min_dist > 0.0 and _min_distance(at) < min_dist * r0:
+            at = rattle(base, rng.uniform() * rmax, rng, strain)
         ct = configtype
         if vacancies:
             nv = int(rng.integers(0, vacancies + 1))

@@ -244,8 +244,8 @@ static void eval_cluster(const block_t* B, int i, const nbr_t** leg, int what,
     }
 }
 
-static void eval_config_block(const block_t* B, int nat, const double* pos, const double* cell,
-                              const uint8_t* pbc, int what, double* E, double* F, double* V) {
+static void eval_config_block_par(const block_t* B, int nat, const double* pos, const double* cell,
+                                  const uint8_t* pbc, int what, double* E, double* F, double* V, int par) {
     const double rcut = B->D.rc2;
     int64_t cap = ipfo_neighbours(nat, pos, cell, pbc, rcut, 0, NULL, NULL, NULL, NULL);
     int32_t* I = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cap + 1));
@@ -262,12 +262,34 @@ static void eval_config_block(const block_t* B, int nat, const double* pos, cons
         for (int d = 0; d < 3; ++d) { q->R[d] = R[3 * p + d]; q->Rh[d] = R[3 * p + d] / q->r; }
         desc_eval(&B->D, q->r, &q->x, &q->dx, &q->fc, &q->dfc);
     }
-    double* scratch = (double*)malloc(sizeof(double) * (size_t)B->nb * (1 + IPFO_MAX_VARS));
     const int nx = B->N - 1;
-    int64_t p0 = 0;
+    /* first pair of every site */
+    int64_t* soff = (int64_t*)malloc(sizeof(int64_t) * (size_t)(nat + 1));
+    {
+        int64_t q = 0;
+        for (int i = 0; i < nat; ++i) { soff[i] = q; while (q < cap && I[q] == i) ++q; }
+        soff[nat] = q;
+    }
+    /* par != 0: the sites are shared out over the OpenMP threads (dynamic), every thread accumulates into private
+     * E/F/V copies that are added up in thread order at the end (bench.py's CPU arms on a small sample of
+     * configurations: keeps all host threads busy; the sums differ from the serial order by rounding only) */
+#pragma omp parallel if (par)
+    {
+    double *Et = E, *Ft = F, *Vt = V;
+    int priv = 0;
+#ifdef _OPENMP
+    if (par && omp_get_num_threads() > 1) {
+        priv = 1;
+        Et = (double*)calloc((size_t)B->nb, sizeof(double));
+        Ft = (double*)calloc((size_t)B->nb * 3 * (size_t)nat + 1, sizeof(double));
+        Vt = (double*)calloc((size_t)B->nb * 9, sizeof(double));
+    }
+#endif
+    double* scratch = (double*)malloc(sizeof(double) * (size_t)B->nb * (1 + IPFO_MAX_VARS));
+#pragma omp for schedule(dynamic, 1)
     for (int i = 0; i < nat; ++i) {
-        int64_t p1 = p0;
-        while (p1 < cap && I[p1] == i) ++p1;
+        double *E = Et, *F = Ft, *V = Vt;
+        const int64_t p0 = soff[i], p1 = soff[i + 1];
         const int n = (int)(p1 - p0);
         const nbr_t* base = nb + p0;
         const nbr_t* leg[IPFO_MAX_LEGS];
@@ -295,9 +317,24 @@ static void eval_config_block(const block_t* B, int nat, const double* pos, cons
                             eval_cluster(B, i, leg, what, nat, E, F, V, scratch);
                         }
         }
-        p0 = p1;
     }
-    free(scratch); free(nb); free(R); free(S); free(J); free(I);
+    free(scratch);
+    if (priv) {
+#pragma omp critical(ipfo_site_reduce)
+        {
+            for (int b = 0; b < B->nb; ++b) E[b] += Et[b];
+            for (size_t k = 0; k < (size_t)B->nb * 3 * (size_t)nat; ++k) F[k] += Ft[k];
+            for (int k = 0; k < B->nb * 9; ++k) V[k] += Vt[k];
+        }
+        free(Et); free(Ft); free(Vt);
+    }
+    }
+    free(soff); free(nb); free(R); free(S); free(J); free(I);
+}
+
+static void eval_config_block(const block_t* B, int nat, const double* pos, const double* cell,
+                              const uint8_t* pbc, int what, double* E, double* F, double* V) {
+    eval_config_block_par(B, nat, pos, cell, pbc, what, E, F, V, 0);
 }
 
 /* ------------------------------------------------------------------ */
@@ -310,7 +347,9 @@ static void eval_config_block(const block_t* B, int nat, const double* pos, cons
  * mode 1: reference-like: one task per (config, okey), E/F/V evaluated
  *         separately (neighbour list + basis recomputed each time), tasks
  *         taken from a shared queue in descending natoms order
- *         (src/obsiter.jl:87-102, src/tools.jl:35-56). */
+ *         (src/obsiter.jl:87-102, src/tools.jl:35-56).
+ * mode 2: the tasks of mode 1 one after the other, the SITES of each task shared out over the threads
+ *         (for timing a small sample of configurations with every host thread busy). */
 int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t* mono_b,
                             const uint8_t* mono_exp, int32_t transform, double a, double r0,
                             double rc1, double rc2, int64_t ncfg, const int64_t* atom_off,
@@ -324,6 +363,9 @@ int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t*
 
     /* task list */
     const int tasks_per_cfg = mode ? 3 : 1;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
     const int64_t ntask = ncfg * tasks_per_cfg;
     int64_t* order = (int64_t*)malloc(sizeof(int64_t) * (size_t)(ntask + 1));
     for (int64_t t = 0; t < ntask; ++t) order[t] = t;
@@ -341,6 +383,37 @@ int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t*
 #ifdef _OPENMP
     if (nthreads > 0) omp_set_num_threads(nthreads);
 #endif
+    if (mode == 2) {
+        for (int64_t slot = 0; slot < ntask; ++slot) {
+            const int64_t t = order[slot];
+            const int64_t c = t / tasks_per_cfg;
+            int what = 1 << (int)(t % 3);
+            if (!rowE[c]) what &= ~1;
+            if (!rowF[c]) what &= ~2;
+            if (!rowV[c]) what &= ~4;
+            if (!what) continue;
+            const int nat = (int)(atom_off[c + 1] - atom_off[c]);
+            double* E = (double*)calloc((size_t)nb, sizeof(double));
+            double* F = (double*)calloc((size_t)nb * 3 * (size_t)nat + 1, sizeof(double));
+            double* V = (double*)calloc((size_t)nb * 9, sizeof(double));
+            eval_config_block_par(&B, nat, pos + 3 * atom_off[c], cell + 9 * c, pbc + 3 * c, what, E, F, V, 1);
+            for (int b = 0; b < nb; ++b) {
+                double* col = Psi + (size_t)(col0 + b) * (size_t)ld;
+                if (what & 1) col[rowE[c] - 1] = E[b];
+                if (what & 2)
+                    for (int k = 0; k < 3 * nat; ++k) col[rowF[c] - 1 + k] = F[(size_t)b * 3 * nat + k];
+                if (what & 4) {
+                    const double* Vb = V + (size_t)b * 9;
+                    double* o = col + (rowV[c] - 1);
+                    o[0] = Vb[0]; o[1] = Vb[4]; o[2] = Vb[8];
+                    o[3] = Vb[3 * 2 + 1]; o[4] = Vb[3 * 2 + 0]; o[5] = Vb[3 * 1 + 0];
+                }
+            }
+            free(V); free(F); free(E);
+        }
+        free(order);
+        return 0;
+    }
     int64_t next = 0;
 #pragma omp parallel
     {

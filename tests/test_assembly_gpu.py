@@ -201,3 +201,75 @@ def test_other_transforms_and_lattices(ctx, species, transform):
         assert ctx.profile_get("site_deriv_2b")[1] > 0 and ctx.profile_get("site_deriv_3b")[1] > 0
     finally:
         ctx.profile(False)
+
+
+def _entrywise(Psi, ref):
+    """Largest entry-wise relative error over the entries that are not cancellation residue (|ref| above 1e-6 of the
+    column's largest entry of the same observation block is not assumed here: plain |a - b| / |b| where |b| > 0)."""
+    nz = np.abs(ref) > 1e-8 * np.abs(ref).max(axis=0, keepdims=True)
+    return float((np.abs(Psi - ref)[nz] / np.abs(ref)[nz]).max())
+
+
+@pytest.mark.parametrize("D", [1, 2, 3, 4, 6, 8])
+def test_4b_specialised_path(ctx, D):
+    """nbpolys(4, desc, D) goes through the moment-factorised 4-body kernel (basis_4b.cu): small cells with many
+    periodic images of the same atoms, vacancies (odd sizes) and an isolated cluster."""
+    configs = (synth.rattled_configs("Si", 1, 2, seed=90 + D, calc=synth.StillingerWeber())
+               + synth.rattled_configs("Si", 1, 1, seed=95 + D, calc=synth.StillingerWeber(), vacancies=3))
+    iso = synth.rattled_configs("Si", 1, 1, seed=72, calc=synth.StillingerWeber())[0]
+    iso.at = ipf.Atoms(iso.at.X[:6] + 50.0, iso.at.cell * 40.0, (False, False, False), iso.at.Z[:6])
+    iso.D["F"] = iso.D["F"][:18]
+    B = ipf.nbpolys(4, si_desc(1.9 if D <= 6 else 1.7), D)
+    ctx.profile(True); ctx.profile_reset()
+    try:
+        db, ref = _check(B, configs + [iso], ctx)
+        assert ctx.profile_get("site_deriv_4b")[1] > 0, "specialised 4-body path was not taken"
+        assert _entrywise(db.Psi, ref) < 1e-7
+    finally:
+        ctx.profile(False)
+
+
+def test_4b_deg8_64_atom_cells(ctx):
+    """The north-star block: nbpolys(4, desc, 8) (589 functions) on rattled 64-atom Si cells at the README cutoff
+    (2.5 r0, ~34 neighbours per atom) against the oracle (`README.md:41-47`)."""
+    configs = synth.rattled_configs("Si", 2, 2, seed=11, calc=synth.StillingerWeber())
+    B = ipf.nbpolys(4, si_desc(), 8)
+    assert len(B) == 589
+    ctx.profile(True); ctx.profile_reset()
+    try:
+        db, ref = _check(B, configs, ctx)
+        assert ctx.profile_get("site_deriv_4b")[1] > 0
+        print("4-body deg 8, 64 atoms: block-scaled error", psi_errors(db.Psi, ref, configs),
+              "entry-wise (entries above 1e-8 of the column scale)", _entrywise(db.Psi, ref))
+    finally:
+        ctx.profile(False)
+
+
+def test_4b_specialised_equals_table_driven_and_is_reproducible(ctx):
+    configs = synth.rattled_configs("Si", 1, 3, seed=52, calc=synth.StillingerWeber()) + \
+        synth.rattled_configs("W", 2, 1, seed=53, calc=synth.PairPotential(ipf.rnn("W")), vacancies=2)
+    B = ipf.nbpolys(3, si_desc(2.0), 4) + ipf.nbpolys(4, si_desc(1.6), 5)
+    fast = LsqDB("", B, configs, ctx=ctx).Psi
+    again = LsqDB("", B, configs, ctx=ctx).Psi
+    assert np.array_equal(fast, again)
+    ctx.force_generic(True)
+    try:
+        slow = LsqDB("", B, configs, ctx=ctx).Psi
+    finally:
+        ctx.force_generic(False)
+    scale = np.abs(slow).max(axis=0)
+    assert (np.abs(fast - slow).max(axis=0) <= 1e-11 * scale).all()
+
+
+def test_4b_subset_of_orbits_uses_the_specialised_path(ctx):
+    """Any set of complete orbits (here every other function of the canonical basis, reordered) is served by the
+    factorised kernel: its tables are built per function, not per canonical basis."""
+    configs = synth.rattled_configs("Si", 1, 2, seed=54, calc=synth.StillingerWeber())
+    full = ipf.nbpolys(4, si_desc(1.6), 5)
+    B = full[1::2][::-1]
+    ctx.profile(True); ctx.profile_reset()
+    try:
+        _check(B, configs, ctx)
+        assert ctx.profile_get("site_deriv_4b")[1] > 0
+    finally:
+        ctx.profile(False)
