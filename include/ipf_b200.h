@@ -52,6 +52,8 @@ extern "C" {
 #define IPF_MAX_VARS 10      /* (N-1) + (N-1)(N-2)/2 for N = 5 */
 #define IPF_MAX_DEGREE 20
 #define IPF_MAX_ATOMS 4096   /* per configuration */
+#define IPF_MAX_SOLVE_COLS 3072    /* columns of a system handed to ipf_solve* (shared-memory bound of the n x n factor kernels) */
+#define IPF_MAX_PREDICT_COLS 6144  /* columns of a matrix handed to ipf_predict / ipf_residual_stats */
 
 typedef struct ipf_ctx ipf_ctx;
 typedef struct ipf_basis ipf_basis;

@@ -157,7 +157,7 @@ __device__ __forceinline__ void q_terms(const T4Term* __restrict__ t, int nterm,
     }
 }
 
-__global__ void __maxnreg__(144) site4b_kernel(Site4Args A) {
+__global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
     extern __shared__ __align__(16) double sm[];
     double* M = sm;                                          // [G4_NROWS][32]
     double* xp = sm + (size_t)G4_NROWS * 32;                 // [G4_D + 1][32]  x_j^e
@@ -460,6 +460,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         ProfScope prof_(ctx, "pair_record4");
         rec4_kernel<<<(unsigned)((nl.npairs + 127) / 128), 128, 0, st>>>(nl.npairs, rec, rs, (double*)rec4);
         ctx->launches++;
+        IPF_CUDA(ctx, cudaGetLastError());
     }
     const int nbs = T->nbs;
     static const size_t s_budget = getenv("IPF_4B_SCRATCH_GB") ? (size_t)atol(getenv("IPF_4B_SCRATCH_GB")) << 30 : (size_t)4 << 30;
@@ -496,9 +497,9 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         // plus the combination (table cost) and 19 flops per (own leg, function) for the scatter sums
         ctx->prof["count:flops_4b"].ms += lk * (2.0 * G4_NROWS + 30.0) + legs * (T->flops_leg + 19.0 * blk.nb);
     }
-    cudaFuncSetAttribute(site4b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM);
+    IPF_CUDA(ctx, cudaFuncSetAttribute(site4b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     constexpr size_t g_bytes = sizeof(double) * (32 * G_LDT + G_WARPS * 7 * 32);
-    cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes);
+    IPF_CUDA(ctx, cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes));
     static const bool no_overlap = getenv("IPF_NO_OVERLAP") != nullptr;
     cudaStream_t st2 = no_overlap ? ctx->stream : ctx->stream2;
     cudaEvent_t gathered[2] = {nullptr, nullptr};
@@ -525,6 +526,16 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
             ProfScope prof_(ctx, "site_deriv_4b");
             site4b_kernel<<<(unsigned)((A.np + 31) / 32), Q_THREADS, Q_SMEM, st>>>(A);
             ctx->launches++;
+            const cudaError_t le = cudaGetLastError();
+            if (le != cudaSuccess) {
+                cudaFuncAttributes fa;
+                memset(&fa, 0, sizeof(fa));
+                cudaFuncGetAttributes(&fa, site4b_kernel);
+                return ipf_set_error(ctx, IPF_ECUDA, "%s:%d: site4b_kernel<<<%lld, %d, %zu>>>: %s (regs %d, static smem %zu, "
+                                     "max dynamic smem %d, max threads %d, local %zu)", __FILE__, __LINE__,
+                                     (long long)((A.np + 31) / 32), Q_THREADS, Q_SMEM, cudaGetErrorString(le), fa.numRegs,
+                                     fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.maxThreadsPerBlock, fa.localSizeBytes);
+            }
         }
         cudaEvent_t produced;
         IPF_CUDA(ctx, cudaEventCreateWithFlags(&produced, cudaEventDisableTiming));
@@ -542,6 +553,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
             dim3 grid((unsigned)(c1 - c0), (unsigned)((nbs + 31) / 32));
             gather3b_kernel<<<grid, G_THREADS, g_bytes, st2>>>(G);
             ctx->launches++;
+            IPF_CUDA(ctx, cudaGetLastError());
         }
         IPF_CUDA(ctx, cudaEventCreateWithFlags(&gathered[buf], cudaEventDisableTiming));
         IPF_CUDA(ctx, cudaEventRecord(gathered[buf], st2));

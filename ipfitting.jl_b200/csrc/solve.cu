@@ -672,7 +672,11 @@ int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* d
     const int64_t nrows = Psi->nrows;
     const int64_t M = dIrows ? nIrows : nrows;
     const int64_t n64 = dIcols ? nIcols : Psi->ncols;
-    if (M < 0 || n64 <= 0 || n64 > 1 << 20) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad system size");
+    if (M < 0 || n64 <= 0) return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: bad system size");
+    // the n x n factor kernels keep one column of n doubles per warp in shared memory (trinv: 9 n doubles per CTA)
+    if (n64 > IPF_MAX_SOLVE_COLS)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_solve_begin: %lld columns selected, the solve supports at most %d",
+                             (long long)n64, IPF_MAX_SOLVE_COLS);
     ipf_solver* S = new ipf_solver();
     S->M = M; S->n = (int)n64; S->n1 = S->n + 1;
     S->Mpad = ((M + 15) / 16) * 16;
@@ -1128,6 +1132,9 @@ int32_t ipf_predict(ipf_ctx* ctx, const ipf_matrix* Psi, const double* c, double
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     DevBuf<double> dc, dy;
+    if (Psi->ncols > IPF_MAX_PREDICT_COLS)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_predict: %lld columns, at most %d are supported", (long long)Psi->ncols,
+                             IPF_MAX_PREDICT_COLS);
     IPF_CUDA(ctx, dc.alloc(Psi->ncols));
     IPF_CUDA(ctx, dy.alloc(Psi->nrows));
     IPF_CUDA(ctx, cudaMemcpyAsync(dc.p, c, sizeof(double) * Psi->ncols, cudaMemcpyHostToDevice, st));
@@ -1144,6 +1151,9 @@ int32_t ipf_residual_stats(ipf_ctx* ctx, const ipf_matrix* Psi, const double* c,
                            double* sse, double* ssy, int64_t* cnt) {
     if (!ctx || !Psi || !c || !Yraw || !werr || !group || ngroups <= 0 || !sse || !ssy || !cnt)
         return ipf_set_error(ctx, IPF_EINVAL, "ipf_residual_stats: bad arguments");
+    if (Psi->ncols > IPF_MAX_PREDICT_COLS)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_residual_stats: %lld columns, at most %d are supported",
+                             (long long)Psi->ncols, IPF_MAX_PREDICT_COLS);
     IPF_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const int64_t nrows = Psi->nrows;

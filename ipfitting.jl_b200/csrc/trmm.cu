@@ -183,8 +183,13 @@ int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpa
     void* W = nullptr;
     IPF_CHECK(ipf_scratch(ctx, 2, sizeof(double) * (size_t)kpad * ncp, &W));
     IPF_CUDA(ctx, cudaMemsetAsync(W, 0, sizeof(double) * (size_t)kpad * ncp, st));
-    trinv_kernel<<<(n1 + TI_WARPS - 1) / TI_WARPS, 32 * TI_WARPS, sizeof(double) * (size_t)n * (TI_WARPS + 1), st>>>(
-        L, n, (double*)W, kpad);
+    const size_t ti_bytes = sizeof(double) * (size_t)n * (TI_WARPS + 1);
+    if (ti_bytes > (size_t)227 * 1024)
+        return ipf_set_error(ctx, IPF_EINVAL, "ipf_apply_inverse_transpose: n = %d exceeds the shared-memory limit of trinv_kernel", n);
+    if (ti_bytes > 48 * 1024)
+        IPF_CUDA(ctx, cudaFuncSetAttribute(trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ti_bytes));
+    trinv_kernel<<<(n1 + TI_WARPS - 1) / TI_WARPS, 32 * TI_WARPS, ti_bytes, st>>>(L, n, (double*)W, kpad);
+    IPF_CUDA(ctx, cudaGetLastError());
     IPF_CUDA(ctx, cudaFuncSetAttribute(applyw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
     applyw_kernel<<<(unsigned)((Mpad + BT - 1) / BT), AW_THREADS, AW_SMEM, st>>>(A, ld, Mpad, n1, kpad, (const double*)W);
     ctx->launches += 2;
