@@ -25,9 +25,14 @@
 // Mapping.  CTA = 32 consecutive ordered pairs (rows) x G4_NW worker warps; lane = row.
 //   phase 1: worker w accumulates its share of the 612 moments of the 32 rows in registers over the k loop
 //            (generated straight-line bodies, basis_4b_gen.inc) and stores them to shared memory M[moment][row];
-//   phase 2: worker w evaluates its share of the basis functions from table-driven product lists (warp-uniform
-//            indices, conflict-free [moment][row] reads), stages (g_p, e_p) of 4 functions at a time and flushes
-//            g_p to the HBM scratch S[pair][scol][3] and the per-centre-atom own sums to O[site][slot][scol][4];
+//   phase 2: worker w evaluates its share of the basis functions, one ENTRY (class {m, m'} of one function) at a time.
+//            The moment rows are laid out so that the terms of one entry with equal nu0 are runs of consecutive rows
+//            (block (e, m0), then s = m1 + m2, then m2): an entry is one 64-byte record (block rows of both sides,
+//            prefetched one entry ahead) and a body specialised on (c23, raised sides) with every row offset and every
+//            multinomial weight a compile-time constant -- no per-term table loads (the first version spent 60 % of its
+//            stall samples waiting for them).  Reads are conflict-free ([moment][row], lane = row).  (g_p, e_p) of 4
+//            functions at a time are staged and flushed: g_p to the HBM scratch S[pair][scol][3], the per-centre-atom
+//            own sums to O[site][slot][scol][4];
 //   then gather3b_kernel (basis_3b_shared.cuh) turns S and O into the E / F / V rows in a fixed order (no atomics).
 #include <algorithm>
 #include <cstdlib>
@@ -43,23 +48,28 @@ int ipf_pair_records(ipf_ctx* ctx, const BlockDev& blk, const NeighList& nl, con
 namespace {
 
 constexpr int Q_NG = 4;                     // functions per staged output group
-constexpr int Q_LD = 4 * Q_NG + 2;          // doubles per staged row: g(3) x 4, e x 4, pad 2
-constexpr int Q_EOFF = 3 * Q_NG;
+constexpr int Q_GLD = 3 * Q_NG + 2;         // doubles per staged row of g: (gx, gy, gz) x 4, pad 2 (two-way conflicts at most)
+constexpr int Q_STAGE = 32 * Q_GLD + Q_NG * 32;     // doubles per worker: g rows, then e[function][row]
 constexpr int Q_THREADS = 32 * G4_NW;
-constexpr size_t Q_SMEM = sizeof(double) * ((size_t)G4_NROWS * 32 + (size_t)(G4_D + 1) * 32 + (size_t)G4_NW * 32 * Q_LD);
+constexpr size_t Q_SMEM = sizeof(double) * ((size_t)G4_NROWS * 32 + 2 * (size_t)(G4_D + 1) * 32 + (size_t)G4_NW * Q_STAGE);
+static_assert(Q_NG == 4, "the flush maps 5 rows x 6 double2 onto a warp and 16 columns onto a half warp");
 
-struct __align__(16) T4Term {               // one nu of one entry
-    uint32_t offA, offB, offA1, offA2, offB1, offB2;      // byte offsets of moment rows in shared memory
-    double kappa;
+// one class {m, m'} of monomials of one basis function (m' = m with the two other legs exchanged), 16 words:
+//   w[0..4]   rows of the blocks M[a2][c12 - 1 + t][.][.], t = 0..9 (16 bits each; t = 0 is unused when c12 = 0)
+//   w[5..9]   the same for the B side, M[a3][c13 - 1 + t]
+//   w[10]     row of Z2[a2 + a3][c12 + c13] | row of Z2q_1[a2 + a3][c12 + c13 - 1] << 16
+//   w[11]     row of Z2q_2
+//   w[12..14] c12, c13 (0 unless raised) and the weight of S (1/2 for a self-conjugate class): the HIGH words of
+//             the doubles (their low words are zero)
+//   w[15]     a1 | class << 4 | last << 9   (class = 3 c23 + number of raised sides; last entry of its function)
+// (every word is read: a dead word of the prefetched record would be reused by the compiler as a temporary, and that
+//  write-after-write dependency on the load in flight stalled every entry for a full memory latency)
+struct __align__(16) T4Ent {
+    uint32_t w[16];
 };
-struct __align__(16) T4Ent {                // one class {m, m'} of monomials (m' = m with the two other legs exchanged)
-    uint32_t term0;
-    uint16_t nterm;
-    uint8_t a1, flags;                      // flags: bit0 = raised-A products (c12 > 0), bit1 = raised-B products
-    uint32_t offZ2, offZq1, offZq2;
-    float cA, cB, wS;
-};
-static_assert(sizeof(T4Term) == 32 && sizeof(T4Ent) == 32, "table records are read as two 16-byte words");
+static_assert(sizeof(T4Ent) == 64, "entry records are read as four 16-byte words");
+constexpr uint32_t ENT_LAST = 1u << 9;
+inline uint32_t dbl_hi(double v) { uint64_t u; memcpy(&u, &v, 8); return (uint32_t)(u >> 32); }     // v has a zero low word
 
 struct Site4Args {
     int64_t p0, np;                 // batch pair range
@@ -69,9 +79,8 @@ struct Site4Args {
     const int32_t* psite;
     const int64_t* pbeg;
     const int32_t* pcnt;
-    const T4Term* term;
     const T4Ent* ent;
-    const uint32_t* ent0;           // [nbs + 1] entries of every scratch column
+    int went[G4_NW + 1];            // entry range of every worker
     int wsc[G4_NW + 1];             // scratch-column range of every worker (multiples of Q_NG)
     int nb;                         // scratch columns (row length of S)
     double* S;
@@ -94,74 +103,136 @@ __global__ void __launch_bounds__(128) rec4_kernel(int64_t npairs, const double*
     for (int e = 4 + G4_D + 1; e < G4_RS; ++e) o[e] = 0.0;
 }
 
-__device__ __forceinline__ double q_column_sum(const double* __restrict__ stage, int r0, int r1, int lane) {
-    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-    int r = r0;
-    for (; r + 3 < r1; r += 4) {
-        a0 += stage[r * Q_LD + lane];
-        a1 += stage[(r + 1) * Q_LD + lane];
-        a2 += stage[(r + 2) * Q_LD + lane];
-        a3 += stage[(r + 3) * Q_LD + lane];
-    }
-    for (; r < r1; ++r) a0 += stage[r * Q_LD + lane];
-    return (a0 + a1) + (a2 + a3);
-}
-
-// write-out of the Q_NG staged functions of the warp's 32 rows: S rows (96 contiguous bytes per pair) and the
-// per-centre-atom column sums O (same protocol as flush_group of basis_3b.cu, which gather3b_kernel reads)
+// write-out of the Q_NG staged functions of the warp's 32 rows.  S is group-major, S[column group][pair][4][3]: the
+// 32 rows of a group are 3 KB of consecutive bytes (5 rows x 6 double2 per warp instruction).  The per-centre-atom
+// column sums go to O[site][slot][scol][4] (the protocol gather3b_kernel reads): lane = (column 0..15, half), the two
+// halves of the warp sum the even and the odd rows of a piece.
 __device__ __forceinline__ void q_flush(const Site4Args& A, const double* __restrict__ wstage, int64_t plw, int nrw,
                                         int sc0, unsigned pmask, int pout) {
     __syncwarp();
     const int lane = threadIdx.x & 31;
-    constexpr int CH = 3 * Q_NG / 2;
-    double2* S2 = reinterpret_cast<double2*>(A.S);
-    const double2* st2 = reinterpret_cast<const double2*>(wstage);
-    for (int q = lane; q < nrw * CH; q += 32) {
-        const int row = q / CH, c = q - row * CH;
-        S2[((plw + row) * A.nb + sc0) * 3 / 2 + c] = st2[row * (Q_LD / 2) + c];
+    {
+        double2* Sg = reinterpret_cast<double2*>(A.S + ((int64_t)(sc0 >> 2) * A.np + plw) * (3 * Q_NG));
+        const double2* st2 = reinterpret_cast<const double2*>(wstage);
+        const int rl = lane / 6, cl = lane - 6 * rl;        // lanes 30, 31 idle
+        if (lane < 30) {
+#pragma unroll
+            for (int i = 0; i < 7; ++i) {
+                const int row = 5 * i + rl;
+                if (row < nrw) Sg[row * 6 + cl] = st2[row * (Q_GLD / 2) + cl];
+            }
+        }
     }
-    const bool vlive = lane < 4 * Q_NG;
-    const int f = lane < Q_EOFF ? lane / 3 : lane - Q_EOFF;
-    const int d = lane < Q_EOFF ? lane - 3 * f : 3;
+    const int col = lane & 15, half = lane >> 4;
+    // column of the staged group: 0..11 = g of function col / 3, 12..15 = e of function col - 12
+    const double* cp = col < 3 * Q_NG ? wstage + col : wstage + 32 * Q_GLD + (col - 3 * Q_NG) * 32;
+    const int cstride = col < 3 * Q_NG ? Q_GLD : 1;
+    const int f = col < 3 * Q_NG ? col / 3 : col - 3 * Q_NG;
+    const int d = col < 3 * Q_NG ? col - 3 * f : 3;
     unsigned m = pmask;
     while (m) {
         const int r0 = __ffs(m) - 1;
         m &= m - 1;
         const int r1 = m ? (__ffs(m) - 1) : nrw;
-        const double acc = vlive ? q_column_sum(wstage, r0, r1, lane) : 0.0;
+        double a0 = 0.0, a1 = 0.0;
+        int r = r0 + half;
+        for (; r + 2 < r1; r += 4) { a0 += cp[r * cstride]; a1 += cp[(r + 2) * cstride]; }
+        if (r < r1) a0 += cp[r * cstride];
+        double acc = a0 + a1;
+        acc += __shfl_down_sync(0xffffffffu, acc, 16);
         const int orow = __shfl_sync(0xffffffffu, pout, r0);
-        if (vlive) A.O[((int64_t)orow * A.nb + sc0 + f) * 4 + d] = acc;
+        if (half == 0) A.O[((int64_t)orow * A.nb + sc0 + f) * 4 + d] = acc;
     }
     __syncwarp();
 }
 
-template <bool HA, bool HB>
-__device__ __forceinline__ void q_terms(const T4Term* __restrict__ t, int nterm, const char* __restrict__ Mb, double& s,
-                                        double& a1, double& a2, double& b1, double& b2) {
-    for (int i = 0; i < nterm; ++i, ++t) {
-        const uint4 o0 = __ldg(reinterpret_cast<const uint4*>(t));
-        const uint4 o1 = __ldg(reinterpret_cast<const uint4*>(t) + 1);
-        const double kappa = __hiloint2double((int)o1.w, (int)o1.z);
-        const double Av = *reinterpret_cast<const double*>(Mb + o0.x);
-        const double Bk = kappa * *reinterpret_cast<const double*>(Mb + o0.y);
-        s = fma(Av, Bk, s);
-        if constexpr (HA) {
-            a1 = fma(*reinterpret_cast<const double*>(Mb + o0.z), Bk, a1);
-            a2 = fma(*reinterpret_cast<const double*>(Mb + o0.w), Bk, a2);
-        }
-        if constexpr (HB) {
-            const double Ak = kappa * Av;
-            b1 = fma(*reinterpret_cast<const double*>(Mb + o1.x), Ak, b1);
-            b2 = fma(*reinterpret_cast<const double*>(Mb + o1.y), Ak, b2);
-        }
+__host__ __device__ constexpr double q_fact(int k) { return k <= 1 ? 1.0 : (double)k * q_fact(k - 1); }
+__host__ __device__ constexpr int q_tri(int s) { return s * (s + 1) / 2; }
+
+// row t of side SIDE (0 = A, 1 = B) of an entry record
+template <int SIDE, int T>
+__device__ __forceinline__ uint32_t q_row(const uint32_t (&w)[16]) {
+    const uint32_t v = w[5 * SIDE + T / 2];
+    return (T & 1) ? (v >> 16) : (v & 0xffffu);
+}
+
+// accumulators of one entry; the sums alternate between two sets so that consecutive terms do not wait for each other
+struct QAcc {
+    double s[2], a1[2], a2[2], b1[2], b2[2];
+};
+
+// term nu = (N0, SD - N2, N2) of a run; the multinomial weight is a compile-time constant
+template <int C, int N0, int N2, bool HA, bool HB>
+__device__ __forceinline__ void q_term(const double* __restrict__ pA, const double* __restrict__ pB, const double* __restrict__ pRA,
+                                       const double* __restrict__ pRB, double& ra, double& rb, QAcc& Q) {
+    constexpr int SD = C - N0;
+    constexpr int P = N2 & 1;
+    constexpr double kappa = q_fact(C) / (q_fact(N0) * q_fact(SD - N2) * q_fact(N2));
+    const double Av = pA[N2 * 32];
+    const double Bk = kappa == 1.0 ? pB[N2 * 32] : kappa * pB[N2 * 32];
+    Q.s[P] = fma(Av, Bk, Q.s[P]);
+    if constexpr (HA) {
+        const double ra1 = pRA[(N2 + 1) * 32];
+        Q.a1[P] = fma(ra, Bk, Q.a1[P]);
+        Q.a2[P] = fma(ra1, Bk, Q.a2[P]);
+        ra = ra1;
     }
+    if constexpr (HB) {
+        const double Ak = kappa == 1.0 ? Av : kappa * Av;
+        const double rb1 = pRB[(N2 + 1) * 32];
+        Q.b1[P] = fma(rb, Ak, Q.b1[P]);
+        Q.b2[P] = fma(rb1, Ak, Q.b2[P]);
+        rb = rb1;
+    }
+    if constexpr (N2 < SD) q_term<C, N0, N2 + 1, HA, HB>(pA, pB, pRA, pRB, ra, rb, Q);
+}
+
+template <int C, int N0, bool HA, bool HB>
+__device__ __forceinline__ void q_run(const uint32_t (&w)[16], const char* __restrict__ Mb, QAcc& Q) {
+    constexpr int SD = C - N0;              // nu1 + nu2 of this run
+    const double* pA = reinterpret_cast<const double*>(Mb + ((size_t)q_row<0, N0 + 1>(w) << 8)) + q_tri(SD) * 32;
+    const double* pB = reinterpret_cast<const double*>(Mb + ((size_t)q_row<1, N0 + 1>(w) << 8)) + q_tri(SD) * 32;
+    const double* pRA = nullptr;
+    const double* pRB = nullptr;
+    if constexpr (HA) pRA = reinterpret_cast<const double*>(Mb + ((size_t)q_row<0, N0>(w) << 8)) + q_tri(SD + 1) * 32;
+    if constexpr (HB) pRB = reinterpret_cast<const double*>(Mb + ((size_t)q_row<1, N0>(w) << 8)) + q_tri(SD + 1) * 32;
+    double ra = 0.0, rb = 0.0;
+    if constexpr (HA) ra = pRA[0];
+    if constexpr (HB) rb = pRB[0];
+    q_term<C, N0, 0, HA, HB>(pA, pB, pRA, pRB, ra, rb, Q);
+    if constexpr (N0 < C) q_run<C, N0 + 1, HA, HB>(w, Mb, Q);
+}
+
+// sum over nu (|nu| = C) of one entry of class CLS = 3 C + (number of raised sides); a raised side needs c12 >= 1
+// (C <= D - 1), two raised sides C <= D - 2
+template <int CLS>
+__device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __restrict__ Mb, QAcc& Q) {
+    constexpr int C = CLS / 3, V = CLS % 3;
+    if constexpr (C + V <= G4_D) q_run<C, 0, (V >= 1), (V >= 2)>(w, Mb, Q);
+}
+
+__device__ __forceinline__ void q_dispatch(uint32_t cls, const uint32_t (&w)[16], const char* __restrict__ Mb, QAcc& Q) {
+    static_assert(G4_D == 8, "one case per class 0 .. 3 (D + 1) - 1");
+#define Q_CASE(K) case K: q_entry<K>(w, Mb, Q); break;
+    switch (cls) {
+        Q_CASE(0) Q_CASE(1) Q_CASE(2) Q_CASE(3) Q_CASE(4) Q_CASE(5) Q_CASE(6) Q_CASE(7) Q_CASE(8)
+        Q_CASE(9) Q_CASE(10) Q_CASE(11) Q_CASE(12) Q_CASE(13) Q_CASE(14) Q_CASE(15) Q_CASE(16) Q_CASE(17)
+        Q_CASE(18) Q_CASE(19) Q_CASE(20) Q_CASE(21) Q_CASE(22) Q_CASE(23) Q_CASE(24) Q_CASE(25) Q_CASE(26)
+        default: break;
+    }
+#undef Q_CASE
+}
+
+__device__ __forceinline__ void q_load_entry(const T4Ent* __restrict__ e, uint4 (&v)[4]) {
+    const uint4* p = reinterpret_cast<const uint4*>(e);
+    v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2); v[3] = __ldg(p + 3);
 }
 
 __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
     extern __shared__ __align__(16) double sm[];
     double* M = sm;                                          // [G4_NROWS][32]
-    double* xp = sm + (size_t)G4_NROWS * 32;                 // [G4_D + 1][32]  x_j^e
-    double* stage = xp + (size_t)(G4_D + 1) * 32;            // [G4_NW][32][Q_LD]
+    double* xp = sm + (size_t)G4_NROWS * 32;                 // [2][G4_D + 1][32]  x_j^e, then e x_j^(e-1)
+    double* stage = xp + 2 * (size_t)(G4_D + 1) * 32;        // [G4_NW][Q_STAGE]
     const int lane = threadIdx.x & 31, worker = threadIdx.x >> 5;
     const int64_t pl0 = (int64_t)blockIdx.x * 32;
     const int64_t pl = pl0 + lane;
@@ -193,82 +264,91 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
     if (worker == 0) {
         double v = 1.0;
 #pragma unroll
-        for (int e = 0; e <= G4_D; ++e) { xp[e * 32 + lane] = v; v *= xj; }
+        for (int e = 0; e <= G4_D; ++e) {
+            xp[e * 32 + lane] = v;
+            if (e < G4_D) xp[(G4_D + 2 + e) * 32 + lane] = (double)(e + 1) * v;       // (e + 1) x^e: derivative of x^(e+1)
+            v *= xj;
+        }
+        xp[(G4_D + 1) * 32 + lane] = 0.0;
     }
     // ---- phase 1: moments of the 32 rows
     g4_phase1(worker, A.rec4 + k0 * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
     __syncthreads();
 
-    // ---- phase 2: basis functions of this worker, 4 scratch columns at a time
+    // ---- phase 2: basis functions of this worker, entry by entry; 4 scratch columns per staged group
     const char* Mb = reinterpret_cast<const char*>(M + lane);
-    double* wstage = stage + (size_t)worker * 32 * Q_LD;
-    double* myrow = wstage + lane * Q_LD;
+    const char* xb = reinterpret_cast<const char*>(xp + lane);
+    double* wstage = stage + (size_t)worker * Q_STAGE;
+    double* myrow = wstage + lane * Q_GLD;
+    double* mye = wstage + 32 * Q_GLD + lane;
     const double tang = fcj * rinvj, fdx = fcj * dxj, third = fcj * (1.0 / 3.0);
-    for (int sc = A.wsc[worker]; sc < A.wsc[worker + 1]; sc += Q_NG) {
+    int ei = A.went[worker];
+    const int ei_end = A.went[worker + 1];
+    int sc = A.wsc[worker], f = 0;
+    uint4 nx[4];
+    if (ei < ei_end) q_load_entry(A.ent + ei, nx);
+    double S0 = 0.0, S1 = 0.0, T1 = 0.0, T2 = 0.0;
 #pragma unroll 1
-        for (int f = 0; f < Q_NG; ++f) {
-            const uint32_t e0 = __ldg(A.ent0 + sc + f), e1 = __ldg(A.ent0 + sc + f + 1);
-            double S0 = 0.0, S1 = 0.0, T1 = 0.0, T2 = 0.0;
-            for (uint32_t ei = e0; ei < e1; ++ei) {
-                const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(A.ent + ei));
-                const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(A.ent + ei) + 1);
-                const int nterm = (int)(w0.y & 0xffffu), a1 = (int)((w0.y >> 16) & 0xffu), flags = (int)(w0.y >> 24);
-                const T4Term* t = A.term + w0.x;
-                double s = 0.0, ta1 = 0.0, ta2 = 0.0, tb1 = 0.0, tb2 = 0.0;
-                if (flags == 3) q_terms<true, true>(t, nterm, Mb, s, ta1, ta2, tb1, tb2);
-                else if (flags == 1) q_terms<true, false>(t, nterm, Mb, s, ta1, ta2, tb1, tb2);
-                else q_terms<false, false>(t, nterm, Mb, s, ta1, ta2, tb1, tb2);
-                s -= *reinterpret_cast<const double*>(Mb + w0.z);
-                const double xa = xp[a1 * 32 + lane];
-                const double xd = a1 > 0 ? (double)a1 * xp[(a1 - 1) * 32 + lane] : 0.0;
-                const double wS = (double)__uint_as_float(w1.w);
-                const double ws = wS * s;
-                S0 = fma(xa, ws, S0);
-                S1 = fma(xd, ws, S1);
-                if (flags) {
-                    const double z1 = *reinterpret_cast<const double*>(Mb + w0.w);
-                    const double z2 = *reinterpret_cast<const double*>(Mb + w1.x);
-                    const double cA = (double)__uint_as_float(w1.y), cB = (double)__uint_as_float(w1.z);
-                    // c12 (tA - z) + c13 (tB - z)
-                    const double u1 = fma(cA, ta1 - z1, cB * (tb1 - z1));
-                    const double u2 = fma(cA, ta2 - z2, cB * (tb2 - z2));
-                    T1 = fma(xa, u1, T1);
-                    T2 = fma(xa, u2, T2);
-                }
-            }
+    for (; ei < ei_end; ++ei) {
+        uint32_t w[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { w[4 * q] = nx[q].x; w[4 * q + 1] = nx[q].y; w[4 * q + 2] = nx[q].z; w[4 * q + 3] = nx[q].w; }
+        if (ei + 1 < ei_end) q_load_entry(A.ent + ei + 1, nx);        // the next record is in flight during this entry
+        // operands of the entry's epilogue first: their latency overlaps the term sums
+        const double zs = *reinterpret_cast<const double*>(Mb + ((size_t)(w[10] & 0xffffu) << 8));
+        const double z1 = *reinterpret_cast<const double*>(Mb + ((size_t)(w[10] >> 16) << 8));
+        const double z2 = *reinterpret_cast<const double*>(Mb + ((size_t)(w[11] & 0xffffu) << 8));
+        const uint32_t xoff = (w[15] & 0xfu) << 8;
+        const double xa = *reinterpret_cast<const double*>(xb + xoff);
+        const double xd = *reinterpret_cast<const double*>(xb + xoff + (G4_D + 1) * 256);
+        QAcc Q;
+#pragma unroll
+        for (int q = 0; q < 2; ++q) { Q.s[q] = 0.0; Q.a1[q] = 0.0; Q.a2[q] = 0.0; Q.b1[q] = 0.0; Q.b2[q] = 0.0; }
+        q_dispatch((w[15] >> 4) & 0x1fu, w, Mb, Q);
+        const double ws = __hiloint2double((int)w[14], 0) * ((Q.s[0] + Q.s[1]) - zs);
+        S0 = fma(xa, ws, S0);
+        S1 = fma(xd, ws, S1);
+        {
+            // c12 (tA - z) + c13 (tB - z); both weights are zero for an entry without raised products (rows 0 are read then)
+            const double cA = __hiloint2double((int)w[12], 0), cB = __hiloint2double((int)w[13], 0);
+            const double u1 = fma(cA, (Q.a1[0] + Q.a1[1]) - z1, cB * ((Q.b1[0] + Q.b1[1]) - z1));
+            const double u2 = fma(cA, (Q.a2[0] + Q.a2[1]) - z2, cB * ((Q.b2[0] + Q.b2[1]) - z2));
+            T1 = fma(xa, u1, T1);
+            T2 = fma(xa, u2, T2);
+        }
+        if (w[15] & ENT_LAST) {
             const double radial = fma(dfcj, S0, fdx * S1);
             T1 *= tang; T2 *= tang;
             myrow[3 * f] = fma(radial, Rj0, fma(T1, E1[0], T2 * E2[0]));
             myrow[3 * f + 1] = fma(radial, Rj1, fma(T1, E1[1], T2 * E2[1]));
             myrow[3 * f + 2] = fma(radial, Rj2, fma(T1, E1[2], T2 * E2[2]));
-            myrow[Q_EOFF + f] = third * S0;
+            mye[f * 32] = third * S0;
+            S0 = 0.0; S1 = 0.0; T1 = 0.0; T2 = 0.0;
+            if (++f == Q_NG) {
+                q_flush(A, wstage, pl0, nrw, sc, pmask, pout);
+                sc += Q_NG;
+                f = 0;
+            }
         }
-        q_flush(A, wstage, pl0, nrw, sc, pmask, pout);
     }
 }
 
 // ---- host tables --------------------------------------------------------------------------------------------
 struct Tables4 {
     int D = 0, nbs = 0;
-    std::vector<T4Term> term;
     std::vector<T4Ent> ent;
-    std::vector<uint32_t> ent0;
     std::vector<int16_t> s2c;
+    int went[G4_NW + 1] = {};
     int wsc[G4_NW + 1] = {};
     double flops_leg = 0.0;         // combine flops per own leg (FMA = 2)
-    T4Term* d_term = nullptr;
     T4Ent* d_ent = nullptr;
-    uint32_t* d_ent0 = nullptr;
     int16_t* d_s2c = nullptr;
 };
 
-struct Mono { int a[3], c12, c13, c23; };      // slots 1,2,3; pairs (1,2), (1,3), (2,3)
-
-inline uint32_t row_off(int row) { return (uint32_t)row * 32u * 8u; }
-inline int midx(int e, int m0, int m1, int m2) {
+inline int block_row(int e, int m0) {
     constexpr int n1 = G4_D + 1;
-    if (e < 0 || m0 < 0 || m1 < 0 || m2 < 0 || e >= n1 || m0 >= n1 || m1 >= n1 || m2 >= n1) return -1;
-    return g4_midx[((e * n1 + m0) * n1 + m1) * n1 + m2];
+    if (e < 0 || m0 < 0 || e >= n1 || m0 >= n1) return -1;
+    return g4_base[e * n1 + m0];
 }
 
 // returns false when the block is not a set of S3-closed orbits of total degree <= G4_D
@@ -289,6 +369,7 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
             D = std::max(D, deg);
             mons.push_back(v);
         }
+        if (mons.empty()) return false;
         std::sort(mons.begin(), mons.end());
         if (std::adjacent_find(mons.begin(), mons.end()) != mons.end()) return false;
         auto has = [&](const std::array<int, 6>& v) { return std::binary_search(mons.begin(), mons.end(), v); };
@@ -311,6 +392,7 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
             fcls[b].push_back(c);
             const int nt = (c.c23 + 1) * (c.c23 + 2) / 2;
             const bool ha = c.c12 > 0, hb = !self && c.c13 > 0;
+            // per term: kappa B, S (3 flops); raised A: 2 FMA; raised B: kappa A + 2 FMA; per entry: 14
             cost[b] += nt * (3.0 + (ha ? 4.0 : 0.0) + (hb ? 5.0 : 0.0)) + 14.0;
         }
         cost[b] += 25.0;
@@ -328,74 +410,65 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
         wl[w].push_back(b);
         wload[w] += cost[b];
     }
-    T.term.clear(); T.ent.clear(); T.ent0.clear(); T.s2c.clear();
+    T.ent.clear(); T.s2c.clear();
     T.flops_leg = 0.0;
+    auto put16 = [](T4Ent& E, int word, int half, int v) { E.w[word] |= (uint32_t)(v & 0xffff) << (16 * half); };
     int sc = 0;
     for (int w = 0; w < G4_NW; ++w) {
         T.wsc[w] = sc;
+        T.went[w] = (int)T.ent.size();
         std::sort(wl[w].begin(), wl[w].end());
         const int npad = (int)((wl[w].size() + Q_NG - 1) / Q_NG * Q_NG);
         for (int q = 0; q < npad; ++q) {
-            T.ent0.push_back((uint32_t)T.ent.size());
-            if (q >= (int)wl[w].size()) { T.s2c.push_back(-1); ++sc; continue; }
-            const int b = wl[w][q];
-            T.s2c.push_back((int16_t)b);
             ++sc;
-            T.flops_leg += cost[b];
-            for (const Cls& c : fcls[b]) {
+            if (q >= (int)wl[w].size()) {
+                // padding column: one entry of weight zero that closes the (never gathered) function
+                T.s2c.push_back(-1);
                 T4Ent E;
                 memset(&E, 0, sizeof(E));
-                E.term0 = (uint32_t)T.term.size();
+                E.w[15] = ENT_LAST;
+                T.ent.push_back(E);
+                continue;
+            }
+            const int b = wl[w][q];
+            T.s2c.push_back((int16_t)b);
+            T.flops_leg += cost[b];
+            for (size_t ic = 0; ic < fcls[b].size(); ++ic) {
+                const Cls& c = fcls[b][ic];
+                T4Ent E;
+                memset(&E, 0, sizeof(E));
                 const bool ha = c.c12 > 0, hb = !c.self && c.c13 > 0;
-                E.a1 = (uint8_t)c.a1;
-                E.flags = (uint8_t)((ha ? 1 : 0) | (hb ? 2 : 0));
                 if (hb && !ha) return false;      // excluded by the orientation rule
-                E.cA = (float)c.c12; E.cB = hb ? (float)c.c13 : 0.f;
-                E.wS = c.self ? 0.5f : 1.0f;
+                if (c.a2 + c.c12 + c.c23 > G4_D || c.a3 + c.c13 + c.c23 > G4_D) return false;
+                for (int t = 0; t <= c.c23 + 1; ++t) {
+                    // block rows of M[a2][c12 - 1 + t] and M[a3][c13 - 1 + t]; t = 0 is read by the raised products only
+                    const int rA = block_row(c.a2, c.c12 - 1 + t), rB = block_row(c.a3, c.c13 - 1 + t);
+                    if ((t >= 1 || ha) && rA < 0) return false;
+                    if ((t >= 1 || hb) && rB < 0) return false;
+                    put16(E, t / 2, t & 1, std::max(rA, 0));
+                    put16(E, 5 + t / 2, t & 1, std::max(rB, 0));
+                }
                 const int zr = g4_z2idx[(c.a2 + c.a3) * (G4_D + 1) + c.c12 + c.c13];
                 if (zr < 0) return false;
-                E.offZ2 = row_off(zr);
+                put16(E, 10, 0, zr);
                 if (ha) {
                     const int q1 = g4_z2qidx[((0) * (G4_D + 1) + c.a2 + c.a3) * (G4_D + 1) + c.c12 + c.c13 - 1];
                     const int q2 = g4_z2qidx[((1) * (G4_D + 1) + c.a2 + c.a3) * (G4_D + 1) + c.c12 + c.c13 - 1];
                     if (q1 < 0 || q2 < 0) return false;
-                    E.offZq1 = row_off(q1); E.offZq2 = row_off(q2);
+                    put16(E, 10, 1, q1);
+                    put16(E, 11, 0, q2);
                 }
-                int nt = 0;
-                for (int n0 = 0; n0 <= c.c23; ++n0)
-                    for (int n1 = 0; n1 <= c.c23 - n0; ++n1) {
-                        const int n2 = c.c23 - n0 - n1;
-                        double kap = 1.0;      // c23! / (n0! n1! n2!)
-                        {
-                            auto fact = [](int k) { double f = 1.0; for (int i = 2; i <= k; ++i) f *= i; return f; };
-                            kap = fact(c.c23) / (fact(n0) * fact(n1) * fact(n2));
-                        }
-                        T4Term t;
-                        memset(&t, 0, sizeof(t));
-                        const int rA = midx(c.a2, c.c12 + n0, n1, n2), rB = midx(c.a3, c.c13 + n0, n1, n2);
-                        if (rA < 0 || rB < 0) return false;
-                        t.offA = row_off(rA); t.offB = row_off(rB);
-                        if (ha) {
-                            const int r1 = midx(c.a2, c.c12 - 1 + n0, n1 + 1, n2), r2 = midx(c.a2, c.c12 - 1 + n0, n1, n2 + 1);
-                            if (r1 < 0 || r2 < 0) return false;
-                            t.offA1 = row_off(r1); t.offA2 = row_off(r2);
-                        }
-                        if (hb) {
-                            const int r1 = midx(c.a3, c.c13 - 1 + n0, n1 + 1, n2), r2 = midx(c.a3, c.c13 - 1 + n0, n1, n2 + 1);
-                            if (r1 < 0 || r2 < 0) return false;
-                            t.offB1 = row_off(r1); t.offB2 = row_off(r2);
-                        }
-                        t.kappa = kap;
-                        T.term.push_back(t);
-                        ++nt;
-                    }
-                E.nterm = (uint16_t)nt;
+                const uint32_t cls = 3u * (uint32_t)c.c23 + (ha ? 1u : 0u) + (hb ? 1u : 0u);
+                E.w[15] = (uint32_t)c.a1 | cls << 4 | (ic + 1 == fcls[b].size() ? ENT_LAST : 0u);
+                E.w[12] = dbl_hi((double)c.c12);
+                E.w[13] = dbl_hi(hb ? (double)c.c13 : 0.0);
+                E.w[14] = dbl_hi(c.self ? 0.5 : 1.0);
                 T.ent.push_back(E);
             }
         }
     }
     T.wsc[G4_NW] = sc;
-    T.ent0.push_back((uint32_t)T.ent.size());
+    T.went[G4_NW] = (int)T.ent.size();
     T.nbs = sc;
     return true;
 }
@@ -403,9 +476,7 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
 void free_tables(void* q) {
     Tables4* T = (Tables4*)q;
     if (!T) return;
-    if (T->d_term) cudaFree(T->d_term);
     if (T->d_ent) cudaFree(T->d_ent);
-    if (T->d_ent0) cudaFree(T->d_ent0);
     if (T->d_s2c) cudaFree(T->d_s2c);
     delete T;
 }
@@ -435,13 +506,9 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         Tables4* T = new Tables4();
         if (!build_tables(blk, *T)) { delete T; T = nullptr; }
         if (T) {
-            IPF_CUDA(ctx, cudaMalloc((void**)&T->d_term, sizeof(T4Term) * std::max<size_t>(1, T->term.size())));
             IPF_CUDA(ctx, cudaMalloc((void**)&T->d_ent, sizeof(T4Ent) * std::max<size_t>(1, T->ent.size())));
-            IPF_CUDA(ctx, cudaMalloc((void**)&T->d_ent0, sizeof(uint32_t) * T->ent0.size()));
             IPF_CUDA(ctx, cudaMalloc((void**)&T->d_s2c, sizeof(int16_t) * std::max<size_t>(1, T->s2c.size())));
-            IPF_CUDA(ctx, cudaMemcpy(T->d_term, T->term.data(), sizeof(T4Term) * T->term.size(), cudaMemcpyHostToDevice));
             IPF_CUDA(ctx, cudaMemcpy(T->d_ent, T->ent.data(), sizeof(T4Ent) * T->ent.size(), cudaMemcpyHostToDevice));
-            IPF_CUDA(ctx, cudaMemcpy(T->d_ent0, T->ent0.data(), sizeof(uint32_t) * T->ent0.size(), cudaMemcpyHostToDevice));
             IPF_CUDA(ctx, cudaMemcpy(T->d_s2c, T->s2c.data(), sizeof(int16_t) * T->s2c.size(), cudaMemcpyHostToDevice));
         }
         it = ctx->tabs4b.emplace((const void*)&blk, (void*)T).first;
@@ -513,8 +580,8 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         A.p0 = nl.h_cfg_pair_off[c0]; A.np = nl.h_cfg_pair_off[c1] - A.p0;
         A.rec = rec; A.rs = rs; A.rec4 = (const double*)rec4;
         A.psite = nl.psite.p; A.pbeg = nl.pbeg.p; A.pcnt = nl.pcnt.p;
-        A.term = T->d_term; A.ent = T->d_ent; A.ent0 = T->d_ent0;
-        for (int w = 0; w <= G4_NW; ++w) A.wsc[w] = T->wsc[w];
+        A.ent = T->d_ent;
+        for (int w = 0; w <= G4_NW; ++w) { A.wsc[w] = T->wsc[w]; A.went[w] = T->went[w]; }
         A.nb = nbs; A.S = (double*)Sbuf[buf]; A.O = (double*)Obuf[buf];
         A.s0 = ch.h_atom_off[c0]; A.nslot = nslot;
         if (gathered[buf]) {
@@ -544,6 +611,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         cudaEventDestroy(produced);
         Gather3Args G;
         G.p0 = A.p0; G.c0 = c0; G.s0 = A.s0; G.nb = nbs; G.S = (const double*)Sbuf[buf];
+        G.pstride = 3 * Q_NG; G.gstride = (int64_t)3 * Q_NG * A.np;
         G.O = (const double*)Obuf[buf]; G.nslot = nslot; G.scol2col = T->d_s2c;
         G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
         G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;
