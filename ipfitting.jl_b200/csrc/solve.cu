@@ -24,7 +24,8 @@
 
 int ipf_gram(ipf_ctx* ctx, const double* A, int64_t ld, int64_t Mpad, int ncp, int n1, double* G, double* kernel_ms);
 
-int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpad, int ncp, int n, const double* L);
+int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpad, int ncp, int n, const double* L,
+                                double* Wsave);
 
 struct ipf_solver {
     int64_t M = 0, Mpad = 0;        // local rows (selected, weight != 0), padded to 16
@@ -46,6 +47,13 @@ struct ipf_solver {
     int pass = 0;
     int state = 0;                  // 0: need gram, 1: need factor, 2: done
     double defect = -1.0, shift = 0.0, gram_ms = 0.0, trsm_ms = 0.0;
+    // The operator that every completed re-orthogonalisation pass actually applied, A_{p+1} = A_p W_p: the explicit
+    // inverse W_p = fl(L_p^-1)^T of the tensor-core product (hist_inverse = true; carried back with c <- W_p c) or, for
+    // the substitution kernel, L_p^T (carried back with a triangular solve).  The solution must be mapped back to
+    // the original basis with the SAME operators: A_0 fl(L^-1)^T and A_0 L^-T differ by eps cond(L_p)^2, which for a
+    // first pass with cond(L_0) ~ 1e6 (systems with cond(R) ~ 1e16) is 1e-3 of the residual.
+    std::vector<double*> hist;
+    bool hist_inverse = true;
 };
 
 namespace {
@@ -644,6 +652,8 @@ void free_solve(ipf_solver* S) {
     for (void* p : {(void*)S->A, (void*)S->yorig, (void*)S->G, (void*)S->L, (void*)S->Rtot, (void*)S->Rtmp,
                     (void*)S->vec, (void*)S->dscale, (void*)S->work, (void*)S->Lt, (void*)S->dinv, (void*)S->flag, (void*)S->red})
         if (p) cudaFree(p);
+    if (!S->pooled)
+        for (double* p : S->hist) cudaFree(p);
     delete S;
 }
 
@@ -938,12 +948,18 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         // A <- A L^-T: product with the explicit inverse on the FP64 tensor cores (trmm.cu);
         // IPF_TRSM_ROWS=1 selects the thread-per-row substitution on the FMA pipe (2.5x slower, kept for A/B runs)
         static const bool trsm_rows = getenv("IPF_TRSM_ROWS") != nullptr;
+        double* hp = nullptr;
+        if (S->pooled) IPF_CHECK(ipf_arena_alloc_in(ctx, ctx->solve_arena, sizeof(double) * nn, (void**)&hp));
+        else IPF_CUDA(ctx, cudaMalloc((void**)&hp, sizeof(double) * nn));
+        S->hist.push_back(hp);
+        S->hist_inverse = !trsm_rows;
         { ProfScope prof_(ctx, "trsm");
         if (trsm_rows) {
+            rprod_kernel<<<nblk, 256, 0, st>>>(S->L, nullptr, hp, n);          // hp = L^T
             trsm_rows_kernel<<<(unsigned)((S->Mpad + TRSM_THREADS - 1) / TRSM_THREADS), TRSM_THREADS, 0, st>>>(S->A, S->Mpad, S->M, S->L, n);
-            ctx->launches++;
+            ctx->launches += 2;
         } else {
-            IPF_CHECK(ipf_apply_inverse_transpose(ctx, S->A, S->Mpad, S->Mpad, S->ncp, n, S->L));
+            IPF_CHECK(ipf_apply_inverse_transpose(ctx, S->A, S->Mpad, S->Mpad, S->ncp, n, S->L, hp));
         } }
         S->pass++;
         S->state = 0;
@@ -980,10 +996,21 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
     { ProfScope prof_(ctx, "residual");
     residual_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, n, cc, S->red + 8); }
     sum_pairs_kernel<<<1, 1024, 0, st>>>(S->red + 8, nb, S->red);
-    // solution in the original (scaled) basis: A_p = A_0 Rprev^-1  =>  c = Rprev^-1 cc
-    // (Rtmp holds Rprev: factor swapped it out when it formed Rtot = L^T Rprev)
+    // solution in the original (scaled) basis: A_p = A_0 W_0 ... W_{p-1}  =>  c = W_0 ( ... (W_{p-1} cc)), with the
+    // operators the passes applied (see ipf_solver::hist)
     IPF_CUDA(ctx, cudaMemcpyAsync(cf, cc, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
-    trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->Rtmp, n, cf, 1);
+    {
+        double* tmp = S->work + 3 * S->n1;
+        for (size_t q = S->hist.size(); q-- > 0;) {
+            if (S->hist_inverse) {
+                triu_matvec_kernel<<<nvb, 256, 0, st>>>(S->hist[q], n, cf, tmp);
+                IPF_CUDA(ctx, cudaMemcpyAsync(cf, tmp, sizeof(double) * n, cudaMemcpyDeviceToDevice, st));
+            } else {
+                trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->hist[q], n, cf, 1);
+            }
+            ctx->launches++;
+        }
+    }
     if (S->dinv) scale_vec_kernel<<<(n + 255) / 256, 256, 0, st>>>(cf, S->dinv, n);
     ctx->launches += 4;
     ctx->launches += 6;

@@ -175,7 +175,9 @@ __global__ void __launch_bounds__(32 * TI_WARPS) trinv_kernel(const double* __re
 }  // namespace
 
 // A (Mpad x ncp column-major, ld) <- A W with W = blockdiag(L^-T, 1);  L: n x n column-major lower.
-int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpad, int ncp, int n, const double* L) {
+// Wsave (n x n column-major, may be NULL) receives the L^-T block that was actually applied.
+int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpad, int ncp, int n, const double* L,
+                                double* Wsave) {
     cudaStream_t st = ctx->stream;
     const int n1 = n + 1;
     const int kpad = (n1 + BK - 1) / BK * BK;
@@ -190,6 +192,9 @@ int ipf_apply_inverse_transpose(ipf_ctx* ctx, double* A, int64_t ld, int64_t Mpa
         IPF_CUDA(ctx, cudaFuncSetAttribute(trinv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ti_bytes));
     trinv_kernel<<<(n1 + TI_WARPS - 1) / TI_WARPS, 32 * TI_WARPS, ti_bytes, st>>>(L, n, (double*)W, kpad);
     IPF_CUDA(ctx, cudaGetLastError());
+    if (Wsave)
+        IPF_CUDA(ctx, cudaMemcpy2DAsync(Wsave, sizeof(double) * n, W, sizeof(double) * kpad, sizeof(double) * n, n,
+                                        cudaMemcpyDeviceToDevice, st));
     IPF_CUDA(ctx, cudaFuncSetAttribute(applyw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)AW_SMEM));
     applyw_kernel<<<(unsigned)((Mpad + BT - 1) / BT), AW_THREADS, AW_SMEM, st>>>(A, ld, Mpad, n1, kpad, (const double*)W);
     ctx->launches += 2;

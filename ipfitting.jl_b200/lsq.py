@@ -523,8 +523,6 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     if isinstance(saveqr, dict):
         saveqr["R"] = R
         saveqr["Y"] = (W * Y)[Irows]
-    if deldb:
-        db.delete()
     # combine(db.basis, c) uses the FULL basis (`src/lsq.jl:603`): scatter a subset fit
     cfull = np.zeros(len(db.basis))
     if Icols is None:
@@ -536,6 +534,10 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
         IP = SumIP(Vref, IP)
     infodict = asm_fitinfo(db, IP, c, Icols, weights, Vref, E0, regularisers, verbose, error_table,
                            cfull=cfull, comm=comm)
+    if deldb:
+        # the reference drops the matrix before its error table, which re-evaluates the IP (`src/lsq.jl:642-648`);
+        # here the table is Psi*c, so the device matrix must outlive it
+        db.delete()
     infodict["cond_R"] = kappa
     infodict["rel_rms"] = info["rel_rms"]
     infodict["solve_info"] = info

@@ -98,7 +98,9 @@ class Dat:
         return {"__id__": "IPFitting.Dat", "at": self.at.write_dict(),
                 "configtype": self.configtype,
                 "D": {k: v.tolist() for k, v in self.D.items()},
-                "rows": {k: [int(r[0]) + 1, int(r[0]) + int(r[1])] for k, r in self.rows.items()},
+                # the explicit 1-based index vector, as `set_matrows!(d, okey, collect(nrows .+ (1:len)))` stores it
+                # (`src/lsq_db.jl:244-246`, written as is by `write_dict`, `src/prototypes.jl:47-53`)
+                "rows": {k: list(range(int(r[0]) + 1, int(r[0]) + int(r[1]) + 1)) for k, r in self.rows.items()},
                 "info": _jsonable(self.info)}
 
     @staticmethod
@@ -107,7 +109,12 @@ class Dat:
                 D={k: np.asarray(v, dtype=np.float64) for k, v in Dd["D"].items()},
                 info=Dd.get("info", {}))
         for k, r in Dd.get("rows", {}).items():
-            d.rows[k] = (int(r[0]) - 1, int(r[1]) - int(r[0]) + 1)
+            r = [int(v) for v in np.atleast_1d(r)]
+            if not r:
+                continue
+            if any(r[i + 1] != r[i] + 1 for i in range(len(r) - 1)):
+                raise ValueError(f"rows[{k!r}] is not a contiguous block: the design matrix stores one block per observation")
+            d.rows[k] = (r[0] - 1, len(r))
         return d
 
 

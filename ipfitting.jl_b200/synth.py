@@ -61,8 +61,13 @@ def repeat(at: Atoms, n: Sequence[int]) -> Atoms:
     return Atoms(X, cell, at.pbc, Z)
 
 
-def rattle(at: Atoms, amp: float, rng: np.random.Generator, strain: float = 0.0) -> Atoms:
-    X = at.X + amp * rng.uniform(-1.0, 1.0, size=at.X.shape)
+def rattle(at: Atoms, amp: float, rng: np.random.Generator, strain: float = 0.0, mode: str = "box") -> Atoms:
+    """mode "box": every coordinate moves by up to +-amp (the frozen recipe of the fixtures); mode "julip": the
+    displacement of JuLIP's `rattle!(at, amp)`, amp * 2/sqrt(3) * (rand(3) - 0.5): at most amp in norm."""
+    if mode == "julip":
+        X = at.X + amp * (2.0 / np.sqrt(3.0)) * (rng.uniform(0.0, 1.0, size=at.X.shape) - 0.5)
+    else:
+        X = at.X + amp * rng.uniform(-1.0, 1.0, size=at.X.shape)
     cell = at.cell.copy()
     if strain > 0.0:
         e = rng.uniform(-strain, strain, size=(3, 3))
@@ -206,7 +211,7 @@ class StillingerWeber:
 
 def rattled_configs(species: str, L: int, nconfigs: int, *, rmax: Optional[float] = None,
                     strain: float = 0.02, seed: int = 1, calc=None, configtype: str = "rand",
-                    virial: bool = True, vacancies: int = 0, min_dist: float = 0.0) -> List[Dat]:
+                    virial: bool = True, vacancies: int = 0, min_dist: float = 0.0, mode: str = "box") -> List[Dat]:
     """`generate_data(species, L, rmax, N, calc)` of the reference tests, with the
     frozen recipe above.  `vacancies`: remove up to this many random atoms.
     `min_dist` (in units of r0): a rattled cell with a pair closer than this is drawn again (same
@@ -218,9 +223,9 @@ def rattled_configs(species: str, L: int, nconfigs: int, *, rmax: Optional[float
     base = repeat(bulk(species), L)
     out = []
     for _ in range(nconfigs):
-        at = rattle(base, rng.uniform() * rmax, rng, strain)
+        at = rattle(base, rng.uniform() * rmax, rng, strain, mode)
         while min_dist > 0.0 and _min_distance(at) < min_dist * r0:
-            at = rattle(base, rng.uniform() * rmax, rng, strain)
+            at = rattle(base, rng.uniform() * rmax, rng, strain, mode)
         ct = configtype
         if vacancies:
             nv = int(rng.integers(0, vacancies + 1))

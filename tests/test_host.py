@@ -60,6 +60,20 @@ def test_dat_roundtrip_and_equality():
     assert d2 != d
 
 
+def test_dat_reads_reference_style_rows():
+    """`_info.json` stores the explicit 1-based index vector per observation (`src/lsq_db.jl:244-246`); a dict in the
+    reference's layout (E: one row, F: nine consecutive rows) loads as blocks, and ours writes the same layout."""
+    at = synth.rattled_configs("Si", 1, 1, seed=3)[0].at
+    Dd = {"__id__": "IPFitting.Dat", "at": at.write_dict(), "configtype": "a",
+          "D": {"E": [1.0], "F": [0.0] * 9}, "rows": {"E": [1], "F": list(range(2, 11))}, "info": {}}
+    d = ipf.Dat.read_dict(Dd)
+    assert d.rows["E"] == (0, 1) and d.rows["F"] == (1, 9)
+    assert d.write_dict()["rows"] == {"E": [1], "F": list(range(2, 11))}
+    Dd["rows"]["F"] = [2, 3, 5]
+    with pytest.raises(ValueError):
+        ipf.Dat.read_dict(Dd)
+
+
 def test_row_assignment_follows_observation_order():
     """`_alloc_lsq_matrix` (`src/lsq_db.jl:237-250`) with arbitrary key order and missing observations."""
     at = synth.bulk("Si")
@@ -129,7 +143,8 @@ def test_db_files_roundtrip(tmp_path):
     db.flush()        # second save backs the old files up instead of overwriting (`_backupfile`)
     assert len(list(tmp_path.iterdir())) == 4
     info = json.load(open(str(tmp_path / "db_info.json")))
-    assert info["version"] == 2 and info["configs"][0]["rows"]["E"] == [1, 1]     # 1-based on disk
+    assert info["version"] == 2 and info["configs"][0]["rows"]["E"] == [1]        # 1-based index vectors on disk
+    assert info["configs"][0]["rows"]["F"] == list(range(2, 2 + 3 * len(cfgs[0])))
     # README-era argument order
     db3 = LsqDB("", cfgs, B, _assemble=False)
     assert db3.basis == db.basis
