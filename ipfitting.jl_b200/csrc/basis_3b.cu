@@ -489,7 +489,7 @@ int ipf_assemble_block_3b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         cudaEventDestroy(produced);
         Gather3Args G;
         G.p0 = A.p0; G.c0 = c0; G.s0 = A.s0; G.nb = nbs; G.S = (const double*)Sbuf[buf];
-        G.pstride = (int64_t)3 * nbs; G.gstride = 0;
+        G.pstride = (int64_t)3 * nbs; G.gstride = 0; G.cfg_aligned = 0;
         G.O = (const double*)Obuf[buf]; G.nslot = nslot; G.scol2col = s2c.p;
         G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
         G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;

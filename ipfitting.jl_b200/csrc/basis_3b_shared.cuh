@@ -142,6 +142,7 @@ struct Gather3Args {
     int nb;
     const double* S;          // [np][nb][3] (gstride = 0) or group-major [nb / 4][np][4][3] (gstride = 12 np)
     int64_t pstride, gstride; // doubles between consecutive pairs / between consecutive groups of 4 columns
+    int cfg_aligned;          // 1: the producer's 32-row blocks start at the first pair of every configuration
     const double* O;          // [nsites][nslot][nb][4]
     int nslot;
     const int16_t* scol2col;  // [nb] scratch column -> local basis column
@@ -185,7 +186,8 @@ __global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
             double f0 = 0.0, f1 = 0.0, f2 = 0.0;
             if (q1 > q0) {
                 // own sums: one slot per 32-row block of the producer that holds pairs of this atom
-                const int ns = (int)(((q1 - 1 - A.p0) >> 5) - ((q0 - A.p0) >> 5)) + 1;
+                const int64_t b0 = A.cfg_aligned ? A.site_off[a0] : A.p0;
+                const int ns = (int)(((q1 - 1 - b0) >> 5) - ((q0 - b0) >> 5)) + 1;
                 for (int sl = 0; sl < ns; ++sl) {
                     const double4 o = O4[((s - A.s0) * A.nslot + sl) * A.nb];
                     f0 += o.x; f1 += o.y; f2 += o.z; e += o.w;

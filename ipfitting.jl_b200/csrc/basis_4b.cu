@@ -80,6 +80,7 @@ struct Site4Args {
     const int64_t* pbeg;
     const int32_t* pcnt;
     const T4Ent* ent;
+    const int4* blk;                // row blocks of the batch: {first pair, first pair of its configuration, rows, -}
     int went[G4_NW + 1];            // entry range of every worker
     int wsc[G4_NW + 1];             // scratch-column range of every worker (multiples of Q_NG)
     int nb;                         // scratch columns (row length of S)
@@ -234,10 +235,13 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
     double* xp = sm + (size_t)G4_NROWS * 32;                 // [2][G4_D + 1][32]  x_j^e, then e x_j^(e-1)
     double* stage = xp + 2 * (size_t)(G4_D + 1) * 32;        // [G4_NW][Q_STAGE]
     const int lane = threadIdx.x & 31, worker = threadIdx.x >> 5;
-    const int64_t pl0 = (int64_t)blockIdx.x * 32;
+    // row blocks start at the first pair of every configuration (the last block of a configuration is short): the
+    // partial sums of a block never depend on how the configurations were batched or sharded over GPUs
+    const int4 bk = __ldg(A.blk + blockIdx.x);
+    const int64_t pl0 = (int64_t)bk.x - A.p0;
     const int64_t pl = pl0 + lane;
-    const bool live = pl < A.np;
-    const int nrw = (int)min((int64_t)32, A.np - pl0);
+    const int nrw = bk.z;
+    const bool live = lane < nrw;
     const int64_t p = A.p0 + (live ? pl : pl0);
     const int64_t k0 = A.pbeg[p];
     const int n = live ? A.pcnt[p] : 0;
@@ -245,7 +249,7 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
     const int site_prev = __shfl_up_sync(0xffffffffu, site, 1);
     const bool piece_start = live && (lane == 0 || site != site_prev);
     const unsigned pmask = __ballot_sync(0xffffffffu, piece_start);
-    const int pout = (int)(site - A.s0) * A.nslot + (int)((pl >> 5) - ((k0 - A.p0) >> 5));
+    const int pout = (int)(site - A.s0) * A.nslot + (int)(((int64_t)(bk.x - bk.y) >> 5) - ((k0 - bk.y) >> 5));
     const double* recp = A.rec + (int64_t)A.rs * p;
     const double4 o0v = ld4(recp);
     const double4 o1v = ld4(recp + 4);
@@ -544,6 +548,20 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         }
     }
     const int nslot = (nl.max_nbrs + 31) / 32 + 1;
+    // row blocks of the chunk, aligned to the configurations
+    std::vector<int4> h_blk;
+    std::vector<int64_t> cfg_blk(ch.ncfg + 1, 0);
+    for (int64_t c = 0; c < ch.ncfg; ++c) {
+        const int64_t q0 = nl.h_cfg_pair_off[c], q1 = nl.h_cfg_pair_off[c + 1];
+        cfg_blk[c] = (int64_t)h_blk.size();
+        for (int64_t q = q0; q < q1; q += 32) h_blk.push_back(make_int4((int)q, (int)q0, (int)std::min<int64_t>(32, q1 - q), 0));
+    }
+    cfg_blk[ch.ncfg] = (int64_t)h_blk.size();
+    if (nl.npairs > (int64_t)0x7fffffff) return ipf_set_error(ctx, IPF_EINVAL, "4-body path: more than 2^31 pairs in one chunk");
+    void* d_blk = nullptr;
+    IPF_CHECK(ipf_scratch(ctx, 10, sizeof(int4) * std::max<size_t>(1, h_blk.size()), &d_blk));
+    IPF_CUDA(ctx, cudaMemcpyAsync(d_blk, h_blk.data(), sizeof(int4) * h_blk.size(), cudaMemcpyHostToDevice, st));
+    IPF_CUDA(ctx, cudaStreamSynchronize(st));          // h_blk must outlive the copy
     const size_t o_bytes = (size_t)32 * nslot * nbs * (size_t)max_sites_batch;
     void* Sbuf[2] = {nullptr, nullptr};
     void* Obuf[2] = {nullptr, nullptr};
@@ -589,9 +607,11 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
             cudaEventDestroy(gathered[buf]);
             gathered[buf] = nullptr;
         }
-        if (A.np > 0) {
+        A.blk = (const int4*)d_blk + cfg_blk[c0];
+        const unsigned nblocks = (unsigned)(cfg_blk[c1] - cfg_blk[c0]);
+        if (nblocks > 0) {
             ProfScope prof_(ctx, "site_deriv_4b");
-            site4b_kernel<<<(unsigned)((A.np + 31) / 32), Q_THREADS, Q_SMEM, st>>>(A);
+            site4b_kernel<<<nblocks, Q_THREADS, Q_SMEM, st>>>(A);
             ctx->launches++;
             const cudaError_t le = cudaGetLastError();
             if (le != cudaSuccess) {
@@ -600,7 +620,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
                 cudaFuncGetAttributes(&fa, site4b_kernel);
                 return ipf_set_error(ctx, IPF_ECUDA, "%s:%d: site4b_kernel<<<%lld, %d, %zu>>>: %s (regs %d, static smem %zu, "
                                      "max dynamic smem %d, max threads %d, local %zu)", __FILE__, __LINE__,
-                                     (long long)((A.np + 31) / 32), Q_THREADS, Q_SMEM, cudaGetErrorString(le), fa.numRegs,
+                                     (long long)nblocks, Q_THREADS, Q_SMEM, cudaGetErrorString(le), fa.numRegs,
                                      fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes, fa.maxThreadsPerBlock, fa.localSizeBytes);
             }
         }
@@ -611,7 +631,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         cudaEventDestroy(produced);
         Gather3Args G;
         G.p0 = A.p0; G.c0 = c0; G.s0 = A.s0; G.nb = nbs; G.S = (const double*)Sbuf[buf];
-        G.pstride = 3 * Q_NG; G.gstride = (int64_t)3 * Q_NG * A.np;
+        G.pstride = 3 * Q_NG; G.gstride = (int64_t)3 * Q_NG * A.np; G.cfg_aligned = 1;
         G.O = (const double*)Obuf[buf]; G.nslot = nslot; G.scol2col = T->d_s2c;
         G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
         G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;

@@ -38,7 +38,7 @@ def main():
 
     r0 = ipf.rnn("Si")
     desc = ipf.BondAngleDesc(f"exp(- (r/{r0} - 1.0))", ipf.CosCut(2.0 * r0 - 1.0, 2.0 * r0))
-    basis = ipf.NBodyBasis(ipf.nbpolys(2, desc, 10) + ipf.nbpolys(3, desc, 6) + ipf.nbpolys(4, desc, 4))
+    basis = ipf.NBodyBasis(ipf.nbpolys(2, desc, 6) + ipf.nbpolys(3, desc, 4) + ipf.nbpolys(4, desc, 3))
     calc = synth.StillingerWeber()
     full = []
     for c in range(ncfg):
