@@ -228,8 +228,11 @@ int32_t ipf_solve_append_rows(ipf_ctx* ctx, ipf_solver* S, int64_t nextra, const
  * (src/lsq.jl:482-497), whose small dense work (SVD / pivoted QR of the n x n factor) stays on the host. */
 int32_t ipf_solve_qty(ipf_ctx* ctx, ipf_solver* S, double* qty);
 int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double* ssr, double* ssy);
+/* Diagnostics of a solve: Gram passes, orthogonality defect |A^T A - I|_F seen by the last pass, largest diagonal shift
+ * used, kappa_hat = (max / min diagonal of the equilibrated Cholesky factor)^2 of the last pass, and the number of
+ * refinement steps of the corrected semi-normal equations (0: the last pass was orthonormal to 0.1). */
 int32_t ipf_solve_info(const ipf_solver* S, int32_t* npasses, double* defect, double* shift,
-                       double* gram_ms, double* trsm_ms);
+                       double* kappa_hat, double* refine_steps);
 int32_t ipf_solve_destroy(ipf_ctx* ctx, ipf_solver* S);
 int32_t ipf_solve(ipf_ctx* ctx, const ipf_matrix* Psi, const double* Y, const double* W,
                   const int64_t* Irows, int64_t nIrows, const int64_t* Icols, int64_t nIcols,

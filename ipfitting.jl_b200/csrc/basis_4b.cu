@@ -275,8 +275,22 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
         }
         xp[(G4_D + 1) * 32 + lane] = 0.0;
     }
-    // ---- phase 1: moments of the 32 rows
-    g4_phase1(worker, A.rec4 + k0 * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
+    // ---- phase 1: moments of the 32 rows.  The neighbour records of the block's centre atoms (one contiguous run of
+    // pairs) are staged in the output staging area, which is idle until phase 2: every worker walks the same records.
+    {
+        const int64_t kb0 = __shfl_sync(0xffffffffu, k0, 0);
+        const int64_t kb1 = __shfl_sync(0xffffffffu, k0 + n, nrw - 1);
+        const int nd2 = (int)(kb1 - kb0) * (G4_RS / 2);             // double2 words of the run
+        if (nd2 <= G4_NW * Q_STAGE / 2) {
+            const double2* src = reinterpret_cast<const double2*>(A.rec4 + kb0 * G4_RS);
+            double2* dst = reinterpret_cast<double2*>(stage);
+            for (int q = threadIdx.x; q < nd2; q += Q_THREADS) dst[q] = __ldg(src + q);
+            __syncthreads();
+            g4_phase1<true>(worker, stage + (k0 - kb0) * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
+        } else {
+            g4_phase1<false>(worker, A.rec4 + k0 * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
+        }
+    }
     __syncthreads();
 
     // ---- phase 2: basis functions of this worker, entry by entry; 4 scratch columns per staged group

@@ -333,7 +333,7 @@ class _Solver:
         npass, defect, shift, gms, tms = C.c_int32(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
         self.ctx.lib.ipf_solve_info(self.h, C.byref(npass), C.byref(defect), C.byref(shift), C.byref(gms), C.byref(tms))
         return {"passes": npass.value, "orth_defect": defect.value, "shift": shift.value,
-                "gram_ms": gms.value, "trsm_ms": tms.value}
+                "kappa_hat": gms.value, "csne_steps": int(tms.value)}
 
     def close(self):
         if self.h:

@@ -108,7 +108,9 @@ def test_ill_conditioned_system_needs_reorthogonalisation(ctx):
     Q, Rr = sla.qr(A, mode="economic")
     c_ref = sla.solve_triangular(Rr, Q.T @ y)
     kappa = np.linalg.cond(Rr)
-    assert info["passes"] >= 3
+    # the first Gram matrix is numerically singular: at least one re-orthogonalisation pass, then either a third Gram
+    # pass or the corrected semi-normal equations on the second
+    assert info["passes"] >= 3 or (info["passes"] == 2 and info["csne_steps"] >= 1)
     # both are backward stable: compare residuals and the well-determined part of c
     r, r_ref = np.linalg.norm(A @ c - y), np.linalg.norm(A @ c_ref - y)
     assert abs(r - r_ref) <= 1e-8 * r_ref
