@@ -140,8 +140,8 @@ struct Gather3Args {
     int64_t c0;               // first config (chunk-local) of the batch
     int64_t s0;               // first site of the batch
     int nb;
-    const double* S;          // [np][nb][3] (gstride = 0) or group-major [nb / 4][np][4][3] (gstride = 12 np)
-    int64_t pstride, gstride; // doubles between consecutive pairs / between consecutive groups of 4 columns
+    const double* S;          // [np][nb][3] (gstride = 0) or group-major [nb / 8][np][8][3] (gstride = 24 np)
+    int64_t pstride, gstride; // doubles between consecutive pairs / between consecutive groups of 8 columns
     int cfg_aligned;          // 1: the producer's 32-row blocks start at the first pair of every configuration
     const double* O;          // [nsites][nslot][nb][4]
     int nslot;
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(G_THREADS) gather3b_kernel(Gather3Args A) {
     const int64_t a0 = A.atom_off[c];
     const int nat = (int)(A.atom_off[c + 1] - a0);
     const int64_t rE = A.rowE[c], rF = A.rowF[c], rV = A.rowV[c];
-    const double* S3 = A.gstride ? A.S + (int64_t)(scl >> 2) * A.gstride + 3 * (scl & 3) : A.S + 3 * scl;
+    const double* S3 = A.gstride ? A.S + (int64_t)(scl >> 3) * A.gstride + 3 * (scl & 7) : A.S + 3 * scl;
     const double4* O4 = reinterpret_cast<const double4*>(A.O) + scl;
     double e = 0.0, v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0, v4 = 0.0, v5 = 0.0;
     for (int ab = 0; ab < nat; ab += G_ACH) {

@@ -104,8 +104,10 @@ __global__ void __launch_bounds__(128) rec4_kernel(int64_t npairs, const double*
     for (int e = 4 + G4_D + 1; e < G4_RS; ++e) o[e] = 0.0;
 }
 
-// write-out of the Q_NG staged functions of the warp's 32 rows.  S is group-major, S[column group][pair][4][3]: the
-// 32 rows of a group are 3 KB of consecutive bytes (5 rows x 6 double2 per warp instruction).  The per-centre-atom
+// write-out of the Q_NG staged functions of the warp's 32 rows.  S is group-major, S[group of 8 columns][pair][8][3]:
+// a flush writes one 96-byte half of 32 consecutive 192-byte records (5 rows x 6 double2 per warp instruction; the
+// other half follows with the worker's next flush and merges in L2), and the gather reads whole 192-byte records
+// (three full 64-byte DRAM bursts; 96-byte records cost it twice the algorithmic DRAM traffic).  The per-centre-atom
 // column sums go to O[site][slot][scol][4] (the protocol gather3b_kernel reads): lane = (column 0..15, half), the two
 // halves of the warp sum the even and the odd rows of a piece.
 __device__ __forceinline__ void q_flush(const Site4Args& A, const double* __restrict__ wstage, int64_t plw, int nrw,
@@ -113,14 +115,14 @@ __device__ __forceinline__ void q_flush(const Site4Args& A, const double* __rest
     __syncwarp();
     const int lane = threadIdx.x & 31;
     {
-        double2* Sg = reinterpret_cast<double2*>(A.S + ((int64_t)(sc0 >> 2) * A.np + plw) * (3 * Q_NG));
+        double2* Sg = reinterpret_cast<double2*>(A.S + ((int64_t)(sc0 >> 3) * A.np + plw) * (6 * Q_NG) + (sc0 & 4) * 3);
         const double2* st2 = reinterpret_cast<const double2*>(wstage);
         const int rl = lane / 6, cl = lane - 6 * rl;        // lanes 30, 31 idle
         if (lane < 30) {
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
                 const int row = 5 * i + rl;
-                if (row < nrw) Sg[row * 6 + cl] = st2[row * (Q_GLD / 2) + cl];
+                if (row < nrw) Sg[row * 12 + cl] = st2[row * (Q_GLD / 2) + cl];
             }
         }
     }
@@ -487,6 +489,7 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
     }
     T.wsc[G4_NW] = sc;
     T.went[G4_NW] = (int)T.ent.size();
+    while (sc % 8) { T.s2c.push_back(-1); ++sc; }      // whole groups of 8 scratch columns (never written, never gathered)
     T.nbs = sc;
     return true;
 }
@@ -645,7 +648,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         cudaEventDestroy(produced);
         Gather3Args G;
         G.p0 = A.p0; G.c0 = c0; G.s0 = A.s0; G.nb = nbs; G.S = (const double*)Sbuf[buf];
-        G.pstride = 3 * Q_NG; G.gstride = (int64_t)3 * Q_NG * A.np; G.cfg_aligned = 1;
+        G.pstride = 6 * Q_NG; G.gstride = (int64_t)6 * Q_NG * A.np; G.cfg_aligned = 1;
         G.O = (const double*)Obuf[buf]; G.nslot = nslot; G.scol2col = T->d_s2c;
         G.atom_off = ch.atom_off.p; G.site_off = nl.site_off.p; G.prev = nl.prev.p;
         G.pR = nl.pR.p; G.rowE = ch.rowE.p; G.rowF = ch.rowF.p; G.rowV = ch.rowV.p;

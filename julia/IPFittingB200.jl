@@ -39,11 +39,84 @@ const CTX = Ref{Union{Nothing, Ctx}}(nothing)
 context() = (CTX[] === nothing && (CTX[] = Ctx(parse(Int, get(ENV, "LOCAL_RANK", "0")))); CTX[])
 
 """
-`blockspecs(basis)`: the (N, descriptor, monomial table) runs of an NBodyIPs-style basis.
-A basis element must expose `bodyorder`, its descriptor (transform id, a, r0, rc1, rc2) and the
-exponent tuples of its monomial orbit -- the tables `ipfitting.jl_b200/basis.py` emits.
+`basisdict(basis)`: the serialised form of a bond-angle polynomial basis,
+
+    Dict("__id__" => "IPFittingB200.NBodyBasis",
+         "descs"  => [Dict("kind" => 0|1, "a" => a, "r0" => r0, "rc1" => rc1, "rc2" => rc2), ...],
+         "polys"  => [Dict("N" => N, "desc" => index into descs (0-based), "orbit" => [[e_1, ..., e_nv], ...]), ...])
+
+one entry of "polys" per basis function (column of Ψ), "orbit" = the exponent tuples of its S_{N-1} orbit over the
+variables (x_1..x_{N-1}, w_12, w_13, .., w_23, ..); kind 0: x = exp(-a (r/r0 - 1)), 1: x = (r0/r)^a; cutoff
+CosCut(rc1, rc2).  It is what `NBodyBasis.write_dict` of ipfitting.jl_b200/basis.py emits and what the `basis` entry of
+the `_info.json` written by either side holds.  For an NBodyIPs basis the method below reads the same information from
+the basis elements: `bodyorder(b)`, the descriptor (`b.D.transform`, `b.D.cutoff`) and the exponent tuples of the
+invariant polynomial (`b.t`, NBodyIPs `NBPoly`); a basis that is already such a Dict passes through.
 """
-function blockspecs end
+basisdict(basis::AbstractDict) = basis
+function basisdict(basis::AbstractVector)
+   descs = Any[]; polys = Any[]
+   for b in basis
+      D = b.D                                                # BondAngleDesc(transform, cutoff)
+      d = Dict("kind" => transform_kind(D.transform), "a" => transform_a(D.transform), "r0" => transform_r0(D.transform),
+               "rc1" => D.cutoff.rc1, "rc2" => D.cutoff.rc2)
+      i = findfirst(isequal(d), descs)
+      i === nothing && (push!(descs, d); i = length(descs))
+      push!(polys, Dict("N" => bodyorder(b), "desc" => i - 1, "orbit" => [collect(Int, t) for t in orbit_exponents(b)]))
+   end
+   return Dict("__id__" => "IPFittingB200.NBodyBasis", "descs" => descs, "polys" => polys)
+end
+# The three accessors a maintainer maps onto NBodyIPs' SpaceTransform (the README's "exp(- (r/r0 - 1.0))" is kind 0,
+# a = 1; "(r0/r)^p" is kind 1, a = p) and the expansion of an NBPoly's invariant tuples into monomial exponents.
+function transform_kind end; function transform_a end; function transform_r0 end; function orbit_exponents end
+
+"""
+`blockspecs(basis) -> (specs::Vector{BlockSpec}, keep)`: consecutive basis functions with the same body-order and
+descriptor form one `ipf_block_spec` (the C side evaluates a block per kernel pass); `keep` holds the arrays the
+specs point into and must be GC-preserved across `ipf_basis_create`.  Same grouping as `NBodyBasis.__init__` /
+`_compile` of ipfitting.jl_b200/basis.py.
+"""
+function blockspecs(basis)
+   Bd = basisdict(basis)
+   descs, polys = Bd["descs"], Bd["polys"]
+   specs = BlockSpec[]; keep = Any[]
+   start = 1
+   while start <= length(polys)
+      p0 = polys[start]
+      stop = start
+      while stop < length(polys) && polys[stop + 1]["N"] == p0["N"] && polys[stop + 1]["desc"] == p0["desc"]
+         stop += 1
+      end
+      nv = (p0["N"] - 1) + (p0["N"] - 1) * (p0["N"] - 2) ÷ 2
+      mono_b = Int32[]; mono_exp = UInt8[]
+      for k in start:stop, m in polys[k]["orbit"]
+         length(m) == nv || error("monomial has the wrong number of variables")
+         push!(mono_b, Int32(k - start))                        # local basis index, non-decreasing
+         append!(mono_exp, UInt8.(m)); append!(mono_exp, zeros(UInt8, MAX_VARS - nv))   # row-major [nmono, MAX_VARS]
+      end
+      d = descs[p0["desc"] + 1]
+      push!(keep, mono_b); push!(keep, mono_exp)
+      push!(specs, BlockSpec(Int32(p0["N"]), Int32(stop - start + 1), Int32(length(mono_b)), Int32(d["kind"]),
+                             Float64(d["a"]), Float64(d["r0"]), Float64(d["rc1"]), Float64(d["rc2"]),
+                             pointer(mono_b), pointer(mono_exp)))
+      start = stop + 1
+   end
+   return specs, keep
+end
+
+# ---------------------------------------------------------------- multi-GPU: one Julia process per GPU
+"""
+`attach_communicator(ctx, rank, nranks, bcast)`: creates the library's NCCL communicator over `nranks` processes (one
+GPU each).  `bcast(bytes, root)` is any byte broadcast of the host program (`MPI.Bcast!`, a shared file, ...): it only
+carries the 128-byte NCCL unique id of rank 0.  Afterwards `ipf_solve*` on this ctx sums the Gram blocks (and the
+residual sums) over all ranks on the ctx stream: every rank assembles the rows of its own configurations and calls
+`solve_qr` with them; all ranks receive the same coefficients.  No torch, no MPI inside the library.
+"""
+function attach_communicator(ctx::Ctx, rank::Integer, nranks::Integer, bcast)
+   uid = zeros(UInt8, 128)
+   rank == 0 && check(ctx, ccall((:ipf_comm_unique_id, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), ctx.h, uid))
+   bcast(uid, 0)
+   check(ctx, ccall((:ipf_comm_init, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}), ctx.h, nranks, rank, uid))
+end
 
 # ---------------------------------------------------------------- (1) assembly
 function IPFitting.DB.LsqDB(dbpath::AbstractString, basis, configs::AbstractVector{Dat};
