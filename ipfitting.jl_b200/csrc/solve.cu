@@ -223,6 +223,100 @@ __global__ void __launch_bounds__(256) chol_lower_kernel(double* __restrict__ L,
     chol_lower_body(L, n, flag, pcap > 0 ? chol_panel : nullptr, pcap);
 }
 
+
+// ---- multi-CTA Cholesky for n > 256: the same blocked algorithm, one launch per phase of a block column -----------
+// (diagonal block by one warp -> D; panel rows, one thread per row; trailing update, one warp per column over the
+// whole GPU).  The single-CTA kernel takes 5.6 ms at n = 805 (latency bound) and, in a multi-GPU solve, is the part
+// that every rank repeats: it does not shrink with the number of GPUs.
+__global__ void __launch_bounds__(32) chol_diag_kernel(double* __restrict__ L, int n, int J0, double* __restrict__ D,
+                                                       int* __restrict__ flag) {
+    __shared__ double sD[KB][KB + 1];
+    if (flag[1]) return;
+    const int lane = threadIdx.x;
+    const int nbk = min(KB, n - J0);
+    for (int e = lane; e < KB * KB; e += 32) {
+        const int i = e % KB, j = e / KB;
+        sD[i][j] = (i < nbk && j < nbk && i >= j) ? L[(size_t)(J0 + j) * n + J0 + i] : (i == j ? 1.0 : 0.0);
+    }
+    __syncwarp();
+    double rdiag = 1.0;
+    for (int j = 0; j < nbk; ++j) {
+        double sv = 0.0;
+        if (lane >= j && lane < nbk) {
+            sv = sD[lane][j];
+            for (int k = 0; k < j; ++k) sv = fma(-sD[lane][k], sD[j][k], sv);
+        }
+        const double d = __shfl_sync(0xffffffffu, sv, j);
+        if (!(d > 0.0) || !isfinite(d)) {
+            if (lane == 0) { flag[1] = 1; flag[2] = J0 + j; }
+            return;
+        }
+        const double ljj = sqrt(d);
+        if (lane == j) { sD[j][j] = ljj; rdiag = 1.0 / ljj; }
+        else if (lane > j && lane < nbk) sD[lane][j] = sv / ljj;
+        __syncwarp();
+    }
+    // D: the factored block, [k][m] row-major with stride KB (identity beyond nbk), then the reciprocal diagonal
+    for (int e = lane; e < KB * KB; e += 32) D[e] = sD[e / KB][e % KB];
+    D[KB * KB + lane] = rdiag;
+    for (int e = lane; e < nbk * nbk; e += 32) {
+        const int i = e % nbk, j = e / nbk;
+        if (i >= j) L[(size_t)(J0 + j) * n + J0 + i] = sD[i][j];
+    }
+}
+
+__global__ void __launch_bounds__(128) chol_panel_kernel(double* __restrict__ L, int n, int J0, const double* __restrict__ D,
+                                                         const int* __restrict__ flag) {
+    __shared__ double sD[KB * KB + KB];
+    if (flag[1]) return;
+    for (int e = threadIdx.x; e < KB * KB + KB; e += blockDim.x) sD[e] = D[e];
+    __syncthreads();
+    const int nbk = min(KB, n - J0);
+    const int r = J0 + nbk + blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double x[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) x[k] = (k < nbk) ? L[(size_t)(J0 + k) * n + r] : 0.0;
+#pragma unroll
+    for (int k = 0; k < KB; ++k) {
+        double v = x[k];
+#pragma unroll
+        for (int m = 0; m < k; ++m) v -= x[m] * sD[k * KB + m];
+        x[k] = v * sD[KB * KB + k];
+    }
+#pragma unroll
+    for (int k = 0; k < KB; ++k) if (k < nbk) L[(size_t)(J0 + k) * n + r] = x[k];
+}
+
+// L[r][c] -= sum_k L[r][J0+k] L[c][J0+k] for the columns c >= r0 = J0 + nbk, rows r >= c: one warp per column
+__global__ void __launch_bounds__(256) chol_trail_kernel(double* __restrict__ L, int n, int J0, const int* __restrict__ flag) {
+    if (flag[1]) return;
+    const int lane = threadIdx.x & 31;
+    const int nbk = min(KB, n - J0);
+    const int r0 = J0 + nbk;
+    const int c = r0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (c >= n) return;
+    double lc[KB];
+#pragma unroll
+    for (int k = 0; k < KB; ++k) lc[k] = (k < nbk) ? L[(size_t)(J0 + k) * n + c] : 0.0;
+    double* col = L + (size_t)c * n;
+    for (int r = c + lane; r < n; r += 32) {
+        double a0 = col[r], a1 = 0.0;
+#pragma unroll
+        for (int k = 0; k < KB; k += 2) {
+            a0 = fma(-L[(size_t)(J0 + min(k, nbk - 1)) * n + r], lc[k], a0);
+            a1 = fma(-L[(size_t)(J0 + min(k + 1, nbk - 1)) * n + r], lc[k + 1], a1);
+        }
+        col[r] = a0 + a1;
+    }
+}
+
+__global__ void zero_upper_kernel(double* __restrict__ L, int n) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)n * n) return;
+    if ((int)(e % n) < (int)(e / n)) L[e] = 0.0;
+}
+
 // ---- K8: force preconditioner (src/lsq.jl:184-234): batched per-configuration blocks --------------
 // one CTA per block: in-place lower Cholesky of P_b (flag[1] / flag[2] report the first failure)
 __global__ void __launch_bounds__(256) chol_batched_kernel(double* __restrict__ P, const int64_t* __restrict__ off,
@@ -780,7 +874,7 @@ int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* d
         take(sizeof(double) * nn, (void**)&S->Rtmp);
         take(sizeof(double) * S->n1, (void**)&S->vec);
         take(sizeof(double) * S->n1, (void**)&S->dscale);
-        take(sizeof(double) * 4 * S->n1, (void**)&S->work);
+        take(sizeof(double) * (4 * (size_t)S->n1 + KB * KB + KB), (void**)&S->work);
         take(sizeof(double) * nn, (void**)&S->Lt);
         take(sizeof(int) * 4, (void**)&S->flag);
         take(sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8), (void**)&S->red);
@@ -795,7 +889,7 @@ int32_t ipf_solve_begin_dev(ipf_ctx* ctx, const ipf_matrix* Psi, const double* d
             (e = cudaMalloc((void**)&S->Rtmp, sizeof(double) * nn)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->vec, sizeof(double) * S->n1)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->dscale, sizeof(double) * S->n1)) != cudaSuccess ||
-            (e = cudaMalloc((void**)&S->work, sizeof(double) * 4 * S->n1)) != cudaSuccess ||
+            (e = cudaMalloc((void**)&S->work, sizeof(double) * (4 * (size_t)S->n1 + KB * KB + KB))) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->Lt, sizeof(double) * nn)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->flag, sizeof(int) * 4)) != cudaSuccess ||
             (e = cudaMalloc((void**)&S->red, sizeof(double) * (2 * (size_t)(S->Mpad / 256 + 2) + 8))) != cudaSuccess ||
@@ -968,7 +1062,24 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         copy_shift_kernel<<<nblk, 256, 0, st>>>(S->G, n1, S->L, n, S->dscale, shift);
         IPF_CUDA(ctx, cudaMemsetAsync(S->flag, 0, sizeof(int) * 4, st));
         { ProfScope prof_(ctx, "cholesky");
-          chol_lower_kernel<<<1, 256, pbytes, st>>>(S->L, n, S->flag, pcap); }
+          static const bool chol_single = getenv("IPF_CHOL_SINGLE") != nullptr;
+          if (n <= 256 || chol_single) {
+              chol_lower_kernel<<<1, 256, pbytes, st>>>(S->L, n, S->flag, pcap);
+          } else {
+              double* Dblk = S->work + 4 * (size_t)S->n1;          // KB * KB + KB doubles behind the small vectors
+              for (int J0 = 0; J0 < n; J0 += KB) {
+                  const int rows = n - std::min(n, J0 + KB);
+                  chol_diag_kernel<<<1, 32, 0, st>>>(S->L, n, J0, Dblk, S->flag);
+                  if (rows > 0) {
+                      chol_panel_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(S->L, n, J0, Dblk, S->flag);
+                      chol_trail_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(S->L, n, J0, S->flag);
+                      ctx->launches += 2;
+                  }
+                  ctx->launches++;
+              }
+              zero_upper_kernel<<<nblk, 256, 0, st>>>(S->L, n);
+          }
+        }
         diag_minmax_kernel<<<1, 256, 0, st>>>(S->L, n, S->red + 2);
         ctx->launches += 3;
         int hf[4];
