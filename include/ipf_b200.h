@@ -67,7 +67,12 @@ typedef struct ipf_configs ipf_configs;
  * (x_1..x_{N-1}, w_12, w_13, .., w_23, ..); a basis function is the sum of its
  * monomials (an S_{N-1} orbit).  transform 0: x = exp(-a (r/r0 - 1)); 1: x = (r0/r)^a.
  * cutoff: CosCut(rc1, rc2).  Replaces the NBodyIPs objects built by
- * nbpolys(N, BondAngleDesc(transform, CosCut(rc1, rc2)), deg)   README.md:34-47. */
+ * nbpolys(N, BondAngleDesc(transform, CosCut(rc1, rc2)), deg)   README.md:34-47.
+ * Species (JuLIP Atoms.Z, src/prototypes.jl:19-25): zc > 0 makes the run species-resolved: it acts on the clusters
+ * whose centre atom has atomic number zc and whose N-1 neighbours have exactly the atomic numbers zs[0] <= .. <= zs[N-2]
+ * (legs assigned to the variable slots in that order; the monomial sums need only be invariant under exchanges of
+ * equal-species slots) and is zero on every other cluster.  zc = 0: species-agnostic, every cluster (zs ignored).
+ * Species-resolved runs are evaluated by the table-driven kernel. */
 typedef struct {
     int32_t N;
     int32_t nb;
@@ -76,6 +81,8 @@ typedef struct {
     double a, r0, rc1, rc2;
     const int32_t* mono_b;
     const uint8_t* mono_exp;
+    int32_t zc;
+    int32_t zs[4];
 } ipf_block_spec;
 
 /* ---- context ---------------------------------------------------------- */
@@ -150,7 +157,7 @@ int32_t ipf_neighbours(ipf_ctx* ctx, int32_t nat, const double* pos, const doubl
  * vec_obs(okey, eval_obs(okey, basis, cfg))  (src/lsq_db.jl:268-278).
  *   atom_off[ncfg+1]  prefix offsets into pos/Z
  *   pos[3*natoms]     atom-major xyz;  cell[9*ncfg] row-major, rows = lattice vectors
- *   pbc[3*ncfg];  Z[natoms] (atomic numbers; currently informational)
+ *   pbc[3*ncfg];  Z[natoms] (atomic numbers; read by species-resolved blocks, may be NULL otherwise)
  *   rowE/rowF/rowV[ncfg]: 1-based first row of the E / F / V block of each config,
  *       0 = observation absent (rows come from _alloc_lsq_matrix, src/lsq_db.jl:237-250,
  *       so any Dict key order is honoured).  Block lengths are 1 / 3*nat / 6.

@@ -30,7 +30,8 @@ class IPFError(RuntimeError):
 class BlockSpec(C.Structure):
     _fields_ = [("N", C.c_int32), ("nb", C.c_int32), ("nmono", C.c_int32), ("transform", C.c_int32),
                 ("a", C.c_double), ("r0", C.c_double), ("rc1", C.c_double), ("rc2", C.c_double),
-                ("mono_b", C.POINTER(C.c_int32)), ("mono_exp", C.POINTER(C.c_uint8))]
+                ("mono_b", C.POINTER(C.c_int32)), ("mono_exp", C.POINTER(C.c_uint8)),
+                ("zc", C.c_int32), ("zs", C.c_int32 * 4)]
 
 
 _lib = None
@@ -225,7 +226,9 @@ class DeviceBasis:
             mb = np.ascontiguousarray(b.mono_b, dtype=np.int32)
             me = np.ascontiguousarray(b.mono_exp, dtype=np.uint8)
             keep += [mb, me]
-            arr[k] = BlockSpec(b.N, b.nb, len(mb), kind, a, r0, rc1, rc2, ptr(mb, C.c_int32), ptr(me, C.c_uint8))
+            zs = (C.c_int32 * 4)(*([int(z) for z in getattr(b, "zs", ())] + [0] * 4)[:4])
+            arr[k] = BlockSpec(b.N, b.nb, len(mb), kind, a, r0, rc1, rc2, ptr(mb, C.c_int32), ptr(me, C.c_uint8),
+                               int(getattr(b, "zc", 0)), zs)
         h = _vp()
         ctx.check(ctx.lib.ipf_basis_create(ctx.h, len(blocks), arr, C.byref(h)))
         self.h = h

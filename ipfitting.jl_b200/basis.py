@@ -122,10 +122,12 @@ def _pairs(nx: int):
 
 
 @lru_cache(maxsize=None)
-def invariant_orbits(N: int, deg: int) -> Tuple[Tuple[Tuple[int, ...], ...], ...]:
+def invariant_orbits(N: int, deg: int, groups: Tuple[int, ...] = None) -> Tuple[Tuple[Tuple[int, ...], ...], ...]:
     """All S_{N-1}-orbits of monomials of total degree 1..deg in the nvars(N)
     bond-angle variables.  Returns a tuple of orbits, each a sorted tuple of
-    exponent tuples; orbits are sorted by (degree, smallest member)."""
+    exponent tuples; orbits are sorted by (degree, smallest member).
+    `groups` (one label per neighbour slot, e.g. the sorted species of the neighbours): only the permutations
+    that keep every label in place act, i.e. the polynomial is invariant under exchanging legs of the SAME species."""
     if not (2 <= N <= MAX_BODYORDER):
         raise ValueError("body-order must be 2..5")
     if not (1 <= deg <= MAX_DEGREE):
@@ -135,6 +137,10 @@ def invariant_orbits(N: int, deg: int) -> Tuple[Tuple[Tuple[int, ...], ...], ...
     pidx = {p: k for k, p in enumerate(pairs)}
     nv = nx + len(pairs)
     perms = list(itertools.permutations(range(nx)))
+    if groups is not None:
+        if len(groups) != nx:
+            raise ValueError("one group label per neighbour slot")
+        perms = [p for p in perms if all(groups[p[i]] == groups[i] for i in range(nx))]
     # for each permutation, the induced permutation of the variable slots
     slot_maps = []
     for p in perms:
@@ -170,6 +176,11 @@ class NBPoly:
     N: int
     desc: BondAngleDesc
     orbit: Tuple[Tuple[int, ...], ...]
+    # species-resolved function: centre species zc and the SORTED species of the N-1 neighbours; the function acts on
+    # the clusters with exactly these species (legs assigned to the slots in species order) and is zero elsewhere.
+    # zc = 0: species-agnostic (every cluster, full S_{N-1} symmetry).
+    zc: int = 0
+    zs: Tuple[int, ...] = ()
 
     @property
     def degree(self) -> int:
@@ -184,9 +195,27 @@ def degree(b: NBPoly) -> int:
     return b.degree
 
 
-def nbpolys(N: int, desc: BondAngleDesc, deg: int) -> List[NBPoly]:
-    """`nbpolys(bodyorder, descriptor, degree)` (`README.md:38-42`)."""
-    return [NBPoly(N, desc, orb) for orb in invariant_orbits(N, deg)]
+def nbpolys(N: int, desc: BondAngleDesc, deg: int, species=None) -> List[NBPoly]:
+    """`nbpolys(bodyorder, descriptor, degree)` (`README.md:38-42`).
+    `species = (zc, (z_1, .., z_{N-1}))`: the functions of ONE species tuple (centre, neighbours); the polynomials are
+    invariant under permutations of equal-species neighbours only.  `species_nbpolys` builds all tuples."""
+    if species is None:
+        return [NBPoly(N, desc, orb) for orb in invariant_orbits(N, deg)]
+    zc, zs = int(species[0]), tuple(sorted(int(z) for z in species[1]))
+    if zc <= 0 or len(zs) != N - 1 or min(zs) <= 0:
+        raise ValueError("species = (zc, (z_1, .., z_{N-1})) with positive atomic numbers")
+    return [NBPoly(N, desc, orb, zc, zs) for orb in invariant_orbits(N, deg, zs)]
+
+
+def species_nbpolys(N: int, desc: BondAngleDesc, deg: int, zlist: Sequence[int]) -> List[NBPoly]:
+    """The species-resolved N-body basis of a multi-component system (JuLIP `Atoms.Z`, `src/prototypes.jl:19-25`): one
+    run of functions per (centre species, multiset of neighbour species), centre-major, multisets in lexicographic order."""
+    out: List[NBPoly] = []
+    zl = sorted(int(z) for z in zlist)
+    for zc in zl:
+        for zs in itertools.combinations_with_replacement(zl, N - 1):
+            out += nbpolys(N, desc, deg, (zc, zs))
+    return out
 
 
 @dataclass
@@ -200,6 +229,8 @@ class BasisBlock:
     mono_b: np.ndarray         # int32[nmono]   local basis index of each monomial
     mono_exp: np.ndarray       # uint8[nmono, MAX_VARS] exponents (zero padded)
     maxdeg: int
+    zc: int = 0                # centre species (0 = any)
+    zs: Tuple[int, ...] = ()   # sorted neighbour species (empty = any)
 
 
 class NBodyBasis:
@@ -218,7 +249,8 @@ class NBodyBasis:
             p0 = self.polys[start]
             end = start
             while (end < len(self.polys) and self.polys[end].N == p0.N
-                   and self.polys[end].desc == p0.desc):
+                   and self.polys[end].desc == p0.desc and self.polys[end].zc == p0.zc
+                   and self.polys[end].zs == p0.zs):
                 end += 1
             self.blocks.append(self._compile(start, end))
             start = end
@@ -239,7 +271,7 @@ class NBodyBasis:
         return BasisBlock(N=p0.N, desc=p0.desc, col0=start, nb=end - start,
                           mono_b=np.asarray(mb, dtype=np.int32),
                           mono_exp=np.asarray(me, dtype=np.uint8).reshape(-1, MAX_VARS),
-                          maxdeg=maxdeg)
+                          maxdeg=maxdeg, zc=p0.zc, zs=tuple(p0.zs))
 
     def __len__(self) -> int:
         return len(self.polys)
@@ -267,15 +299,19 @@ class NBodyBasis:
                 index[p.desc] = len(descs)
                 descs.append({"kind": p.desc.kind, "a": p.desc.a, "r0": p.desc.r0,
                               "rc1": p.desc.cutoff.rc1, "rc2": p.desc.cutoff.rc2})
-            polys.append({"N": p.N, "desc": index[p.desc],
-                          "orbit": [list(m) for m in p.orbit]})
+            e = {"N": p.N, "desc": index[p.desc], "orbit": [list(m) for m in p.orbit]}
+            if p.zc:
+                e["zc"] = p.zc
+                e["zs"] = list(p.zs)
+            polys.append(e)
         return {"__id__": "IPFittingB200.NBodyBasis", "descs": descs, "polys": polys}
 
     @staticmethod
     def read_dict(D: dict) -> "NBodyBasis":
         descs = [BondAngleDesc((d["kind"], d["a"], d["r0"]), CosCut(d["rc1"], d["rc2"]))
                  for d in D["descs"]]
-        polys = [NBPoly(p["N"], descs[p["desc"]], tuple(tuple(m) for m in p["orbit"]))
+        polys = [NBPoly(p["N"], descs[p["desc"]], tuple(tuple(m) for m in p["orbit"]), int(p.get("zc", 0)),
+                        tuple(int(z) for z in p.get("zs", ())))
                  for p in D["polys"]]
         return NBodyBasis(polys)
 

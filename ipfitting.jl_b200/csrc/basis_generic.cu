@@ -88,6 +88,12 @@ struct GenArgs {
     int64_t ld, col0;
     double* scratch;       // [gridDim][unit][maxpairs][4]
     int* counter;
+    // species-resolved block (zc > 0): atomic numbers of the chunk's atoms, neighbour atom of every pair, the sorted
+    // neighbour species and the exponent tables with the own-leg slot moved to position 0 (capi.cu)
+    const int32_t* Z;
+    const int32_t* pj;
+    int zc, zs[4];
+    const uint8_t* mono_exp_var[4];
 };
 
 constexpr int GEN_THREADS = 256;
@@ -202,17 +208,37 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
             for (int k = 0; k < REC; ++k) own[k] = A.rec[(int64_t)A.rs * p + k];
             const int64_t s = a0 + A.pi[p];
             const int64_t o0 = A.site_off[s], o1 = A.site_off[s + 1];
+            // species rule: the own leg takes the first slot of its species, the other legs (sorted by species) must
+            // match the remaining slots; the exponent table is the one with that slot moved to position 0
+            bool active = true;
+            const uint8_t* etab = s_exp;
+            int rem[3] = {0, 0, 0};
+            if (A.zc > 0) {
+                const int zj = A.Z[a0 + A.pj[p]];
+                int s0 = -1;
+#pragma unroll
+                for (int t = 0; t < NX; ++t) if (s0 < 0 && A.zs[t] == zj) s0 = t;
+                active = A.Z[s] == A.zc && s0 >= 0;
+                if (active) {
+                    etab = A.mono_exp_var[s0] + (size_t)mbase * IPF_MAX_VARS;
+                    int k = 0;
+#pragma unroll
+                    for (int t = 0; t < NX; ++t) if (t != s0) { if (k < 3) rem[k] = A.zs[t]; ++k; }
+                }
+            }
             for (int bl = 0; bl < nbu; ++bl) {
                 const int m0 = s_mstart[bl], m1 = s_mstart[bl + 1];
                 double S0 = 0.0, S1 = 0.0, T[3] = {0.0, 0.0, 0.0};
                 int64_t oth[3] = {0, 0, 0};
-                if (NX == 1) {
-                    cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                if (!active) {
+                } else if (NX == 1) {
+                    cluster_accumulate<NX>(A, p, oth, own, etab, m0, m1, S0, S1, T);
                 } else if (NX == 2) {
                     for (int64_t k = o0; k < o1; ++k) {
                         if (k == p) continue;
+                        if (A.zc > 0 && A.Z[a0 + A.pj[k]] != rem[0]) continue;
                         oth[0] = k;
-                        cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                        cluster_accumulate<NX>(A, p, oth, own, etab, m0, m1, S0, S1, T);
                     }
                 } else if (NX == 3) {
                     for (int64_t k = o0; k < o1; ++k) {
@@ -220,7 +246,12 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
                         for (int64_t l = k + 1; l < o1; ++l) {
                             if (l == p) continue;
                             oth[0] = k; oth[1] = l;
-                            cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                            if (A.zc > 0) {
+                                const int zk = A.Z[a0 + A.pj[k]], zl = A.Z[a0 + A.pj[l]];
+                                if (zk > zl) { oth[0] = l; oth[1] = k; }          // stable: equal species keep the index order
+                                if (min(zk, zl) != rem[0] || max(zk, zl) != rem[1]) continue;
+                            }
+                            cluster_accumulate<NX>(A, p, oth, own, etab, m0, m1, S0, S1, T);
                         }
                     }
                 } else {
@@ -231,7 +262,17 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
                             for (int64_t q = l + 1; q < o1; ++q) {
                                 if (q == p) continue;
                                 oth[0] = k; oth[1] = l; oth[2] = q;
-                                cluster_accumulate<NX>(A, p, oth, own, s_exp, m0, m1, S0, S1, T);
+                                if (A.zc > 0) {
+                                    int z0 = A.Z[a0 + A.pj[k]], z1 = A.Z[a0 + A.pj[l]], z2 = A.Z[a0 + A.pj[q]];
+                                    // stable three-element insertion sort by species
+                                    if (z0 > z1) { int t = z0; z0 = z1; z1 = t; int64_t u = oth[0]; oth[0] = oth[1]; oth[1] = u; }
+                                    if (z1 > z2) {
+                                        int t = z1; z1 = z2; z2 = t; int64_t u = oth[1]; oth[1] = oth[2]; oth[2] = u;
+                                        if (z0 > z1) { t = z0; z0 = z1; z1 = t; u = oth[0]; oth[0] = oth[1]; oth[1] = u; }
+                                    }
+                                    if (z0 != rem[0] || z1 != rem[1] || z2 != rem[2]) continue;
+                                }
+                                cluster_accumulate<NX>(A, p, oth, own, etab, m0, m1, S0, S1, T);
                             }
                         }
                     }
@@ -359,6 +400,8 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     A.pi = nl.pi.p; A.prev = nl.prev.p; A.pR = nl.pR.p; A.rec = rec; A.rs = rs;
     A.npairs = npairs; A.rowE = ch.rowE.p; A.rowF = ch.rowF.p; A.rowV = ch.rowV.p;
     A.Psi = Psi->d; A.ld = Psi->ld; A.col0 = blk.col0; A.scratch = (double*)scr; A.counter = (int*)cnt;
+    A.Z = ch.Z.p; A.pj = nl.pj.p; A.zc = blk.zc;
+    for (int t = 0; t < 4; ++t) { A.zs[t] = blk.zs[t]; A.mono_exp_var[t] = blk.mono_exp_var[t]; }
     if (ctx->profiling) {
         // algorithmic work counter: unordered clusters sum_i C(n_i, N-1) (roofline numerator)
         static const char* cnames[6] = {"", "", "count:clusters_2b", "count:clusters_3b", "count:clusters_4b", "count:clusters_5b"};

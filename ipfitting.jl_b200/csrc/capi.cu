@@ -195,6 +195,14 @@ int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* bl
         BlockDev b;
         b.N = s.N; b.nb = s.nb; b.nmono = s.nmono; b.transform = s.transform;
         b.a = s.a; b.r0 = s.r0; b.rc1 = s.rc1; b.rc2 = s.rc2; b.col0 = col;
+        if (s.zc < 0) { delete B; return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: negative species", k); }
+        b.zc = s.zc;
+        for (int t = 0; t < 4; ++t) b.zs[t] = (s.zc > 0 && t < nx) ? s.zs[t] : 0;
+        for (int t = 0; s.zc > 0 && t < nx; ++t)
+            if (b.zs[t] <= 0 || (t > 0 && b.zs[t] < b.zs[t - 1])) {
+                delete B;
+                return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: neighbour species must be positive and sorted", k);
+            }
         b.h_mono_start.assign(s.nb + 1, 0);
         b.h_mono_exp.assign(s.mono_exp, s.mono_exp + (size_t)s.nmono * IPF_MAX_VARS);
         int prevb = 0;
@@ -237,6 +245,33 @@ int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* bl
         if (e == cudaSuccess) e = cudaMalloc((void**)&b.mono_exp, (size_t)b.nmono * IPF_MAX_VARS);
         if (e == cudaSuccess) e = cudaMemcpy(b.mono_start, b.h_mono_start.data(), sizeof(int32_t) * (b.nb + 1), cudaMemcpyHostToDevice);
         if (e == cudaSuccess) e = cudaMemcpy(b.mono_exp, b.h_mono_exp.data(), (size_t)b.nmono * IPF_MAX_VARS, cudaMemcpyHostToDevice);
+        // species-resolved block: one exponent table per own-leg slot (first slot of every species), the slot moved to
+        // position 0 and the pair variables renumbered accordingly
+        const int nx = b.N - 1;
+        for (int s0 = 0; e == cudaSuccess && b.zc > 0 && s0 < nx; ++s0) {
+            if (s0 > 0 && b.zs[s0] == b.zs[s0 - 1]) continue;
+            int order[4], k = 0;
+            order[k++] = s0;
+            for (int t = 0; t < nx; ++t) if (t != s0) order[k++] = t;
+            auto pair_index = [&](int a, int c) {          // lexicographic index of the pair (a < c) among nx slots
+                int idx = 0;
+                for (int u = 0; u < a; ++u) idx += nx - 1 - u;
+                return idx + (c - a - 1);
+            };
+            std::vector<uint8_t> tab((size_t)b.nmono * IPF_MAX_VARS, 0);
+            for (int m = 0; m < b.nmono; ++m) {
+                const uint8_t* src = &b.h_mono_exp[(size_t)m * IPF_MAX_VARS];
+                uint8_t* dst = &tab[(size_t)m * IPF_MAX_VARS];
+                for (int i = 0; i < nx; ++i) dst[i] = src[order[i]];
+                for (int i = 0; i < nx; ++i)
+                    for (int j = i + 1; j < nx; ++j) {
+                        const int a = std::min(order[i], order[j]), c = std::max(order[i], order[j]);
+                        dst[nx + pair_index(i, j)] = src[nx + pair_index(a, c)];
+                    }
+            }
+            e = cudaMalloc((void**)&b.mono_exp_var[s0], tab.size());
+            if (e == cudaSuccess) e = cudaMemcpy(b.mono_exp_var[s0], tab.data(), tab.size(), cudaMemcpyHostToDevice);
+        }
         if (e != cudaSuccess) {
             ipf_basis_destroy(ctx, B);
             return ipf_set_error(ctx, IPF_ECUDA, "ipf_basis_create: %s", cudaGetErrorString(e));
@@ -252,6 +287,7 @@ int32_t ipf_basis_destroy(ipf_ctx* ctx, ipf_basis* B) {
     for (auto& b : B->blocks) {
         if (b.mono_start) cudaFree(b.mono_start);
         if (b.mono_exp) cudaFree(b.mono_exp);
+        for (int t = 0; t < 4; ++t) if (b.mono_exp_var[t]) cudaFree(b.mono_exp_var[t]);
     }
     delete B;
     return IPF_OK;
@@ -332,7 +368,7 @@ void* ipf_matrix_device_ptr(const ipf_matrix* M) { return M ? (void*)M->d : null
 // ---------------------------------------------------------------- chunk upload
 static int upload_chunk(ipf_ctx* ctx, int64_t c0, int64_t c1, const int64_t* atom_off, const double* pos,
                         const double* cell, const uint8_t* pbc, const int64_t* rowE, const int64_t* rowF,
-                        const int64_t* rowV, ChunkDev& ch, Arena* arena = nullptr) {
+                        const int64_t* rowV, ChunkDev& ch, Arena* arena = nullptr, const int32_t* Z = nullptr) {
     cudaStream_t st = ctx->stream;
     const int64_t ncfg = c1 - c0;
     const int64_t a0 = atom_off[c0], natoms = atom_off[c1] - a0;
@@ -352,6 +388,12 @@ static int upload_chunk(ipf_ctx* ctx, int64_t c0, int64_t c1, const int64_t* ato
     for (int64_t c = 0; c < ncfg; ++c)
         for (int64_t s = ch.h_atom_off[c]; s < ch.h_atom_off[c + 1]; ++s) h_site_cfg[s] = (int32_t)c;
     if (natoms) IPF_CUDA(ctx, cudaMemcpyAsync(ch.site_cfg.p, h_site_cfg.data(), sizeof(int32_t) * natoms, cudaMemcpyHostToDevice, st));
+    IPF_CHECK(ch.Z.alloc(ctx, arena, natoms));
+    ch.has_Z = Z != nullptr;
+    if (natoms) {
+        if (Z) IPF_CUDA(ctx, cudaMemcpyAsync(ch.Z.p, Z + a0, sizeof(int32_t) * natoms, cudaMemcpyHostToDevice, st));
+        else IPF_CUDA(ctx, cudaMemsetAsync(ch.Z.p, 0, sizeof(int32_t) * natoms, st));
+    }
     IPF_CUDA(ctx, cudaMemcpyAsync(ch.atom_off.p, ch.h_atom_off.data(), sizeof(int64_t) * (ncfg + 1), cudaMemcpyHostToDevice, st));
     if (natoms) IPF_CUDA(ctx, cudaMemcpyAsync(ch.pos.p, pos + 3 * a0, sizeof(double) * 3 * natoms, cudaMemcpyHostToDevice, st));
     IPF_CUDA(ctx, cudaMemcpyAsync(ch.cell.p, cell + 9 * c0, sizeof(double) * 9 * ncfg, cudaMemcpyHostToDevice, st));
@@ -429,7 +471,6 @@ int32_t ipf_configs_create(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, 
 static int32_t configs_create_impl(ipf_ctx* ctx, int64_t ncfg, const int64_t* atom_off, const double* pos,
                                    const double* cell, const uint8_t* pbc, const int32_t* Z, const int64_t* rowE,
                                    const int64_t* rowF, const int64_t* rowV, ipf_configs** out, Arena* arena) {
-    (void)Z;
     if (!ctx || !out || ncfg < 0 || !atom_off || (ncfg && (!cell || !pbc || !rowE || !rowF || !rowV)))
         return ipf_set_error(ctx, IPF_EINVAL, "ipf_configs_create: bad arguments");
     *out = nullptr;
@@ -458,7 +499,7 @@ static int32_t configs_create_impl(ipf_ctx* ctx, int64_t ncfg, const int64_t* at
         ChunkDev* ch = new (std::nothrow) ChunkDev();
         if (!ch) { delete cf; return IPF_ENOMEM; }
         cf->chunks.push_back(ch);
-        int rc = upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, *ch, arena);
+        int rc = upload_chunk(ctx, c0, c1, atom_off, pos, cell, pbc, rowE, rowF, rowV, *ch, arena, Z);
         if (rc != IPF_OK) { delete cf; return rc; }
         c0 = c1;
     }
@@ -502,6 +543,13 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
             for (size_t k2 = 0; k2 < basis->blocks.size(); ++k2)
                 if (basis->blocks[k2].rc2 == rc) {
                     bool handled = false;
+                    if (basis->blocks[k2].zc > 0) {
+                        // species-resolved run: table-driven kernel (the specialised kernels assume every cluster)
+                        if (!ch->has_Z)
+                            return ipf_set_error(ctx, IPF_EINVAL, "a species-resolved basis block needs the atomic numbers Z");
+                        IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
+                        continue;
+                    }
                     if (!ctx->force_generic) IPF_CHECK(ipf_assemble_block_2b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!ctx->force_generic && !handled) IPF_CHECK(ipf_assemble_block_3b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));
                     if (!ctx->force_generic && !handled) IPF_CHECK(ipf_assemble_block_4b(ctx, basis->blocks[k2], *ch, nl, Psi, &handled));

@@ -74,6 +74,10 @@ struct BlockDev {
     uint8_t* mono_exp = nullptr;     // device [nmono][IPF_MAX_VARS]
     std::vector<int32_t> h_mono_start;
     std::vector<uint8_t> h_mono_exp;
+    // species-resolved block: centre species, sorted neighbour species, and for every variable slot s that is the first
+    // of its species the exponent table with slot s moved to position 0 (the kernels pin the own leg to slot 0)
+    int zc = 0, zs[4] = {0, 0, 0, 0};
+    uint8_t* mono_exp_var[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
 struct ipf_basis {
@@ -209,6 +213,8 @@ struct ChunkDev {
     FlexBuf<uint8_t> pbc;        // [3*ncfg]
     FlexBuf<int64_t> rowE, rowF, rowV;   // [ncfg] 1-based, 0 = absent
     FlexBuf<int32_t> site_cfg;           // [natoms] config of every atom
+    FlexBuf<int32_t> Z;                  // [natoms] atomic numbers (zeros when the caller passed none)
+    bool has_Z = false;
     std::vector<int64_t> h_atom_off;
 };
 

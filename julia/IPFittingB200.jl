@@ -20,6 +20,7 @@ struct BlockSpec            # mirrors ipf_block_spec
    N::Int32; nb::Int32; nmono::Int32; transform::Int32
    a::Float64; r0::Float64; rc1::Float64; rc2::Float64
    mono_b::Ptr{Int32}; mono_exp::Ptr{UInt8}
+   zc::Int32; zs::NTuple{4, Int32}     # species-resolved run: centre species, sorted neighbour species (zc = 0: any)
 end
 
 mutable struct Ctx
@@ -46,7 +47,8 @@ context() = (CTX[] === nothing && (CTX[] = Ctx(parse(Int, get(ENV, "LOCAL_RANK",
          "polys"  => [Dict("N" => N, "desc" => index into descs (0-based), "orbit" => [[e_1, ..., e_nv], ...]), ...])
 
 one entry of "polys" per basis function (column of Ψ), "orbit" = the exponent tuples of its S_{N-1} orbit over the
-variables (x_1..x_{N-1}, w_12, w_13, .., w_23, ..); kind 0: x = exp(-a (r/r0 - 1)), 1: x = (r0/r)^a; cutoff
+variables (x_1..x_{N-1}, w_12, w_13, .., w_23, ..), optional "zc" / "zs" (centre species and sorted neighbour species of a
+species-resolved function); kind 0: x = exp(-a (r/r0 - 1)), 1: x = (r0/r)^a; cutoff
 CosCut(rc1, rc2).  It is what `NBodyBasis.write_dict` of ipfitting.jl_b200/basis.py emits and what the `basis` entry of
 the `_info.json` written by either side holds.  For an NBodyIPs basis the method below reads the same information from
 the basis elements: `bodyorder(b)`, the descriptor (`b.D.transform`, `b.D.cutoff`) and the exponent tuples of the
@@ -83,7 +85,8 @@ function blockspecs(basis)
    while start <= length(polys)
       p0 = polys[start]
       stop = start
-      while stop < length(polys) && polys[stop + 1]["N"] == p0["N"] && polys[stop + 1]["desc"] == p0["desc"]
+      while stop < length(polys) && polys[stop + 1]["N"] == p0["N"] && polys[stop + 1]["desc"] == p0["desc"] &&
+            get(polys[stop + 1], "zc", 0) == get(p0, "zc", 0) && get(polys[stop + 1], "zs", Int[]) == get(p0, "zs", Int[])
          stop += 1
       end
       nv = (p0["N"] - 1) + (p0["N"] - 1) * (p0["N"] - 2) ÷ 2
@@ -97,7 +100,8 @@ function blockspecs(basis)
       push!(keep, mono_b); push!(keep, mono_exp)
       push!(specs, BlockSpec(Int32(p0["N"]), Int32(stop - start + 1), Int32(length(mono_b)), Int32(d["kind"]),
                              Float64(d["a"]), Float64(d["r0"]), Float64(d["rc1"]), Float64(d["rc2"]),
-                             pointer(mono_b), pointer(mono_exp)))
+                             pointer(mono_b), pointer(mono_exp),
+                             Int32(get(p0, "zc", 0)), ntuple(i -> Int32(get(get(p0, "zs", Int[]), i, 0)), 4)))
       start = stop + 1
    end
    return specs, keep

@@ -154,6 +154,10 @@ typedef struct {
     const int32_t* mono_b;      /* [nmono] */
     const uint8_t* mono_exp;    /* [nmono][IPFO_MAX_VARS] */
     desc_t D;
+    /* species-resolved block (JuLIP Atoms.Z): the functions act on the clusters whose centre has species zc and whose
+     * N-1 neighbours have exactly the (sorted) species zs, the legs assigned to the variable slots in species order
+     * (legs of equal species in enumeration order: the polynomial is symmetric in them).  zc = 0: every cluster. */
+    int zc, zs[IPFO_MAX_LEGS];
 } block_t;
 
 typedef struct {
@@ -244,8 +248,25 @@ static void eval_cluster(const block_t* B, int i, const nbr_t** leg, int what,
     }
 }
 
+/* species rule for one unordered cluster: returns without contribution when the neighbour species do not match */
+static void eval_cluster_z(const block_t* B, const int32_t* Z, int i, const nbr_t** leg, int what,
+                           int nat, double* E, double* F, double* V, double* scratch) {
+    if (B->zc == 0 || Z == NULL) { eval_cluster(B, i, leg, what, nat, E, F, V, scratch); return; }
+    const int nx = B->N - 1;
+    const nbr_t* srt[IPFO_MAX_LEGS];
+    for (int a = 0; a < nx; ++a) srt[a] = leg[a];
+    for (int a = 1; a < nx; ++a) {                 /* stable insertion sort by species */
+        const nbr_t* t = srt[a];
+        int c = a - 1;
+        while (c >= 0 && Z[srt[c]->j] > Z[t->j]) { srt[c + 1] = srt[c]; --c; }
+        srt[c + 1] = t;
+    }
+    for (int a = 0; a < nx; ++a) if (Z[srt[a]->j] != B->zs[a]) return;
+    eval_cluster(B, i, srt, what, nat, E, F, V, scratch);
+}
+
 static void eval_config_block_par(const block_t* B, int nat, const double* pos, const double* cell,
-                                  const uint8_t* pbc, int what, double* E, double* F, double* V, int par) {
+                                  const uint8_t* pbc, const int32_t* Z, int what, double* E, double* F, double* V, int par) {
     const double rcut = B->D.rc2;
     int64_t cap = ipfo_neighbours(nat, pos, cell, pbc, rcut, 0, NULL, NULL, NULL, NULL);
     int32_t* I = (int32_t*)malloc(sizeof(int32_t) * (size_t)(cap + 1));
@@ -289,24 +310,25 @@ static void eval_config_block_par(const block_t* B, int nat, const double* pos, 
 #pragma omp for schedule(dynamic, 1)
     for (int i = 0; i < nat; ++i) {
         double *E = Et, *F = Ft, *V = Vt;
+        if (B->zc != 0 && Z != NULL && Z[i] != B->zc) continue;
         const int64_t p0 = soff[i], p1 = soff[i + 1];
         const int n = (int)(p1 - p0);
         const nbr_t* base = nb + p0;
         const nbr_t* leg[IPFO_MAX_LEGS];
         if (nx == 1) {
-            for (int a = 0; a < n; ++a) { leg[0] = base + a; eval_cluster(B, i, leg, what, nat, E, F, V, scratch); }
+            for (int a = 0; a < n; ++a) { leg[0] = base + a; eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch); }
         } else if (nx == 2) {
             for (int a = 0; a < n; ++a)
                 for (int c = a + 1; c < n; ++c) {
                     leg[0] = base + a; leg[1] = base + c;
-                    eval_cluster(B, i, leg, what, nat, E, F, V, scratch);
+                    eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch);
                 }
         } else if (nx == 3) {
             for (int a = 0; a < n; ++a)
                 for (int c = a + 1; c < n; ++c)
                     for (int e = c + 1; e < n; ++e) {
                         leg[0] = base + a; leg[1] = base + c; leg[2] = base + e;
-                        eval_cluster(B, i, leg, what, nat, E, F, V, scratch);
+                        eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch);
                     }
         } else if (nx == 4) {
             for (int a = 0; a < n; ++a)
@@ -314,7 +336,7 @@ static void eval_config_block_par(const block_t* B, int nat, const double* pos, 
                     for (int e = c + 1; e < n; ++e)
                         for (int g = e + 1; g < n; ++g) {
                             leg[0] = base + a; leg[1] = base + c; leg[2] = base + e; leg[3] = base + g;
-                            eval_cluster(B, i, leg, what, nat, E, F, V, scratch);
+                            eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch);
                         }
         }
     }
@@ -333,8 +355,8 @@ static void eval_config_block_par(const block_t* B, int nat, const double* pos, 
 }
 
 static void eval_config_block(const block_t* B, int nat, const double* pos, const double* cell,
-                              const uint8_t* pbc, int what, double* E, double* F, double* V) {
-    eval_config_block_par(B, nat, pos, cell, pbc, what, E, F, V, 0);
+                              const uint8_t* pbc, const int32_t* Z, int what, double* E, double* F, double* V) {
+    eval_config_block_par(B, nat, pos, cell, pbc, Z, what, E, F, V, 0);
 }
 
 /* ------------------------------------------------------------------ */
@@ -350,16 +372,20 @@ static void eval_config_block(const block_t* B, int nat, const double* pos, cons
  *         (src/obsiter.jl:87-102, src/tools.jl:35-56).
  * mode 2: the tasks of mode 1 one after the other, the SITES of each task shared out over the threads
  *         (for timing a small sample of configurations with every host thread busy). */
-int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t* mono_b,
-                            const uint8_t* mono_exp, int32_t transform, double a, double r0,
-                            double rc1, double rc2, int64_t ncfg, const int64_t* atom_off,
-                            const double* pos, const double* cell, const uint8_t* pbc,
-                            const int64_t* rowE, const int64_t* rowF, const int64_t* rowV,
-                            int64_t col0, double* Psi, int64_t ld, int32_t mode, int32_t nthreads) {
+/* Z: atomic numbers of all atoms (NULL with zc = 0); zc, zs[N-1]: species tuple of the block (zc = 0: none) */
+int32_t ipfo_assemble_block_z(int32_t N, int32_t nb, int32_t nmono, const int32_t* mono_b,
+                              const uint8_t* mono_exp, int32_t transform, double a, double r0,
+                              double rc1, double rc2, int64_t ncfg, const int64_t* atom_off,
+                              const double* pos, const double* cell, const uint8_t* pbc,
+                              const int64_t* rowE, const int64_t* rowF, const int64_t* rowV,
+                              int64_t col0, double* Psi, int64_t ld, int32_t mode, int32_t nthreads,
+                              const int32_t* Zall, int32_t zc, const int32_t* zs) {
     if (N < 2 || N > 5) return -1;
     block_t B;
     B.N = N; B.nb = nb; B.nmono = nmono; B.mono_b = mono_b; B.mono_exp = mono_exp;
     B.D.transform = transform; B.D.a = a; B.D.r0 = r0; B.D.rc1 = rc1; B.D.rc2 = rc2;
+    B.zc = (Zall != NULL && zs != NULL) ? zc : 0;
+    for (int k = 0; k < IPFO_MAX_LEGS; ++k) B.zs[k] = (B.zc && k < N - 1) ? zs[k] : 0;
 
     /* task list */
     const int tasks_per_cfg = mode ? 3 : 1;
@@ -396,7 +422,8 @@ int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t*
             double* E = (double*)calloc((size_t)nb, sizeof(double));
             double* F = (double*)calloc((size_t)nb * 3 * (size_t)nat + 1, sizeof(double));
             double* V = (double*)calloc((size_t)nb * 9, sizeof(double));
-            eval_config_block_par(&B, nat, pos + 3 * atom_off[c], cell + 9 * c, pbc + 3 * c, what, E, F, V, 1);
+            eval_config_block_par(&B, nat, pos + 3 * atom_off[c], cell + 9 * c, pbc + 3 * c,
+                                  B.zc ? Zall + atom_off[c] : NULL, what, E, F, V, 1);
             for (int b = 0; b < nb; ++b) {
                 double* col = Psi + (size_t)(col0 + b) * (size_t)ld;
                 if (what & 1) col[rowE[c] - 1] = E[b];
@@ -433,7 +460,8 @@ int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t*
             double* E = (double*)calloc((size_t)nb, sizeof(double));
             double* F = (double*)calloc((size_t)nb * 3 * (size_t)nat + 1, sizeof(double));
             double* V = (double*)calloc((size_t)nb * 9, sizeof(double));
-            eval_config_block(&B, nat, pos + 3 * atom_off[c], cell + 9 * c, pbc + 3 * c, what, E, F, V);
+            eval_config_block(&B, nat, pos + 3 * atom_off[c], cell + 9 * c, pbc + 3 * c,
+                              B.zc ? Zall + atom_off[c] : NULL, what, E, F, V);
             /* block placement: Psi[irows, col0 + b]; the reference takes a global lock
              * here (src/lsq_db.jl:274-276); rows of different tasks are disjoint. */
 #pragma omp critical(ipfo_psi_write)
@@ -459,20 +487,41 @@ int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t*
     return 0;
 }
 
+int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t* mono_b,
+                            const uint8_t* mono_exp, int32_t transform, double a, double r0,
+                            double rc1, double rc2, int64_t ncfg, const int64_t* atom_off,
+                            const double* pos, const double* cell, const uint8_t* pbc,
+                            const int64_t* rowE, const int64_t* rowF, const int64_t* rowV,
+                            int64_t col0, double* Psi, int64_t ld, int32_t mode, int32_t nthreads) {
+    return ipfo_assemble_block_z(N, nb, nmono, mono_b, mono_exp, transform, a, r0, rc1, rc2, ncfg, atom_off, pos, cell,
+                                 pbc, rowE, rowF, rowV, col0, Psi, ld, mode, nthreads, NULL, 0, NULL);
+}
+
 /* Single-config convenience for tests: evaluates one block, returns dense
  * E[nb], F[nb][3 nat], V[nb][9]. */
+int32_t ipfo_eval_config_z(int32_t N, int32_t nb, int32_t nmono, const int32_t* mono_b,
+                           const uint8_t* mono_exp, int32_t transform, double a, double r0,
+                           double rc1, double rc2, int32_t nat, const double* pos,
+                           const double* cell, const uint8_t* pbc, double* E, double* F, double* V,
+                           const int32_t* Z, int32_t zc, const int32_t* zs) {
+    block_t B;
+    B.N = N; B.nb = nb; B.nmono = nmono; B.mono_b = mono_b; B.mono_exp = mono_exp;
+    B.D.transform = transform; B.D.a = a; B.D.r0 = r0; B.D.rc1 = rc1; B.D.rc2 = rc2;
+    B.zc = (Z != NULL && zs != NULL) ? zc : 0;
+    for (int k = 0; k < IPFO_MAX_LEGS; ++k) B.zs[k] = (B.zc && k < N - 1) ? zs[k] : 0;
+    memset(E, 0, sizeof(double) * (size_t)nb);
+    memset(F, 0, sizeof(double) * (size_t)nb * 3 * (size_t)nat);
+    memset(V, 0, sizeof(double) * (size_t)nb * 9);
+    eval_config_block(&B, nat, pos, cell, pbc, B.zc ? Z : NULL, 7, E, F, V);
+    return 0;
+}
+
 int32_t ipfo_eval_config(int32_t N, int32_t nb, int32_t nmono, const int32_t* mono_b,
                          const uint8_t* mono_exp, int32_t transform, double a, double r0,
                          double rc1, double rc2, int32_t nat, const double* pos,
                          const double* cell, const uint8_t* pbc, double* E, double* F, double* V) {
-    block_t B;
-    B.N = N; B.nb = nb; B.nmono = nmono; B.mono_b = mono_b; B.mono_exp = mono_exp;
-    B.D.transform = transform; B.D.a = a; B.D.r0 = r0; B.D.rc1 = rc1; B.D.rc2 = rc2;
-    memset(E, 0, sizeof(double) * (size_t)nb);
-    memset(F, 0, sizeof(double) * (size_t)nb * 3 * (size_t)nat);
-    memset(V, 0, sizeof(double) * (size_t)nb * 9);
-    eval_config_block(&B, nat, pos, cell, pbc, 7, E, F, V);
-    return 0;
+    return ipfo_eval_config_z(N, nb, nmono, mono_b, mono_exp, transform, a, r0, rc1, rc2, nat, pos, cell, pbc, E, F, V,
+                              NULL, 0, NULL);
 }
 
 int32_t ipfo_num_threads(void) {

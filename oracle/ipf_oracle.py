@@ -35,10 +35,14 @@ def lib():
                                           C.c_double, C.c_double, C.c_double, C.c_double,
                                           C.c_int64, i64p, dp, dp, u8p, i64p, i64p, i64p,
                                           C.c_int64, dp, C.c_int64, C.c_int32, C.c_int32]
+        L.ipfo_assemble_block_z.restype = C.c_int32
+        L.ipfo_assemble_block_z.argtypes = L.ipfo_assemble_block.argtypes + [ip, C.c_int32, ip]
         L.ipfo_eval_config.restype = C.c_int32
         L.ipfo_eval_config.argtypes = [C.c_int32, C.c_int32, C.c_int32, ip, u8p, C.c_int32,
                                        C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_int32, dp, dp, u8p, dp, dp, dp]
+        L.ipfo_eval_config_z.restype = C.c_int32
+        L.ipfo_eval_config_z.argtypes = L.ipfo_eval_config.argtypes + [ip, C.c_int32, ip]
         L.ipfo_num_threads.restype = C.c_int32
         _LIB = L
     return _LIB
@@ -73,10 +77,14 @@ def eval_config(block, at):
     me = np.ascontiguousarray(block.mono_exp, dtype=np.uint8)
     pbc = np.ascontiguousarray(at.pbc, dtype=np.uint8)
     X = np.ascontiguousarray(at.X); cell = np.ascontiguousarray(at.cell)
-    rc = lib().ipfo_eval_config(block.N, block.nb, len(mb), _p(mb, C.c_int32), _p(me, C.c_uint8),
-                                kind, a, r0, rc1, rc2, nat, _p(X, C.c_double),
-                                _p(cell, C.c_double), _p(pbc, C.c_uint8),
-                                _p(E, C.c_double), _p(F, C.c_double), _p(V, C.c_double))
+    Z = np.ascontiguousarray(at.Z, dtype=np.int32)
+    zs = np.zeros(4, dtype=np.int32)
+    zs[:len(block.zs)] = block.zs
+    rc = lib().ipfo_eval_config_z(block.N, block.nb, len(mb), _p(mb, C.c_int32), _p(me, C.c_uint8),
+                                  kind, a, r0, rc1, rc2, nat, _p(X, C.c_double),
+                                  _p(cell, C.c_double), _p(pbc, C.c_uint8),
+                                  _p(E, C.c_double), _p(F, C.c_double), _p(V, C.c_double),
+                                  _p(Z, C.c_int32), int(block.zc), _p(zs, C.c_int32))
     assert rc == 0
     return E, F, V.reshape(-1, 3, 3)
 
@@ -101,15 +109,20 @@ def assemble(basis, configs, rowE, rowF, rowV, nrows, mode=0, nthreads=0):
     rowF = np.ascontiguousarray(rowF, dtype=np.int64)
     rowV = np.ascontiguousarray(rowV, dtype=np.int64)
     L = lib()
+    Zall = np.ascontiguousarray(np.concatenate([np.asarray(d.at.Z, dtype=np.int32) for d in configs])
+                                if len(configs) else np.zeros(0, dtype=np.int32))
     for blk in basis.blocks:
         kind, a, r0, rc1, rc2 = blk.desc.params()
         mb = np.ascontiguousarray(blk.mono_b, dtype=np.int32)
         me = np.ascontiguousarray(blk.mono_exp, dtype=np.uint8)
-        rc = L.ipfo_assemble_block(blk.N, blk.nb, len(mb), _p(mb, C.c_int32), _p(me, C.c_uint8),
-                                   kind, a, r0, rc1, rc2, len(configs), _p(off, C.c_int64),
-                                   _p(pos, C.c_double), _p(cell, C.c_double), _p(pbc, C.c_uint8),
-                                   _p(rowE, C.c_int64), _p(rowF, C.c_int64), _p(rowV, C.c_int64),
-                                   blk.col0, _p(Psi, C.c_double), nrows, mode, nthreads)
+        zs = np.zeros(4, dtype=np.int32)
+        zs[:len(blk.zs)] = blk.zs
+        rc = L.ipfo_assemble_block_z(blk.N, blk.nb, len(mb), _p(mb, C.c_int32), _p(me, C.c_uint8),
+                                     kind, a, r0, rc1, rc2, len(configs), _p(off, C.c_int64),
+                                     _p(pos, C.c_double), _p(cell, C.c_double), _p(pbc, C.c_uint8),
+                                     _p(rowE, C.c_int64), _p(rowF, C.c_int64), _p(rowV, C.c_int64),
+                                     blk.col0, _p(Psi, C.c_double), nrows, mode, nthreads,
+                                     _p(Zall, C.c_int32), int(blk.zc), _p(zs, C.c_int32))
         assert rc == 0
     return Psi
 

@@ -6,7 +6,7 @@ import ipfitting_jl_b200 as ipf
 from ipfitting_jl_b200 import synth
 from ipfitting_jl_b200.lsq_db import LsqDB
 import ipf_oracle as O
-from util import PSI_RTOL, psi_errors, rows_for, si_desc
+from util import PSI_RTOL, psi_entrywise, psi_errors, rows_for, si_desc
 
 pytestmark = pytest.mark.gpu
 
@@ -273,3 +273,37 @@ def test_4b_subset_of_orbits_uses_the_specialised_path(ctx):
         assert ctx.profile_get("site_deriv_4b")[1] > 0
     finally:
         ctx.profile(False)
+
+
+def test_entrywise_error_report(ctx):
+    """north_star states the 1e-10 bar entry-wise; the parity tests apply it per (column, observation type) block because
+    forces of a nearly perfect crystal cancel (any summation order has absolute error eps x sum |terms|).  This test
+    reports and bounds the entry-wise figure on a 2B + 3B + 4B basis: every entry that is not a cancellation zero
+    (|ref| > 1e-6 of its column's largest entry) agrees to 1e-9 entry-wise, 99.9 % of them to 1e-10."""
+    configs = synth.rattled_configs("Si", 2, 3, seed=21, calc=synth.StillingerWeber(), min_dist=0.75)
+    B = ipf.nbpolys(2, si_desc(), 14) + ipf.nbpolys(3, si_desc(2.0), 8) + ipf.nbpolys(4, si_desc(1.8), 6)
+    db, ref = _check(B, configs, ctx)
+    emax, e999, share = psi_entrywise(db.Psi, ref)
+    print(f"entry-wise relative error: max {emax:.2e}, 99.9 % quantile {e999:.2e}, entries within 1e-10: {100 * share:.3f} %")
+    assert emax <= 1e-9 and e999 <= 1e-10 and share >= 0.9999
+
+
+def test_species_resolved_blocks(ctx):
+    """Two-species cells (zincblende Si/C, JuLIP `Atoms.Z`, `src/prototypes.jl:19-25`): species-resolved 2-, 3- and 4-body
+    runs (one per centre species and multiset of neighbour species, polynomials symmetric in equal-species legs only)
+    against the oracle, next to species-agnostic runs of the specialised kernels in the same basis."""
+    desc = ipf.BondAngleDesc("exp(- (r/1.89 - 1.0))", ipf.CosCut(3.6, 4.6))
+    desc4 = ipf.BondAngleDesc("exp(- (r/1.89 - 1.0))", ipf.CosCut(2.6, 3.6))
+    rng = np.random.default_rng(11)
+    configs = []
+    for L in (1, 2, 1):
+        at = synth.rattle(synth.repeat(synth.zincblende(4.36, 14, 6), L), 0.12, rng, 0.02)
+        nat = len(at)
+        configs.append(ipf.Dat(at, "sic", E=0.0, F=np.zeros((nat, 3)), V=np.zeros(6)))
+    B = (ipf.species_nbpolys(2, desc, 6, [14, 6]) + ipf.nbpolys(3, desc, 4)
+         + ipf.species_nbpolys(3, desc, 3, [14, 6]) + ipf.nbpolys(4, desc4, 2, (6, (6, 14, 14)))
+         + ipf.nbpolys(4, desc4, 2, (14, (6, 6, 6))) + ipf.nbpolys(2, desc, 4))
+    db, ref = _check(B, configs, ctx)
+    assert np.abs(ref).max(axis=0).min() > 0          # every column sees clusters of its species tuple
+    # a basis with a species-resolved run needs Z: the specialised (species-agnostic) kernels do not
+    assert [b.zc for b in db.basis.blocks][:2] == [6, 6]

@@ -9,7 +9,7 @@ from ipfitting_jl_b200.lsq import solve_device
 from ipfitting_jl_b200.lsq_db import LsqDB
 import ipf_oracle as O
 import lsq_oracle as LO
-from util import rows_for, si_desc
+from util import PSI_RTOL, psi_errors, rows_for, si_desc
 
 pytestmark = pytest.mark.gpu
 
@@ -175,6 +175,13 @@ def test_bench_basis_fit_matches_householder(ctx):
     assert abs(r_gpu - rel_rms) <= 1e-6 * rel_rms                     # the returned c reproduces the minimum
     assert np.linalg.norm(A @ (info["c"] - c_ref)) <= 2e-3 * np.linalg.norm(y) * rel_rms
     assert abs(np.log10(info["cond_R"]) - np.log10(kappa)) < 0.5
+    # per-configtype RMSE table of this fit against the oracle's table for ITS minimiser: both sit at the same minimum,
+    # so the tables agree far below the 1e-8 bar of the well-conditioned cases
+    IP2, info2 = ipf.lsqfit(db, weights=dict(w), E0=-4.0, Vref=ipf.OneBody(-4.0), error_table=True)
+    rm_ref, _ = LO.rmse_table(ref, configs, c_ref, E0=-4.0)
+    for ct in rm_ref:
+        for okey in rm_ref[ct]:
+            assert abs(info2["errors"]["rmse"][ct][okey] - rm_ref[ct][okey]) <= 1e-6 * rm_ref[ct][okey], (ct, okey)
 
 
 @pytest.mark.parametrize("ndiscard", [0, 2])
@@ -260,3 +267,36 @@ def test_vref_from_a_previous_fit_is_evaluated_on_the_device(fitcase, ctx):
     assert np.allclose(Yl, Y, rtol=1e-10, atol=1e-9 * np.abs(Ydata).max())
     IP3, info3 = ipf.lsqfit(db, weights=dict(w), Vref=IP2)
     assert info3["rel_rms"] < 1.0 and np.isfinite(info3["c"]).all()
+
+
+def test_species_fit_on_mixed_size_cells(ctx):
+    """BASELINE config 5 in miniature: two-species (Si/C zincblende) cells of 8 to 512 atoms, species-resolved 2- and 3-body
+    basis, labels generated from a known coefficient vector through the ORACLE's design matrix: `LsqDB` + `lsqfit` on the
+    GPU must recover the coefficients (the rows of the 512-atom cells go through the large-configuration paths)."""
+    desc = ipf.BondAngleDesc("exp(- (r/1.89 - 1.0))", ipf.CosCut(3.2, 4.2))
+    B = ipf.NBodyBasis(ipf.species_nbpolys(2, desc, 4, [14, 6]) + ipf.species_nbpolys(3, desc, 2, [14, 6]))
+    rng = np.random.default_rng(23)
+    ats = []
+    for L in (1, 1, 2, 1, 3, 2, 4, 1, 2, 1):
+        ats.append(synth.rattle(synth.repeat(synth.zincblende(4.36, 14, 6), L), 0.1 + 0.1 * rng.uniform(), rng, 0.03))
+    blank = [ipf.Dat(a, "sic", E=0.0, F=np.zeros((len(a), 3)), V=np.zeros(6)) for a in ats]
+    from ipfitting_jl_b200.lsq_db import _alloc_rows
+    nrows = _alloc_rows(blank)
+    r = rows_for(blank)
+    ref = O.assemble(B, blank, r["E"], r["F"], r["V"], nrows)
+    c_true = rng.standard_normal(len(B)) / (1.0 + np.arange(len(B)))
+    y = ref @ c_true
+    configs = []
+    for d in blank:
+        e = y[d.rows["E"][0]]
+        f = y[d.rows["F"][0]:d.rows["F"][0] + d.rows["F"][1]].reshape(-1, 3)
+        v = y[d.rows["V"][0]:d.rows["V"][0] + 6]
+        configs.append(ipf.Dat(d.at, "sic", E=e, F=f, V=v))
+    db = LsqDB("", B, configs, ctx=ctx)
+    assert psi_errors(db.Psi, ref, configs) <= PSI_RTOL
+    w = {"default": {"E": 10.0, "F": 1.0, "V": 1.0}}
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=0.0, error_table=True)
+    kappa = info["cond_R"]
+    assert np.linalg.norm(info["c"] - c_true) <= max(1e-8, 100 * kappa * 2.2e-16) * np.linalg.norm(c_true)
+    assert info["rel_rms"] <= 1e-9
+    assert max(len(a) for a in ats) == 512

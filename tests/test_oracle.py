@@ -105,3 +105,48 @@ def test_label_calculators_consistent():
         fd = -(calc.efv(ap)[0] - calc.efv(am)[0]) / (2 * h)
         assert abs(fd - V[0, 1]) < 1e-5 * max(1.0, np.abs(V).max())
         assert np.abs(F.sum(0)).max() < 1e-9
+
+
+# ---------------------------------------------------------------- species-resolved blocks (JuLIP Atoms.Z)
+def _sic(seed=3, L=1):
+    at = synth.repeat(synth.zincblende(4.36, 14, 6), L)
+    return synth.rattle(at, 0.15, np.random.default_rng(seed), 0.02)
+
+
+def _sic_desc(rcut=4.6):
+    return ipf.BondAngleDesc("exp(- (r/1.89 - 1.0))", ipf.CosCut(rcut - 1.0, rcut))
+
+
+def test_species_blocks_sum_to_the_species_agnostic_basis():
+    """Every cluster belongs to exactly one species tuple: the species-resolved functions whose orbit is contained in a
+    symmetric orbit add up to the species-agnostic function."""
+    at = _sic()
+    for N, deg in ((2, 5), (3, 3), (4, 2)):
+        B0 = ipf.NBodyBasis(ipf.nbpolys(N, _sic_desc(), deg))
+        Bs = ipf.NBodyBasis(ipf.species_nbpolys(N, _sic_desc(), deg, [14, 6]))
+        E0, F0, V0 = O.eval_config(B0.blocks[0], at)
+        Et, Ft, Vt = np.zeros_like(E0), np.zeros_like(F0), np.zeros_like(V0)
+        for blk in Bs.blocks:
+            E, F, V = O.eval_config(blk, at)
+            for k, p in enumerate(Bs.polys[blk.col0:blk.col0 + blk.nb]):
+                for b, q in enumerate(B0.polys):
+                    if set(p.orbit) <= set(q.orbit):
+                        Et[b] += E[k]; Ft[b] += F[k]; Vt[b] += V[k]
+        assert np.abs(Et - E0).max() <= 1e-12 * np.abs(E0).max()
+        assert np.abs(Ft - F0).max() <= 1e-12 * np.abs(F0).max()
+        assert np.abs(Vt - V0).max() <= 1e-12 * np.abs(V0).max()
+
+
+def test_species_forces_match_finite_differences():
+    at = _sic(seed=5)
+    B = ipf.NBodyBasis(ipf.nbpolys(3, _sic_desc(), 3, (14, (6, 14))) + ipf.nbpolys(4, _sic_desc(3.6), 2, (6, (6, 14, 14))))
+    h = 1e-5
+    for blk in B.blocks:
+        E, F, V = O.eval_config(blk, at)
+        assert np.abs(E).max() > 0
+        for (k, d) in ((0, 0), (5, 2)):
+            ap, am = at.copy(), at.copy()
+            ap.X[k, d] += h
+            am.X[k, d] -= h
+            fd = -(O.eval_config(blk, ap)[0] - O.eval_config(blk, am)[0]) / (2 * h)
+            assert np.allclose(fd, F[:, 3 * k + d], rtol=1e-6, atol=1e-7 * np.abs(F).max())

@@ -38,3 +38,16 @@ def psi_errors(Psi, Ref, configs):
         rel = np.where(scale > 0, err / np.where(scale > 0, scale, 1.0), err)
         worst = max(worst, float(rel.max()))
     return worst
+
+
+def psi_entrywise(Psi, Ref, floor=1e-6):
+    """Entry-wise relative error |a - b| / |b| next to the block-scaled figure of `psi_errors`, over the entries that are
+    not cancellation zeros (|ref| > floor x the largest entry of their column).  Returns (max, 99.9 % quantile, share of
+    ALL entries within 1e-10 entry-wise or below 1e-10 x column scale in absolute terms)."""
+    scale = np.abs(Ref).max(axis=0)
+    scale = np.where(scale > 0, scale, 1.0)
+    big = np.abs(Ref) > floor * scale[None, :]
+    rel = np.abs(Psi - Ref)[big] / np.abs(Ref)[big]
+    diff = np.abs(Psi - Ref)
+    ok = (diff <= 1e-10 * np.abs(Ref)) | (diff <= 1e-10 * scale[None, :])
+    return float(rel.max()) if rel.size else 0.0, float(np.quantile(rel, 0.999)) if rel.size else 0.0, float(ok.mean())
