@@ -235,6 +235,9 @@ int32_t ipf_solve_append_rows(ipf_ctx* ctx, ipf_solver* S, int64_t nextra, const
  * (src/lsq.jl:482-497), whose small dense work (SVD / pivoted QR of the n x n factor) stays on the host. */
 int32_t ipf_solve_qty(ipf_ctx* ctx, ipf_solver* S, double* qty);
 int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double* ssr, double* ssy);
+/* cond(R) (src/lsq.jl:469) of the factor ipf_solve_finish returns, estimated on the device by power / inverse iteration
+ * (a lower bound, tight to a few per cent); call after ipf_solve_finish.  The exact value is an SVD of R_out on the host. */
+int32_t ipf_solve_cond(ipf_ctx* ctx, ipf_solver* S, double* kappa);
 /* Diagnostics of a solve: Gram passes, orthogonality defect |A^T A - I|_F seen by the last pass, largest diagonal shift
  * used, kappa_hat = (max / min diagonal of the equilibrated Cholesky factor)^2 of the last pass, and the number of
  * refinement steps of the corrected semi-normal equations (0: the last pass was orthonormal to 0.1). */

@@ -329,6 +329,12 @@ class _Solver:
                                                        C.byref(ssr), C.byref(ssy)))
         return ssr.value, ssy.value
 
+    def cond(self) -> float:
+        """cond(R) of the returned factor, estimated on the device (power / inverse iteration; after `finish`)."""
+        k = C.c_double()
+        self.ctx.check(self.ctx.lib.ipf_solve_cond(self.ctx.h, self.h, C.byref(k)))
+        return k.value
+
     def info(self) -> dict:
         npass, defect, shift, gms, tms = C.c_int32(), C.c_double(), C.c_double(), C.c_double(), C.c_double()
         self.ctx.lib.ipf_solve_info(self.h, C.byref(npass), C.byref(defect), C.byref(shift), C.byref(gms), C.byref(tms))
@@ -371,6 +377,8 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True, factor_solver
     info = S.info()
     info.update(extra)
     info["rel_rms"] = math.sqrt(ssr) / math.sqrt(ssy) if ssy > 0 else float("nan")
+    if hasattr(S, "cond"):
+        info["cond_R_estimate"] = S.cond()
     return c, R, info
 
 
@@ -519,7 +527,12 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     Irows_dev = None if len(Irows) == len(W) else Irows
     c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows_dev, Icols, Dinv, want_R=True, comm=comm, precon=precon,
                               factor_solver=factor_solver, reg=reg)
-    kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
+    # `cond(qrPsi.R)` (`src/lsq.jl:469`; computed but only logged there): the device estimate (a lower bound, tight to a few
+    # per cent) unless the exact SVD of the n x n factor is asked for (`verbose=True` or solver["exact_cond"])
+    if verbose or solver.get("exact_cond") or "cond_R_estimate" not in info:
+        kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
+    else:
+        kappa = float(info["cond_R_estimate"])
     if isinstance(saveqr, dict):
         saveqr["R"] = R
         saveqr["Y"] = (W * Y)[Irows]

@@ -300,3 +300,14 @@ def test_species_fit_on_mixed_size_cells(ctx):
     assert np.linalg.norm(info["c"] - c_true) <= max(1e-8, 100 * kappa * 2.2e-16) * np.linalg.norm(c_true)
     assert info["rel_rms"] <= 1e-9
     assert max(len(a) for a in ats) == 512
+
+
+def test_cond_estimate_is_a_tight_lower_bound(fitcase):
+    """`cond(qrPsi.R)` (`src/lsq.jl:469`): the device estimate (power / inverse iteration on the returned factor) is a lower
+    bound of the SVD value and within 20 % of it."""
+    db, _ = fitcase
+    w = {"default": {"E": 30.0, "F": 1.0, "V": 0.5}}
+    _, est = ipf.lsqfit(db, weights=dict(w), E0=-4.0)
+    _, exact = ipf.lsqfit(db, weights=dict(w), E0=-4.0, solver={"solver": "qr", "exact_cond": True})
+    assert est["cond_R"] <= exact["cond_R"] * (1.0 + 1e-9)
+    assert est["cond_R"] >= 0.8 * exact["cond_R"]

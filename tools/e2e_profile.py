@@ -8,7 +8,7 @@ from ipfitting_jl_b200 import _capi, lsq_db, lsq
 
 ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 ctx = _capi.Context(0)
-basis = bench.make_basis(); configs = bench.make_configs(ncfg, 1)
+basis = bench.make_basis(); configs = bench.make_configs(range(ncfg), 1)
 acc = collections.OrderedDict()
 
 def timed(mod, name, label=None):

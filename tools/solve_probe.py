@@ -6,7 +6,7 @@ import bench
 import ipfitting_jl_b200 as ipf
 from ipfitting_jl_b200.lsq import _Solver, _fix_weights, _select, collect_observations
 ncfg = int(sys.argv[1]) if len(sys.argv) > 1 else 400
-basis = bench.make_basis(); configs = bench.make_configs(ncfg, 1)
+basis = bench.make_basis(); configs = bench.make_configs(range(ncfg), 1)
 db = ipf.LsqDB("", basis, configs)
 Y, W, Icfg = collect_observations(db, _fix_weights(dict(bench.WEIGHTS)), ipf.OneBody(bench.E0))
 Irows, _ = _select(db, Y, W, Icfg, None, None)
