@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + ["-c", src, "-o", obj]
+        cmd = [_nvcc(), "-ccbin", ccbin] + NVCC_FLAGS + os.environ.get("IPF_NVCC_DEFS", "").split() + ["-c", src, "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, p in procs:

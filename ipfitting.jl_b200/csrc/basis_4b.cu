@@ -49,7 +49,10 @@ namespace {
 
 constexpr int Q_NG = 4;                     // functions per staged output group
 constexpr int Q_GLD = 3 * Q_NG + 2;         // doubles per staged row of g: (gx, gy, gz) x 4, pad 2 (two-way conflicts at most)
-constexpr int Q_STAGE = 32 * Q_GLD + Q_NG * 32;     // doubles per worker: g rows, then e[function][row]
+constexpr int Q_ELD = 34;                   // stride of e[function][.]: the four e columns of a column-sum load hit distinct
+                                            // banks (stride 32 made them collide: 8 wavefronts per load instead of 2, 17 %
+                                            // of the kernel's shared-memory traffic, which is what bounds phase 2)
+constexpr int Q_STAGE = 32 * Q_GLD + Q_NG * Q_ELD;  // doubles per worker: g rows, then e[function][row]
 constexpr int Q_THREADS = 32 * G4_NW;
 constexpr size_t Q_SMEM = sizeof(double) * ((size_t)G4_NROWS * 32 + 2 * (size_t)(G4_D + 1) * 32 + (size_t)G4_NW * Q_STAGE);
 static_assert(Q_NG == 4, "the flush maps 5 rows x 6 double2 onto a warp and 16 columns onto a half warp");
@@ -128,7 +131,7 @@ __device__ __forceinline__ void q_flush(const Site4Args& A, const double* __rest
     }
     const int col = lane & 15, half = lane >> 4;
     // column of the staged group: 0..11 = g of function col / 3, 12..15 = e of function col - 12
-    const double* cp = col < 3 * Q_NG ? wstage + col : wstage + 32 * Q_GLD + (col - 3 * Q_NG) * 32;
+    const double* cp = col < 3 * Q_NG ? wstage + col : wstage + 32 * Q_GLD + (col - 3 * Q_NG) * Q_ELD;
     const int cstride = col < 3 * Q_NG ? Q_GLD : 1;
     const int f = col < 3 * Q_NG ? col / 3 : col - 3 * Q_NG;
     const int d = col < 3 * Q_NG ? col - 3 * f : 3;
@@ -231,7 +234,18 @@ __device__ __forceinline__ void q_load_entry(const T4Ent* __restrict__ e, uint4 
     v[0] = __ldg(p); v[1] = __ldg(p + 1); v[2] = __ldg(p + 2); v[3] = __ldg(p + 3);
 }
 
+#ifdef IPF_4B_TIMING
+// development aid (not in the product build): cycles per worker warp, summed over the CTAs
+__device__ unsigned long long g4_tcyc[3][G4_NW];
+#define G4_TICK(slot) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g4_tcyc[slot][threadIdx.x >> 5], (unsigned long long)(clock64() - t_begin)); } while (0)
+#else
+#define G4_TICK(slot) do { } while (0)
+#endif
+
 __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
+#ifdef IPF_4B_TIMING
+    const long long t_begin = clock64();
+#endif
     extern __shared__ __align__(16) double sm[];
     double* M = sm;                                          // [G4_NROWS][32]
     double* xp = sm + (size_t)G4_NROWS * 32;                 // [2][G4_D + 1][32]  x_j^e, then e x_j^(e-1)
@@ -293,7 +307,9 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
             g4_phase1<false>(worker, A.rec4 + k0 * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
         }
     }
+    G4_TICK(0);
     __syncthreads();
+    G4_TICK(1);
 
     // ---- phase 2: basis functions of this worker, entry by entry; 4 scratch columns per staged group
     const char* Mb = reinterpret_cast<const char*>(M + lane);
@@ -342,7 +358,7 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
             myrow[3 * f] = fma(radial, Rj0, fma(T1, E1[0], T2 * E2[0]));
             myrow[3 * f + 1] = fma(radial, Rj1, fma(T1, E1[1], T2 * E2[1]));
             myrow[3 * f + 2] = fma(radial, Rj2, fma(T1, E1[2], T2 * E2[2]));
-            mye[f * 32] = third * S0;
+            mye[f * Q_ELD] = third * S0;
             S0 = 0.0; S1 = 0.0; T1 = 0.0; T2 = 0.0;
             if (++f == Q_NG) {
                 q_flush(A, wstage, pl0, nrw, sc, pmask, pout);
@@ -351,6 +367,7 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
             }
         }
     }
+    G4_TICK(2);
 }
 
 // ---- host tables --------------------------------------------------------------------------------------------
@@ -503,6 +520,16 @@ void free_tables(void* q) {
 }
 
 }  // namespace
+
+#ifdef IPF_4B_TIMING
+extern "C" int32_t ipf_debug_4b_timing(double* out /* [3][G4_NW] */, int32_t reset) {
+    unsigned long long h[3][G4_NW];
+    if (cudaMemcpyFromSymbol(h, g4_tcyc, sizeof(h)) != cudaSuccess) return -1;
+    for (int a = 0; a < 3; ++a) for (int w = 0; w < G4_NW; ++w) out[a * G4_NW + w] = (double)h[a][w];
+    if (reset) { memset(h, 0, sizeof(h)); cudaMemcpyToSymbol(g4_tcyc, h, sizeof(h)); }
+    return G4_NW;
+}
+#endif
 
 void ipf_basis4b_forget(ipf_ctx* ctx, const ipf_basis* B) {
     for (const BlockDev& b : B->blocks) {
