@@ -722,8 +722,10 @@ __global__ void residual_vec_kernel(const double* __restrict__ A, int64_t ld, in
 }
 
 // partial[chunk][k] = sum over the rows of the chunk of A[r][k] rvec[r]: CTA = ATR_ROWS rows (rvec staged in shared
-// memory), warp w takes the columns k = w, w + 8, ...; lanes stride the rows (coalesced), fixed-order reduction
+// memory) x ATR_COLS columns (blockIdx.y; small systems would otherwise run on a handful of SMs), warp w takes the columns
+// k0 + w, k0 + w + 8, ...; lanes stride the rows (coalesced), fixed-order reduction
 constexpr int ATR_ROWS = 2048;
+constexpr int ATR_COLS = 64;
 __global__ void __launch_bounds__(256) atr_partial_kernel(const double* __restrict__ A, int64_t ld, int64_t Mpad, int n,
                                                           const double* __restrict__ rvec, double* __restrict__ partial) {
     __shared__ double s_r[ATR_ROWS];
@@ -732,7 +734,8 @@ __global__ void __launch_bounds__(256) atr_partial_kernel(const double* __restri
     for (int i = threadIdx.x; i < ATR_ROWS; i += blockDim.x) s_r[i] = i < rows ? rvec[m0 + i] : 0.0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int k = warp; k < n; k += 8) {
+    const int k1 = min(n, (int)(blockIdx.y + 1) * ATR_COLS);
+    for (int k = blockIdx.y * ATR_COLS + warp; k < k1; k += 8) {
         const double* col = A + (int64_t)k * ld + m0;
         double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
         int i = lane;
@@ -1231,7 +1234,8 @@ int32_t ipf_solve_finish(ipf_ctx* ctx, ipf_solver* S, double* c, double* R_out, 
         for (int it = 0; it < kSteps; ++it) {
             ProfScope prof_(ctx, "csne");
             residual_vec_kernel<<<(unsigned)nb, 256, sizeof(double) * n, st>>>(S->A, S->Mpad, S->M, S->Mpad, n, cc, S->rvec);
-            atr_partial_kernel<<<(unsigned)nchunk, 256, 0, st>>>(S->A, S->Mpad, S->Mpad, n, S->rvec, (double*)part);
+            atr_partial_kernel<<<dim3((unsigned)nchunk, (unsigned)((n + ATR_COLS - 1) / ATR_COLS)), 256, 0, st>>>(
+                S->A, S->Mpad, S->Mpad, n, S->rvec, (double*)part);
             atr_reduce_kernel<<<nvb, 256, 0, st>>>((const double*)part, nchunk, n, g);
             IPF_CHECK(ipf_comm_allreduce_dev(ctx, g, (size_t)n));          // sum over the ranks (no-op on one GPU)
             trsv_kernel<<<1, 256, sizeof(double) * n, st>>>(S->L, n, g, 0);
