@@ -1097,7 +1097,8 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
     // shared-memory panel for the trailing update: all rows below the first block, if they fit in 200 KB
     const int pcap = (n - KB > 0 && (size_t)(n - KB) * KB * sizeof(double) <= (size_t)200 * 1024) ? ((n - KB + 1) & ~1) : 0;
     const size_t pbytes = sizeof(double) * (size_t)pcap * KB;
-    if (pbytes > 48 * 1024)
+    // (the kernel also has ~9 KB of static shared memory: the opt-in is needed well below 48 KB of dynamic memory)
+    if (pbytes > 32 * 1024)
         IPF_CUDA(ctx, cudaFuncSetAttribute(chol_lower_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pbytes));
     double h[4] = {0.0, 0.0, 0.0, 0.0};
     bool final_pass = false;

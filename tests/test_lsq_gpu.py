@@ -311,3 +311,20 @@ def test_cond_estimate_is_a_tight_lower_bound(fitcase):
     _, exact = ipf.lsqfit(db, weights=dict(w), E0=-4.0, solver={"solver": "qr", "exact_cond": True})
     assert est["cond_R"] <= exact["cond_R"] * (1.0 + 1e-9)
     assert est["cond_R"] >= 0.8 * exact["cond_R"]
+
+
+@pytest.mark.parametrize("n", [150, 216, 256, 257, 400])
+def test_solve_sizes_around_the_kernel_switches(ctx, n):
+    """Column counts on both sides of the single-CTA / multi-CTA Cholesky switch (n = 256) and of the shared-memory opt-in
+    of the single-CTA kernel (n ~ 170): coefficients against LAPACK on a moderately conditioned random system."""
+    rng = np.random.default_rng(n)
+    M = 4 * n + 37
+    A = np.asfortranarray(rng.standard_normal((M, n)) * np.logspace(0, -3, n)[None, :])
+    x = rng.standard_normal(n)
+    y = A @ x + 1e-3 * rng.standard_normal(M)
+    Pm = _capi.DeviceMatrix(ctx, M, n)
+    Pm.from_host(A)
+    c, R, info = solve_device(ctx, Pm, y, np.ones(M))
+    c_ref = np.linalg.lstsq(A, y, rcond=None)[0]
+    assert np.linalg.norm(c - c_ref) <= 1e-9 * np.linalg.norm(c_ref)
+    Pm.close()
