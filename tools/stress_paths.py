@@ -1,5 +1,6 @@
-"""Randomised agreement of the three 3-body paths (configuration-resident, scratch + gather, table-driven) and the
-two 2-body paths on mixed configuration sets -- development aid, run on a GPU box."""
+"""Randomised agreement of the three 3-body paths (configuration-resident, scratch + gather, table-driven), the two
+2-body paths and the two 4-body paths (moment-factorised, table-driven) on mixed configuration sets -- development aid,
+run on a GPU box."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -20,8 +21,13 @@ for case in range(ncase):
     tr = [f"exp(- (r/{r0} - 1.0))", f"({r0}/r)^3", f"exp(- 1.7 * (r/{r0} - 1.0))"][rng.integers(3)]
     B = ipf.nbpolys(2, ipf.BondAngleDesc(tr, ipf.CosCut(rc2 - 0.8, rc2)), D2) + \
         ipf.nbpolys(3, ipf.BondAngleDesc(tr, ipf.CosCut(rc3 - 0.6, rc3)), D3)
+    D4 = 0
+    if case % 2 == 1:          # every second case carries a 4-body block (the table-driven 4-body kernel is slow: small cutoff)
+        D4 = int(rng.integers(1, 7))
+        rc4 = float(rng.uniform(1.2, 1.7)) * r0
+        B = B + ipf.nbpolys(4, ipf.BondAngleDesc(tr, ipf.CosCut(rc4 - 0.5, rc4)), D4)
     configs = []
-    big = rng.random() < 0.15                      # sometimes more than 256 configurations / more than 74 atoms
+    big = rng.random() < 0.15 and D4 == 0          # sometimes more than 256 configurations / more than 74 atoms
     for _ in range(int(rng.integers(260, 300)) if (big and D3 <= 6) else int(rng.integers(1, 7))):
         L = int(rng.integers(1, 3))
         d = synth.rattled_configs(sp, L, 1, seed=int(rng.integers(1 << 30)), calc=synth.PairPotential(r0),
@@ -48,7 +54,7 @@ for case in range(ncase):
     e0 = (np.abs(out[0] - ref) / scale).max(); e2 = (np.abs(out[2] - ref) / scale).max()
     worst = max(worst, e0, e2)
     flag = "" if max(e0, e2) < 1e-9 else "   <-- CHECK"
-    print(f"case {case:3d} {sp:2s} D2={D2:2d} D3={D3:2d} ncfg={len(configs)} nat={[len(c.at) for c in configs][:8]} "
+    print(f"case {case:3d} {sp:2s} D2={D2:2d} D3={D3:2d} D4={D4} ncfg={len(configs)} nat={[len(c.at) for c in configs][:8]} "
           f"rows={ref.shape[0]} resident-vs-table {e0:.2e} scratch-vs-table {e2:.2e}{flag}")
 print("worst", worst)
 sys.exit(0 if worst < 1e-9 else 1)
