@@ -72,7 +72,11 @@ typedef struct ipf_configs ipf_configs;
  * whose centre atom has atomic number zc and whose N-1 neighbours have exactly the atomic numbers zs[0] <= .. <= zs[N-2]
  * (legs assigned to the variable slots in that order; the monomial sums need only be invariant under exchanges of
  * equal-species slots) and is zero on every other cluster.  zc = 0: species-agnostic, every cluster (zs ignored).
- * Species-resolved runs are evaluated by the table-driven kernel. */
+ * Species-resolved runs are evaluated by the table-driven kernel.
+ * Environment (NBodyIPs EnvIP; the `env` of the README's W5Bdeg12env database, README.md:65): env_t > 0 multiplies the
+ * site function by n_i^env_t, n_i = sum_j fenv(r_ij) over the neighbours of the centre atom, fenv = CosCut(env_rc1,
+ * env_rc2) with env_rc2 <= rc2; the forces and virials include the derivative of n_i.  env_t = 0: plain function.
+ * Environment-dependent runs are evaluated by the table-driven kernel. */
 typedef struct {
     int32_t N;
     int32_t nb;
@@ -83,6 +87,8 @@ typedef struct {
     const uint8_t* mono_exp;
     int32_t zc;
     int32_t zs[4];
+    int32_t env_t;
+    double env_rc1, env_rc2;
 } ipf_block_spec;
 
 /* ---- context ---------------------------------------------------------- */

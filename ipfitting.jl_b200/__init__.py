@@ -6,7 +6,7 @@ from .prototypes import (Atoms, Dat, ENERGY, FORCES, VIRIAL, configtype, observa
 from .datatypes import vec_obs, devec_obs, weighthook, err_weighthook
 from .obsiter import observations
 from .basis import (CosCut, BondAngleDesc, NBPoly, NBodyBasis, nbpolys, bodyorder, degree,
-                    as_basis, rnn, invariant_orbits, species_nbpolys)
+                    as_basis, rnn, invariant_orbits, species_nbpolys, envpolys)
 from .potentials import OneBody, NBodyIP, SumIP
 from .lsq_db import LsqDB, matrows, filter_basis, filter_configs, dbpath
 from .lsq import lsqfit, get_lsq_system, collect_observations

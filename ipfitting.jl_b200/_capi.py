@@ -31,7 +31,8 @@ class BlockSpec(C.Structure):
     _fields_ = [("N", C.c_int32), ("nb", C.c_int32), ("nmono", C.c_int32), ("transform", C.c_int32),
                 ("a", C.c_double), ("r0", C.c_double), ("rc1", C.c_double), ("rc2", C.c_double),
                 ("mono_b", C.POINTER(C.c_int32)), ("mono_exp", C.POINTER(C.c_uint8)),
-                ("zc", C.c_int32), ("zs", C.c_int32 * 4)]
+                ("zc", C.c_int32), ("zs", C.c_int32 * 4), ("env_t", C.c_int32),
+                ("env_rc1", C.c_double), ("env_rc2", C.c_double)]
 
 
 _lib = None
@@ -229,7 +230,8 @@ class DeviceBasis:
             keep += [mb, me]
             zs = (C.c_int32 * 4)(*([int(z) for z in getattr(b, "zs", ())] + [0] * 4)[:4])
             arr[k] = BlockSpec(b.N, b.nb, len(mb), kind, a, r0, rc1, rc2, ptr(mb, C.c_int32), ptr(me, C.c_uint8),
-                               int(getattr(b, "zc", 0)), zs)
+                               int(getattr(b, "zc", 0)), zs, int(getattr(b, "env_t", 0)),
+                               float(getattr(b, "env_rc", (0.0, 0.0))[0]), float(getattr(b, "env_rc", (0.0, 0.0))[1]))
         h = _vp()
         ctx.check(ctx.lib.ipf_basis_create(ctx.h, len(blocks), arr, C.byref(h)))
         self.h = h

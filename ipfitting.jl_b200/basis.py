@@ -181,6 +181,11 @@ class NBPoly:
     # zc = 0: species-agnostic (every cluster, full S_{N-1} symmetry).
     zc: int = 0
     zs: Tuple[int, ...] = ()
+    # environment-dependent function (NBodyIPs `EnvIP`, the `env` of the README's `W5Bdeg12env`, `README.md:65`): the
+    # site function is multiplied by n_i^env_t, n_i = sum_j fenv(r_ij) the smooth coordination number of the centre
+    # atom with fenv = CosCut(env_rc[0], env_rc[1]) (env_rc[1] <= the descriptor's cutoff).  env_t = 0: plain function.
+    env_t: int = 0
+    env_rc: Tuple[float, float] = (0.0, 0.0)
 
     @property
     def degree(self) -> int:
@@ -207,6 +212,20 @@ def nbpolys(N: int, desc: BondAngleDesc, deg: int, species=None) -> List[NBPoly]
     return [NBPoly(N, desc, orb, zc, zs) for orb in invariant_orbits(N, deg, zs)]
 
 
+def envpolys(N: int, desc: BondAngleDesc, deg: int, tmax: int, envcut: CosCut, species=None) -> List[NBPoly]:
+    """Environment-dependent N-body basis: for t = 0..tmax the functions n_i^t * nbpolys(N, desc, deg) (t-major), with the
+    smooth coordination number n_i = sum_j envcut(r_ij).  Builder-defined restatement of NBodyIPs' `envpolys` (the maths is
+    not vendored in the reference; `README.md:65` only names a 5-body `env` database)."""
+    if tmax < 0 or not (envcut.rc2 <= desc.rcut):
+        raise ValueError("tmax >= 0 and the environment cutoff must not exceed the descriptor cutoff")
+    base = nbpolys(N, desc, deg, species)
+    out: List[NBPoly] = []
+    for t in range(tmax + 1):
+        out += [NBPoly(p.N, p.desc, p.orbit, p.zc, p.zs, t, (float(envcut.rc1), float(envcut.rc2)) if t > 0 else (0.0, 0.0))
+                for p in base]
+    return out
+
+
 def species_nbpolys(N: int, desc: BondAngleDesc, deg: int, zlist: Sequence[int]) -> List[NBPoly]:
     """The species-resolved N-body basis of a multi-component system (JuLIP `Atoms.Z`, `src/prototypes.jl:19-25`): one
     run of functions per (centre species, multiset of neighbour species), centre-major, multisets in lexicographic order."""
@@ -231,6 +250,8 @@ class BasisBlock:
     maxdeg: int
     zc: int = 0                # centre species (0 = any)
     zs: Tuple[int, ...] = ()   # sorted neighbour species (empty = any)
+    env_t: int = 0             # power of the smooth coordination number (0 = plain function)
+    env_rc: Tuple[float, float] = (0.0, 0.0)
 
 
 class NBodyBasis:
@@ -250,7 +271,8 @@ class NBodyBasis:
             end = start
             while (end < len(self.polys) and self.polys[end].N == p0.N
                    and self.polys[end].desc == p0.desc and self.polys[end].zc == p0.zc
-                   and self.polys[end].zs == p0.zs):
+                   and self.polys[end].zs == p0.zs and self.polys[end].env_t == p0.env_t
+                   and self.polys[end].env_rc == p0.env_rc):
                 end += 1
             self.blocks.append(self._compile(start, end))
             start = end
@@ -271,7 +293,7 @@ class NBodyBasis:
         return BasisBlock(N=p0.N, desc=p0.desc, col0=start, nb=end - start,
                           mono_b=np.asarray(mb, dtype=np.int32),
                           mono_exp=np.asarray(me, dtype=np.uint8).reshape(-1, MAX_VARS),
-                          maxdeg=maxdeg, zc=p0.zc, zs=tuple(p0.zs))
+                          maxdeg=maxdeg, zc=p0.zc, zs=tuple(p0.zs), env_t=p0.env_t, env_rc=tuple(p0.env_rc))
 
     def __len__(self) -> int:
         return len(self.polys)
@@ -303,6 +325,9 @@ class NBodyBasis:
             if p.zc:
                 e["zc"] = p.zc
                 e["zs"] = list(p.zs)
+            if p.env_t:
+                e["env_t"] = p.env_t
+                e["env_rc"] = list(p.env_rc)
             polys.append(e)
         return {"__id__": "IPFittingB200.NBodyBasis", "descs": descs, "polys": polys}
 
@@ -311,7 +336,8 @@ class NBodyBasis:
         descs = [BondAngleDesc((d["kind"], d["a"], d["r0"]), CosCut(d["rc1"], d["rc2"]))
                  for d in D["descs"]]
         polys = [NBPoly(p["N"], descs[p["desc"]], tuple(tuple(m) for m in p["orbit"]), int(p.get("zc", 0)),
-                        tuple(int(z) for z in p.get("zs", ())))
+                        tuple(int(z) for z in p.get("zs", ())), int(p.get("env_t", 0)),
+                        tuple(float(v) for v in p.get("env_rc", (0.0, 0.0))))
                  for p in D["polys"]]
         return NBodyBasis(polys)
 

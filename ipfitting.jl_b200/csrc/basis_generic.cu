@@ -94,6 +94,9 @@ struct GenArgs {
     const int32_t* pj;
     int zc, zs[4];
     const uint8_t* mono_exp_var[4];
+    // environment-dependent block (env_t > 0): site function times n_i^env_t, n_i = sum_j CosCut(env_rc1, env_rc2)(r_ij)
+    int env_t;
+    double env_rc1, env_rc2;
 };
 
 constexpr int GEN_THREADS = 256;
@@ -287,6 +290,40 @@ __global__ void __launch_bounds__(GEN_THREADS) site_deriv_generic_kernel(GenArgs
             }
         }
         __syncthreads();
+        if (A.env_t > 0) {
+            // ---- phase A2: environment factor.  Per (function, centre atom): n_i and V0 = sum of the energy shares of
+            // its pairs; then g_p <- n^t g_p + t n^(t-1) fenv'(r_p) V0 Rhat_p, e_p <- n^t e_p (fixed order)
+            constexpr double kPiD = 3.14159265358979323846;
+            const double we = A.env_rc2 - A.env_rc1;
+            for (int idx = tid; idx < nbu * nat; idx += blockDim.x) {
+                const int bl = idx / nat, at = idx - bl * nat;
+                const int64_t s = a0 + at;
+                const int64_t q0 = A.site_off[s], q1 = A.site_off[s + 1];
+                double* Gb = G + (size_t)bl * A.maxpairs * 4;
+                double ni = 0.0, V0 = 0.0;
+                for (int64_t p = q0; p < q1; ++p) {
+                    const double r = 1.0 / A.rec[(int64_t)A.rs * p + 3];
+                    if (r <= A.env_rc1) ni += 1.0;
+                    else if (r < A.env_rc2) ni += 0.5 * (1.0 + cos(kPiD * (r - A.env_rc1) / we));
+                    V0 += Gb[(p - P0) * 4 + 3];
+                }
+                double nt = 1.0, ntm1 = 1.0;
+                for (int k = 0; k < A.env_t; ++k) { ntm1 = nt; nt *= ni; }
+                ntm1 *= (double)A.env_t;
+                for (int64_t p = q0; p < q1; ++p) {
+                    const double* rc = A.rec + (int64_t)A.rs * p;
+                    const double r = 1.0 / rc[3];
+                    double c = 0.0;
+                    if (r > A.env_rc1 && r < A.env_rc2) c = ntm1 * (-0.5 * kPiD / we * sin(kPiD * (r - A.env_rc1) / we)) * V0;
+                    double* g = Gb + (p - P0) * 4;
+                    g[0] = nt * g[0] + c * rc[0];
+                    g[1] = nt * g[1] + c * rc[1];
+                    g[2] = nt * g[2] + c * rc[2];
+                    g[3] = nt * g[3];
+                }
+            }
+            __syncthreads();
+        }
         // ---- phase B: deterministic gather into Psi ----
         const int64_t rE = A.rowE[c], rF = A.rowF[c], rV = A.rowV[c];
         if (rF) {
@@ -402,6 +439,7 @@ int ipf_assemble_block_generic(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev
     A.Psi = Psi->d; A.ld = Psi->ld; A.col0 = blk.col0; A.scratch = (double*)scr; A.counter = (int*)cnt;
     A.Z = ch.Z.p; A.pj = nl.pj.p; A.zc = blk.zc;
     for (int t = 0; t < 4; ++t) { A.zs[t] = blk.zs[t]; A.mono_exp_var[t] = blk.mono_exp_var[t]; }
+    A.env_t = blk.env_t; A.env_rc1 = blk.env_rc1; A.env_rc2 = blk.env_rc2;
     if (ctx->profiling) {
         // algorithmic work counter: unordered clusters sum_i C(n_i, N-1) (roofline numerator)
         static const char* cnames[6] = {"", "", "count:clusters_2b", "count:clusters_3b", "count:clusters_4b", "count:clusters_5b"};

@@ -197,6 +197,11 @@ int32_t ipf_basis_create(ipf_ctx* ctx, int32_t nblocks, const ipf_block_spec* bl
         b.a = s.a; b.r0 = s.r0; b.rc1 = s.rc1; b.rc2 = s.rc2; b.col0 = col;
         if (s.zc < 0) { delete B; return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: negative species", k); }
         b.zc = s.zc;
+        if (s.env_t < 0 || (s.env_t > 0 && !(s.env_rc1 > 0.0 && s.env_rc2 > s.env_rc1 && s.env_rc2 <= s.rc2))) {
+            delete B;
+            return ipf_set_error(ctx, IPF_EINVAL, "ipf_basis_create: block %d: environment cutoff must satisfy 0 < rc1 < rc2 <= descriptor cutoff", k);
+        }
+        b.env_t = s.env_t; b.env_rc1 = s.env_t > 0 ? s.env_rc1 : 0.0; b.env_rc2 = s.env_t > 0 ? s.env_rc2 : 0.0;
         for (int t = 0; t < 4; ++t) b.zs[t] = (s.zc > 0 && t < nx) ? s.zs[t] : 0;
         for (int t = 0; s.zc > 0 && t < nx; ++t)
             if (b.zs[t] <= 0 || (t > 0 && b.zs[t] < b.zs[t - 1])) {
@@ -543,9 +548,10 @@ int32_t ipf_assemble_configs(ipf_ctx* ctx, const ipf_basis* basis, const ipf_con
             for (size_t k2 = 0; k2 < basis->blocks.size(); ++k2)
                 if (basis->blocks[k2].rc2 == rc) {
                     bool handled = false;
-                    if (basis->blocks[k2].zc > 0) {
-                        // species-resolved run: table-driven kernel (the specialised kernels assume every cluster)
-                        if (!ch->has_Z)
+                    if (basis->blocks[k2].zc > 0 || basis->blocks[k2].env_t > 0) {
+                        // species-resolved / environment-dependent run: table-driven kernel (the specialised kernels
+                        // assume every cluster and the plain site function)
+                        if (basis->blocks[k2].zc > 0 && !ch->has_Z)
                             return ipf_set_error(ctx, IPF_EINVAL, "a species-resolved basis block needs the atomic numbers Z");
                         IPF_CHECK(ipf_assemble_block_generic(ctx, basis->blocks[k2], *ch, nl, Psi));
                         continue;

@@ -78,6 +78,9 @@ struct BlockDev {
     // of its species the exponent table with slot s moved to position 0 (the kernels pin the own leg to slot 0)
     int zc = 0, zs[4] = {0, 0, 0, 0};
     uint8_t* mono_exp_var[4] = {nullptr, nullptr, nullptr, nullptr};
+    // environment-dependent block: site function times n_i^env_t, n_i = sum_j CosCut(env_rc1, env_rc2)(r_ij)
+    int env_t = 0;
+    double env_rc1 = 0.0, env_rc2 = 0.0;
 };
 
 struct ipf_basis {

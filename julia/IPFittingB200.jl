@@ -21,6 +21,7 @@ struct BlockSpec            # mirrors ipf_block_spec
    a::Float64; r0::Float64; rc1::Float64; rc2::Float64
    mono_b::Ptr{Int32}; mono_exp::Ptr{UInt8}
    zc::Int32; zs::NTuple{4, Int32}     # species-resolved run: centre species, sorted neighbour species (zc = 0: any)
+   env_t::Int32; env_rc1::Float64; env_rc2::Float64   # environment factor n_i^env_t, n_i = sum_j CosCut(env_rc1, env_rc2)(r_ij)
 end
 
 mutable struct Ctx
@@ -86,7 +87,8 @@ function blockspecs(basis)
       p0 = polys[start]
       stop = start
       while stop < length(polys) && polys[stop + 1]["N"] == p0["N"] && polys[stop + 1]["desc"] == p0["desc"] &&
-            get(polys[stop + 1], "zc", 0) == get(p0, "zc", 0) && get(polys[stop + 1], "zs", Int[]) == get(p0, "zs", Int[])
+            get(polys[stop + 1], "zc", 0) == get(p0, "zc", 0) && get(polys[stop + 1], "zs", Int[]) == get(p0, "zs", Int[]) &&
+            get(polys[stop + 1], "env_t", 0) == get(p0, "env_t", 0) && get(polys[stop + 1], "env_rc", []) == get(p0, "env_rc", [])
          stop += 1
       end
       nv = (p0["N"] - 1) + (p0["N"] - 1) * (p0["N"] - 2) ÷ 2
@@ -101,7 +103,8 @@ function blockspecs(basis)
       push!(specs, BlockSpec(Int32(p0["N"]), Int32(stop - start + 1), Int32(length(mono_b)), Int32(d["kind"]),
                              Float64(d["a"]), Float64(d["r0"]), Float64(d["rc1"]), Float64(d["rc2"]),
                              pointer(mono_b), pointer(mono_exp),
-                             Int32(get(p0, "zc", 0)), ntuple(i -> Int32(get(get(p0, "zs", Int[]), i, 0)), 4)))
+                             Int32(get(p0, "zc", 0)), ntuple(i -> Int32(get(get(p0, "zs", Int[]), i, 0)), 4),
+                             Int32(get(p0, "env_t", 0)), Float64(get(p0, "env_rc", [0.0, 0.0])[1]), Float64(get(p0, "env_rc", [0.0, 0.0])[2])))
       start = stop + 1
    end
    return specs, keep

@@ -158,6 +158,10 @@ typedef struct {
      * N-1 neighbours have exactly the (sorted) species zs, the legs assigned to the variable slots in species order
      * (legs of equal species in enumeration order: the polynomial is symmetric in them).  zc = 0: every cluster. */
     int zc, zs[IPFO_MAX_LEGS];
+    /* environment-dependent block (NBodyIPs EnvIP as recalled; README.md:65 names a 5-body `env` database): the site
+     * function is multiplied by n_i^env_t with n_i = sum_j fenv(r_ij), fenv = CosCut(env_rc1, env_rc2).  env_t = 0: none. */
+    int env_t;
+    double env_rc1, env_rc2;
 } block_t;
 
 typedef struct {
@@ -167,8 +171,17 @@ typedef struct {
 
 /* E[nb], F[nb][3*nat] (basis-major), V[nb][9] (row-major 3x3) are ACCUMULATED.
  * what: bit0 = E, bit1 = F, bit2 = V. */
+static double g_unused_scale = 1.0;
+static void eval_cluster_s(const block_t* B, int i, const nbr_t** leg, int what,
+                           int nat, double* E, double* F, double* V, double* scratch, double scale);
 static void eval_cluster(const block_t* B, int i, const nbr_t** leg, int what,
                          int nat, double* E, double* F, double* V, double* scratch) {
+    (void)g_unused_scale;
+    eval_cluster_s(B, i, leg, what, nat, E, F, V, scratch, 1.0);
+}
+/* scale: common factor of the cluster's contribution (n_i^t of an environment-dependent block) */
+static void eval_cluster_s(const block_t* B, int i, const nbr_t** leg, int what,
+                           int nat, double* E, double* F, double* V, double* scratch, double scale) {
     const int nx = B->N - 1;
     const int npair = nx * (nx - 1) / 2;
     const int nv = nx + npair;
@@ -196,8 +209,9 @@ static void eval_cluster(const block_t* B, int i, const nbr_t** leg, int what,
     for (int a = 0; a < nx; ++a) {
         double p = 1.0;
         for (int c = 0; c < nx; ++c) if (c != a) p *= leg[c]->fc;
-        FCwo[a] = p;
+        FCwo[a] = p * scale;
     }
+    FC *= scale;
     /* P[b], dP[b][v] */
     double* P = scratch;
     double* dP = scratch + B->nb;
@@ -250,8 +264,8 @@ static void eval_cluster(const block_t* B, int i, const nbr_t** leg, int what,
 
 /* species rule for one unordered cluster: returns without contribution when the neighbour species do not match */
 static void eval_cluster_z(const block_t* B, const int32_t* Z, int i, const nbr_t** leg, int what,
-                           int nat, double* E, double* F, double* V, double* scratch) {
-    if (B->zc == 0 || Z == NULL) { eval_cluster(B, i, leg, what, nat, E, F, V, scratch); return; }
+                           int nat, double* E, double* F, double* V, double* scratch, double scale) {
+    if (B->zc == 0 || Z == NULL) { eval_cluster_s(B, i, leg, what, nat, E, F, V, scratch, scale); return; }
     const int nx = B->N - 1;
     const nbr_t* srt[IPFO_MAX_LEGS];
     for (int a = 0; a < nx; ++a) srt[a] = leg[a];
@@ -262,7 +276,38 @@ static void eval_cluster_z(const block_t* B, const int32_t* Z, int i, const nbr_
         srt[c + 1] = t;
     }
     for (int a = 0; a < nx; ++a) if (Z[srt[a]->j] != B->zs[a]) return;
-    eval_cluster(B, i, srt, what, nat, E, F, V, scratch);
+    eval_cluster_s(B, i, srt, what, nat, E, F, V, scratch, scale);
+}
+
+/* all clusters of site i (neighbours base[0..n)) */
+static void site_clusters(const block_t* B, const int32_t* Z, int i, const nbr_t* base, int n, int what, int nat,
+                          double* E, double* F, double* V, double* scratch, double scale) {
+    const int nx = B->N - 1;
+    const nbr_t* leg[IPFO_MAX_LEGS];
+    if (nx == 1) {
+        for (int a = 0; a < n; ++a) { leg[0] = base + a; eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch, scale); }
+    } else if (nx == 2) {
+        for (int a = 0; a < n; ++a)
+            for (int c = a + 1; c < n; ++c) {
+                leg[0] = base + a; leg[1] = base + c;
+                eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch, scale);
+            }
+    } else if (nx == 3) {
+        for (int a = 0; a < n; ++a)
+            for (int c = a + 1; c < n; ++c)
+                for (int e = c + 1; e < n; ++e) {
+                    leg[0] = base + a; leg[1] = base + c; leg[2] = base + e;
+                    eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch, scale);
+                }
+    } else if (nx == 4) {
+        for (int a = 0; a < n; ++a)
+            for (int c = a + 1; c < n; ++c)
+                for (int e = c + 1; e < n; ++e)
+                    for (int g = e + 1; g < n; ++g) {
+                        leg[0] = base + a; leg[1] = base + c; leg[2] = base + e; leg[3] = base + g;
+                        eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch, scale);
+                    }
+    }
 }
 
 static void eval_config_block_par(const block_t* B, int nat, const double* pos, const double* cell,
@@ -314,30 +359,45 @@ static void eval_config_block_par(const block_t* B, int nat, const double* pos, 
         const int64_t p0 = soff[i], p1 = soff[i + 1];
         const int n = (int)(p1 - p0);
         const nbr_t* base = nb + p0;
-        const nbr_t* leg[IPFO_MAX_LEGS];
-        if (nx == 1) {
-            for (int a = 0; a < n; ++a) { leg[0] = base + a; eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch); }
-        } else if (nx == 2) {
-            for (int a = 0; a < n; ++a)
-                for (int c = a + 1; c < n; ++c) {
-                    leg[0] = base + a; leg[1] = base + c;
-                    eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch);
-                }
-        } else if (nx == 3) {
-            for (int a = 0; a < n; ++a)
-                for (int c = a + 1; c < n; ++c)
-                    for (int e = c + 1; e < n; ++e) {
-                        leg[0] = base + a; leg[1] = base + c; leg[2] = base + e;
-                        eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch);
-                    }
-        } else if (nx == 4) {
-            for (int a = 0; a < n; ++a)
-                for (int c = a + 1; c < n; ++c)
-                    for (int e = c + 1; e < n; ++e)
-                        for (int g = e + 1; g < n; ++g) {
-                            leg[0] = base + a; leg[1] = base + c; leg[2] = base + e; leg[3] = base + g;
-                            eval_cluster_z(B, Z, i, leg, what, nat, E, F, V, scratch);
+        if (B->env_t <= 0) {
+            site_clusters(B, Z, i, base, n, what, nat, E, F, V, scratch, 1.0);
+        } else {
+            /* environment factor n_i^t: V0_b(i) from an energy-only pass, then the scaled clusters and the derivative of
+             * the factor, dV = t n^(t-1) fenv'(r_ij) Rhat_ij V0_b(i) for every neighbour inside the environment cutoff */
+            double ni = 0.0;
+            const double we = B->env_rc2 - B->env_rc1;
+            for (int a = 0; a < n; ++a) {
+                const double r = base[a].r;
+                if (r <= B->env_rc1) ni += 1.0;
+                else if (r < B->env_rc2) ni += 0.5 * (1.0 + cos(IPFO_PI * (r - B->env_rc1) / we));
+            }
+            double nt = 1.0, ntm1 = 1.0;
+            for (int k = 0; k < B->env_t; ++k) { ntm1 = nt; nt *= ni; }
+            ntm1 *= (double)B->env_t;
+            double* V0 = (double*)calloc((size_t)B->nb, sizeof(double));
+            site_clusters(B, Z, i, base, n, 1, nat, V0, NULL, NULL, scratch, 1.0);
+            site_clusters(B, Z, i, base, n, what, nat, E, F, V, scratch, nt);
+            if (what & 6) {
+                for (int a = 0; a < n; ++a) {
+                    const nbr_t* L = base + a;
+                    if (!(L->r > B->env_rc1 && L->r < B->env_rc2)) continue;
+                    const double dfe = -0.5 * IPFO_PI / we * sin(IPFO_PI * (L->r - B->env_rc1) / we);
+                    for (int b = 0; b < B->nb; ++b) {
+                        const double c = ntm1 * dfe * V0[b];
+                        const double dV[3] = { c * L->Rh[0], c * L->Rh[1], c * L->Rh[2] };
+                        if (what & 2) {
+                            double* Fb = F + (size_t)b * 3 * nat;
+                            for (int d = 0; d < 3; ++d) { Fb[3 * L->j + d] -= dV[d]; Fb[3 * i + d] += dV[d]; }
                         }
+                        if (what & 4) {
+                            double* Vb = V + (size_t)b * 9;
+                            for (int p = 0; p < 3; ++p)
+                                for (int q = 0; q < 3; ++q) Vb[3 * p + q] -= dV[p] * L->R[q];
+                        }
+                    }
+                }
+            }
+            free(V0);
         }
     }
     free(scratch);
@@ -379,13 +439,16 @@ int32_t ipfo_assemble_block_z(int32_t N, int32_t nb, int32_t nmono, const int32_
                               const double* pos, const double* cell, const uint8_t* pbc,
                               const int64_t* rowE, const int64_t* rowF, const int64_t* rowV,
                               int64_t col0, double* Psi, int64_t ld, int32_t mode, int32_t nthreads,
-                              const int32_t* Zall, int32_t zc, const int32_t* zs) {
+                              const int32_t* Zall, int32_t zc, const int32_t* zs,
+                              int32_t env_t, double env_rc1, double env_rc2) {
     if (N < 2 || N > 5) return -1;
     block_t B;
     B.N = N; B.nb = nb; B.nmono = nmono; B.mono_b = mono_b; B.mono_exp = mono_exp;
     B.D.transform = transform; B.D.a = a; B.D.r0 = r0; B.D.rc1 = rc1; B.D.rc2 = rc2;
     B.zc = (Zall != NULL && zs != NULL) ? zc : 0;
     for (int k = 0; k < IPFO_MAX_LEGS; ++k) B.zs[k] = (B.zc && k < N - 1) ? zs[k] : 0;
+    B.env_t = env_t; B.env_rc1 = env_rc1; B.env_rc2 = env_rc2;
+    if (env_t > 0 && !(env_rc1 > 0.0 && env_rc2 > env_rc1 && env_rc2 <= rc2)) return -1;
 
     /* task list */
     const int tasks_per_cfg = mode ? 3 : 1;
@@ -494,7 +557,7 @@ int32_t ipfo_assemble_block(int32_t N, int32_t nb, int32_t nmono, const int32_t*
                             const int64_t* rowE, const int64_t* rowF, const int64_t* rowV,
                             int64_t col0, double* Psi, int64_t ld, int32_t mode, int32_t nthreads) {
     return ipfo_assemble_block_z(N, nb, nmono, mono_b, mono_exp, transform, a, r0, rc1, rc2, ncfg, atom_off, pos, cell,
-                                 pbc, rowE, rowF, rowV, col0, Psi, ld, mode, nthreads, NULL, 0, NULL);
+                                 pbc, rowE, rowF, rowV, col0, Psi, ld, mode, nthreads, NULL, 0, NULL, 0, 0.0, 0.0);
 }
 
 /* Single-config convenience for tests: evaluates one block, returns dense
@@ -503,12 +566,15 @@ int32_t ipfo_eval_config_z(int32_t N, int32_t nb, int32_t nmono, const int32_t* 
                            const uint8_t* mono_exp, int32_t transform, double a, double r0,
                            double rc1, double rc2, int32_t nat, const double* pos,
                            const double* cell, const uint8_t* pbc, double* E, double* F, double* V,
-                           const int32_t* Z, int32_t zc, const int32_t* zs) {
+                           const int32_t* Z, int32_t zc, const int32_t* zs,
+                           int32_t env_t, double env_rc1, double env_rc2) {
     block_t B;
     B.N = N; B.nb = nb; B.nmono = nmono; B.mono_b = mono_b; B.mono_exp = mono_exp;
     B.D.transform = transform; B.D.a = a; B.D.r0 = r0; B.D.rc1 = rc1; B.D.rc2 = rc2;
     B.zc = (Z != NULL && zs != NULL) ? zc : 0;
     for (int k = 0; k < IPFO_MAX_LEGS; ++k) B.zs[k] = (B.zc && k < N - 1) ? zs[k] : 0;
+    B.env_t = env_t; B.env_rc1 = env_rc1; B.env_rc2 = env_rc2;
+    if (env_t > 0 && !(env_rc1 > 0.0 && env_rc2 > env_rc1 && env_rc2 <= rc2)) return -1;
     memset(E, 0, sizeof(double) * (size_t)nb);
     memset(F, 0, sizeof(double) * (size_t)nb * 3 * (size_t)nat);
     memset(V, 0, sizeof(double) * (size_t)nb * 9);
@@ -521,7 +587,7 @@ int32_t ipfo_eval_config(int32_t N, int32_t nb, int32_t nmono, const int32_t* mo
                          double rc1, double rc2, int32_t nat, const double* pos,
                          const double* cell, const uint8_t* pbc, double* E, double* F, double* V) {
     return ipfo_eval_config_z(N, nb, nmono, mono_b, mono_exp, transform, a, r0, rc1, rc2, nat, pos, cell, pbc, E, F, V,
-                              NULL, 0, NULL);
+                              NULL, 0, NULL, 0, 0.0, 0.0);
 }
 
 int32_t ipfo_num_threads(void) {

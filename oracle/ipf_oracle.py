@@ -36,13 +36,13 @@ def lib():
                                           C.c_int64, i64p, dp, dp, u8p, i64p, i64p, i64p,
                                           C.c_int64, dp, C.c_int64, C.c_int32, C.c_int32]
         L.ipfo_assemble_block_z.restype = C.c_int32
-        L.ipfo_assemble_block_z.argtypes = L.ipfo_assemble_block.argtypes + [ip, C.c_int32, ip]
+        L.ipfo_assemble_block_z.argtypes = L.ipfo_assemble_block.argtypes + [ip, C.c_int32, ip, C.c_int32, C.c_double, C.c_double]
         L.ipfo_eval_config.restype = C.c_int32
         L.ipfo_eval_config.argtypes = [C.c_int32, C.c_int32, C.c_int32, ip, u8p, C.c_int32,
                                        C.c_double, C.c_double, C.c_double, C.c_double,
                                        C.c_int32, dp, dp, u8p, dp, dp, dp]
         L.ipfo_eval_config_z.restype = C.c_int32
-        L.ipfo_eval_config_z.argtypes = L.ipfo_eval_config.argtypes + [ip, C.c_int32, ip]
+        L.ipfo_eval_config_z.argtypes = L.ipfo_eval_config.argtypes + [ip, C.c_int32, ip, C.c_int32, C.c_double, C.c_double]
         L.ipfo_num_threads.restype = C.c_int32
         _LIB = L
     return _LIB
@@ -84,7 +84,8 @@ def eval_config(block, at):
                                   kind, a, r0, rc1, rc2, nat, _p(X, C.c_double),
                                   _p(cell, C.c_double), _p(pbc, C.c_uint8),
                                   _p(E, C.c_double), _p(F, C.c_double), _p(V, C.c_double),
-                                  _p(Z, C.c_int32), int(block.zc), _p(zs, C.c_int32))
+                                  _p(Z, C.c_int32), int(block.zc), _p(zs, C.c_int32),
+                                  int(block.env_t), float(block.env_rc[0]), float(block.env_rc[1]))
     assert rc == 0
     return E, F, V.reshape(-1, 3, 3)
 
@@ -122,7 +123,8 @@ def assemble(basis, configs, rowE, rowF, rowV, nrows, mode=0, nthreads=0):
                                      _p(pos, C.c_double), _p(cell, C.c_double), _p(pbc, C.c_uint8),
                                      _p(rowE, C.c_int64), _p(rowF, C.c_int64), _p(rowV, C.c_int64),
                                      blk.col0, _p(Psi, C.c_double), nrows, mode, nthreads,
-                                     _p(Zall, C.c_int32), int(blk.zc), _p(zs, C.c_int32))
+                                     _p(Zall, C.c_int32), int(blk.zc), _p(zs, C.c_int32),
+                                     int(blk.env_t), float(blk.env_rc[0]), float(blk.env_rc[1]))
         assert rc == 0
     return Psi
 

@@ -307,3 +307,18 @@ def test_species_resolved_blocks(ctx):
     assert np.abs(ref).max(axis=0).min() > 0          # every column sees clusters of its species tuple
     # a basis with a species-resolved run needs Z: the specialised (species-agnostic) kernels do not
     assert [b.zc for b in db.basis.blocks][:2] == [6, 6]
+
+
+def test_environment_dependent_blocks(ctx):
+    """BASELINE config 4 in miniature (`README.md:65`, `W5Bdeg12env`): W bcc cells with vacancies, environment-dependent
+    3-, 4- and 5-body runs (site function times n_i^t, t = 0..2) against the oracle, mixed with plain runs."""
+    r0 = ipf.rnn("W")
+    d3 = ipf.BondAngleDesc(f"exp(- (r/{r0} - 1.0))", ipf.CosCut(1.5 * r0 - 0.6, 1.5 * r0))
+    d5 = ipf.BondAngleDesc(f"exp(- (r/{r0} - 1.0))", ipf.CosCut(1.25 * r0 - 0.4, 1.25 * r0))
+    env = ipf.CosCut(1.05 * r0, 1.2 * r0)
+    configs = synth.rattled_configs("W", 2, 3, seed=31, calc=synth.PairPotential(r0), vacancies=2)
+    B = (ipf.nbpolys(2, d3, 5) + ipf.envpolys(3, d3, 3, 2, ipf.CosCut(1.1 * r0, 1.45 * r0))
+         + ipf.envpolys(4, d5, 2, 1, env) + ipf.envpolys(5, d5, 2, 1, env))
+    db, ref = _check(B, configs, ctx)
+    assert [b.env_t for b in db.basis.blocks] == [0, 0, 1, 2, 0, 1, 0, 1]
+    assert np.abs(ref).max(axis=0).min() > 0

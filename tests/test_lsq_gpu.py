@@ -328,3 +328,37 @@ def test_solve_sizes_around_the_kernel_switches(ctx, n):
     c_ref = np.linalg.lstsq(A, y, rcond=None)[0]
     assert np.linalg.norm(c - c_ref) <= 1e-9 * np.linalg.norm(c_ref)
     Pm.close()
+
+
+def test_env_fit_with_configtype_weights(ctx):
+    """BASELINE config 4 in miniature: W bcc cells with and without vacancies (configtypes "rand" / "vacancy"), an
+    environment-dependent 3- and 4-body basis, per-configtype weights (`src/lsq.jl:137-146`); labels generated from a known
+    coefficient vector through the ORACLE's matrix: the weighted fit recovers it and the error table has one entry per
+    configtype."""
+    r0 = ipf.rnn("W")
+    d3 = ipf.BondAngleDesc(f"exp(- (r/{r0} - 1.0))", ipf.CosCut(1.5 * r0 - 0.6, 1.5 * r0))
+    d4 = ipf.BondAngleDesc(f"exp(- (r/{r0} - 1.0))", ipf.CosCut(1.25 * r0 - 0.4, 1.25 * r0))
+    B = ipf.NBodyBasis(ipf.nbpolys(2, d3, 6) + ipf.envpolys(3, d3, 2, 1, ipf.CosCut(1.1 * r0, 1.45 * r0))
+                       + ipf.envpolys(4, d4, 2, 1, ipf.CosCut(1.05 * r0, 1.2 * r0)))
+    blank = synth.rattled_configs("W", 2, 12, seed=41, calc=synth.PairPotential(r0), vacancies=2)
+    assert {d.configtype for d in blank} == {"rand", "vacancy"}
+    from ipfitting_jl_b200.lsq_db import _alloc_rows
+    nrows = _alloc_rows(blank)
+    r = rows_for(blank)
+    ref = O.assemble(B, blank, r["E"], r["F"], r["V"], nrows)
+    rng = np.random.default_rng(5)
+    c_true = rng.standard_normal(len(B)) / (1.0 + np.arange(len(B)))
+    y = ref @ c_true
+    configs = []
+    for d in blank:
+        configs.append(ipf.Dat(d.at, d.configtype, E=y[d.rows["E"][0]],
+                               F=y[d.rows["F"][0]:d.rows["F"][0] + d.rows["F"][1]].reshape(-1, 3),
+                               V=y[d.rows["V"][0]:d.rows["V"][0] + 6]))
+    db = LsqDB("", B, configs, ctx=ctx)
+    assert psi_errors(db.Psi, ref, configs) <= PSI_RTOL
+    w = {"default": {"E": 10.0, "F": 1.0, "V": 1.0}, "vacancy": {"E": 40.0, "F": 3.0, "V": 0.5}}
+    IP, info = ipf.lsqfit(db, weights={k: dict(v) for k, v in w.items()}, E0=0.0, error_table=True)
+    assert np.linalg.norm(info["c"] - c_true) <= max(1e-8, 100 * info["cond_R"] * 2.2e-16) * np.linalg.norm(c_true)
+    assert set(info["errors"]["rmse"]) == {"rand", "vacancy", "set"}
+    c_ref = LO.lsqfit_qr(ref, configs, w, E0=0.0)[0]
+    assert np.linalg.norm(info["c"] - c_ref) <= max(1e-8, 100 * info["cond_R"] * 2.2e-16) * np.linalg.norm(c_ref)

@@ -150,3 +150,37 @@ def test_species_forces_match_finite_differences():
             am.X[k, d] -= h
             fd = -(O.eval_config(blk, ap)[0] - O.eval_config(blk, am)[0]) / (2 * h)
             assert np.allclose(fd, F[:, 3 * k + d], rtol=1e-6, atol=1e-7 * np.abs(F).max())
+
+
+# ---------------------------------------------------------------- environment-dependent blocks
+def test_env_forces_match_finite_differences():
+    """n_i^t-weighted functions (`basis.envpolys`): forces and virials are the derivatives of the energies, including the
+    derivative of the smooth coordination number; t = 0 is the plain basis."""
+    at = synth.rattled_configs("W", 2, 1, seed=9, vacancies=2)[0].at
+    r0 = ipf.rnn("W")
+    desc = ipf.BondAngleDesc(f"exp(- (r/{r0} - 1.0))", ipf.CosCut(1.5 * r0 - 0.6, 1.5 * r0))
+    B = ipf.NBodyBasis(ipf.envpolys(3, desc, 3, 2, ipf.CosCut(1.1 * r0, 1.45 * r0)))
+    assert [b.env_t for b in B.blocks] == [0, 1, 2]
+    plain = O.eval_config(ipf.NBodyBasis(ipf.nbpolys(3, desc, 3)).blocks[0], at)
+    E0, F0, V0 = O.eval_config(B.blocks[0], at)
+    assert np.array_equal(E0, plain[0]) and np.array_equal(F0, plain[1])
+    h = 1e-5
+    for blk in B.blocks[1:]:
+        E, F, V = O.eval_config(blk, at)
+        assert np.abs(E).max() > 0 and not np.allclose(E, E0)
+        for (k, d) in ((0, 0), (5, 2), (9, 1)):
+            ap, am = at.copy(), at.copy()
+            ap.X[k, d] += h
+            am.X[k, d] -= h
+            fd = -(O.eval_config(blk, ap)[0] - O.eval_config(blk, am)[0]) / (2 * h)
+            assert np.allclose(fd, F[:, 3 * k + d], rtol=1e-6, atol=1e-7 * np.abs(F).max())
+        for (p, q) in ((0, 0), (2, 1)):
+            def strained(e):
+                Fm = np.eye(3)
+                Fm[q, p] += e
+                a = at.copy()
+                a.X = at.X @ Fm
+                a.cell = at.cell @ Fm
+                return a
+            fd = -(O.eval_config(blk, strained(h))[0] - O.eval_config(blk, strained(-h))[0]) / (2 * h)
+            assert np.allclose(fd, V[:, p, q], rtol=1e-6, atol=1e-7 * np.abs(V).max())
