@@ -78,7 +78,8 @@ struct Site4Args {
     int64_t p0, np;                 // batch pair range
     const double* rec;              // standard pair records (own leg: Rhat, 1/r, x, x', fc, fc')
     int rs;
-    const double* rec4;             // compact neighbour records [Rhat(3), fc, fc x^0..x^D, pad]
+    const double* rec4;             // compact neighbour records [Rhat(3), fc, fc x^0..x^D, pad]; record npairs_all is all zero
+    int64_t npairs_all;             // pairs of the chunk
     const int32_t* psite;
     const int64_t* pbeg;
     const int32_t* pcnt;
@@ -297,14 +298,17 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
         const int64_t kb0 = __shfl_sync(0xffffffffu, k0, 0);
         const int64_t kb1 = __shfl_sync(0xffffffffu, k0 + n, nrw - 1);
         const int nd2 = (int)(kb1 - kb0) * (G4_RS / 2);             // double2 words of the run
-        if (nd2 <= G4_NW * Q_STAGE / 2) {
+        if (nd2 + G4_RS / 2 <= G4_NW * Q_STAGE / 2) {
             const double2* src = reinterpret_cast<const double2*>(A.rec4 + kb0 * G4_RS);
             double2* dst = reinterpret_cast<double2*>(stage);
             for (int q = threadIdx.x; q < nd2; q += Q_THREADS) dst[q] = __ldg(src + q);
+            if (threadIdx.x < G4_RS / 2) dst[nd2 + threadIdx.x] = make_double2(0.0, 0.0);      // the all-zero record
             __syncthreads();
-            g4_phase1<true>(worker, stage + (k0 - kb0) * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
+            g4_phase1<true>(worker, stage + (k0 - kb0) * G4_RS, stage + 2 * (size_t)nd2, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2,
+                            M + lane);
         } else {
-            g4_phase1<false>(worker, A.rec4 + k0 * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2, M + lane);
+            g4_phase1<false>(worker, A.rec4 + k0 * G4_RS, A.rec4 + A.npairs_all * G4_RS, n, (int)(p - k0), Rj0, Rj1, Rj2, E1, E2,
+                             M + lane);
         }
     }
     G4_TICK(0);
@@ -574,6 +578,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     {
         ProfScope prof_(ctx, "pair_record4");
         rec4_kernel<<<(unsigned)((nl.npairs + 127) / 128), 128, 0, st>>>(nl.npairs, rec, rs, (double*)rec4);
+        IPF_CUDA(ctx, cudaMemsetAsync((double*)rec4 + (size_t)nl.npairs * G4_RS, 0, sizeof(double) * G4_RS, st));
         ctx->launches++;
         IPF_CUDA(ctx, cudaGetLastError());
     }
@@ -640,7 +645,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         const int buf = ib & 1;
         Site4Args A;
         A.p0 = nl.h_cfg_pair_off[c0]; A.np = nl.h_cfg_pair_off[c1] - A.p0;
-        A.rec = rec; A.rs = rs; A.rec4 = (const double*)rec4;
+        A.rec = rec; A.rs = rs; A.rec4 = (const double*)rec4; A.npairs_all = nl.npairs;
         A.psite = nl.psite.p; A.pbeg = nl.pbeg.p; A.pcnt = nl.pcnt.p;
         A.ent = T->d_ent;
         for (int w = 0; w <= G4_NW; ++w) { A.wsc[w] = T->wsc[w]; A.went[w] = T->went[w]; }
