@@ -344,7 +344,22 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
         QAcc Q;
 #pragma unroll
         for (int q = 0; q < 2; ++q) { Q.s[q] = 0.0; Q.a1[q] = 0.0; Q.a2[q] = 0.0; Q.b1[q] = 0.0; Q.b2[q] = 0.0; }
-        q_dispatch((w[15] >> 4) & 0x1fu, w, Mb, Q);
+        {
+            // c23 = 0 and 1 are 68 % of the entries and have 1 and 3 terms: compare-and-branch instead of the indirect
+            // branch of the switch (jump-table load + BRX latency per entry)
+            const uint32_t cls = (w[15] >> 4) & 0x1fu;
+            if (cls < 3) {
+                if (cls == 0) q_run<0, 0, false, false>(w, Mb, Q);
+                else if (cls == 1) q_run<0, 0, true, false>(w, Mb, Q);
+                else q_run<0, 0, true, true>(w, Mb, Q);
+            } else if (cls < 6) {
+                if (cls == 3) q_run<1, 0, false, false>(w, Mb, Q);
+                else if (cls == 4) q_run<1, 0, true, false>(w, Mb, Q);
+                else q_run<1, 0, true, true>(w, Mb, Q);
+            } else {
+                q_dispatch(cls, w, Mb, Q);
+            }
+        }
         const double ws = __hiloint2double((int)w[14], 0) * ((Q.s[0] + Q.s[1]) - zs);
         S0 = fma(xa, ws, S0);
         S1 = fma(xd, ws, S1);
