@@ -128,6 +128,10 @@ int32_t ipf_profile_get(ipf_ctx* ctx, const char* name, double* ms, int64_t* cou
 int32_t ipf_comm_unique_id(ipf_ctx* ctx, uint8_t* id /* [IPF_UNIQUE_ID_BYTES] */);
 int32_t ipf_comm_init(ipf_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t* id);
 int32_t ipf_comm_destroy(ipf_ctx* ctx);
+/* paused = 1: the solve stages on this ctx stay rank-local (no exchange inside ipf_solve_gram / finish / residual) until
+ * paused = 0; ipf_comm_allreduce_f64 always exchanges.  Used by the TSQR variant: every rank factors its own rows, the
+ * n x (n+1) blocks [R_p | Q_p^T y] are exchanged once and the stacked system is factored again (src/lsq.jl:468). */
+int32_t ipf_comm_pause(ipf_ctx* ctx, int32_t paused);
 int32_t ipf_comm_size(const ipf_ctx* ctx);
 int32_t ipf_comm_rank(const ipf_ctx* ctx);
 int32_t ipf_comm_allreduce_f64(ipf_ctx* ctx, double* x, int64_t n);

@@ -59,6 +59,7 @@ SIGNATURES = {
     "ipf_comm_unique_id": (C.c_int32, [_vp, _bp]),
     "ipf_comm_init": (C.c_int32, [_vp, C.c_int32, C.c_int32, _bp]),
     "ipf_comm_destroy": (C.c_int32, [_vp]),
+    "ipf_comm_pause": (C.c_int32, [_vp, C.c_int32]),
     "ipf_comm_size": (C.c_int32, [_vp]),
     "ipf_comm_rank": (C.c_int32, [_vp]),
     "ipf_comm_allreduce_f64": (C.c_int32, [_vp, _dp, C.c_int64]),
@@ -184,6 +185,9 @@ class Context:
         if buf.size != 128:
             raise ValueError("the NCCL unique id has 128 bytes")
         self.check(self.lib.ipf_comm_init(self.h, int(nranks), int(rank), ptr(buf, C.c_uint8)))
+
+    def comm_pause(self, paused: bool):
+        self.check(self.lib.ipf_comm_pause(self.h, 1 if paused else 0))
 
     def comm_size(self) -> int:
         return int(self.lib.ipf_comm_size(self.h))

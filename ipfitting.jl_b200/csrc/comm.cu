@@ -57,7 +57,7 @@ int nccl_fail(ipf_ctx* ctx, NcclApi* api, const char* what, int rc) {
 
 // in-place sum over the ranks of n doubles at device address buf, on the ctx stream; no-op without a communicator
 int ipf_comm_allreduce_dev(ipf_ctx* ctx, double* buf, size_t n) {
-    if (!ctx->nccl_comm || ctx->nranks <= 1 || n == 0) return IPF_OK;
+    if (!ctx->nccl_comm || ctx->nranks <= 1 || n == 0 || ctx->comm_paused) return IPF_OK;
     NcclApi* api = nccl_api();
     ProfScope prof_(ctx, "allreduce");
     const int rc = api->AllReduce(buf, buf, n, kNcclFloat64, kNcclSum, (NcclComm)ctx->nccl_comm, ctx->stream);
@@ -108,6 +108,12 @@ int32_t ipf_comm_destroy(ipf_ctx* ctx) {
     return IPF_OK;
 }
 
+int32_t ipf_comm_pause(ipf_ctx* ctx, int32_t paused) {
+    if (!ctx) return IPF_EINVAL;
+    ctx->comm_paused = paused != 0;
+    return IPF_OK;
+}
+
 int32_t ipf_comm_size(const ipf_ctx* ctx) { return ctx ? ctx->nranks : 0; }
 int32_t ipf_comm_rank(const ipf_ctx* ctx) { return ctx ? ctx->rank : 0; }
 
@@ -119,7 +125,11 @@ int32_t ipf_comm_allreduce_f64(ipf_ctx* ctx, double* x, int64_t n) {
     void* d = nullptr;
     IPF_CHECK(ipf_scratch(ctx, 9, sizeof(double) * (size_t)n, &d));
     IPF_CUDA(ctx, cudaMemcpyAsync(d, x, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream));
-    IPF_CHECK(ipf_comm_allreduce_dev(ctx, (double*)d, (size_t)n));
+    const bool paused = ctx->comm_paused;
+    ctx->comm_paused = false;           // an explicit exchange is never paused
+    const int rc_ar = ipf_comm_allreduce_dev(ctx, (double*)d, (size_t)n);
+    ctx->comm_paused = paused;
+    IPF_CHECK(rc_ar);
     IPF_CUDA(ctx, cudaMemcpyAsync(x, d, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream));
     IPF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return IPF_OK;

@@ -58,6 +58,7 @@ struct ipf_ctx {
     const void* gram_tiles_ptr = nullptr;
     void* nccl_comm = nullptr;
     int nranks = 1, rank = 0;
+    bool comm_paused = false;           // ipf_comm_pause: the solve stages run rank-local (first level of a TSQR solve)
 };
 
 struct ipf_matrix {

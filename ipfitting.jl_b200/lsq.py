@@ -383,18 +383,74 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True, factor_solver
 
 
 def solve_device(ctx, Psi_dev, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None, precon=None,
-                 factor_solver=None, reg=None):
+                 factor_solver=None, reg=None, exchange="gram"):
     """Weighted LSQ solve of the device-resident system.  `comm`: a
-    `parallel.Communicator` (rows are sharded over its ranks) or None.  `precon`: (row0, blocks, solver)."""
+    `parallel.Communicator` (rows are sharded over its ranks) or None.  `precon`: (row0, blocks, solver).
+    `exchange`: what the ranks exchange -- "gram" (default: the (n+1)^2 Gram block of every pass is summed) or "tsqr"
+    (every rank factors its own rows, the blocks [R_p | Q_p^T y] are exchanged once and the stacked system is factored
+    again on every rank)."""
     S = _Solver(ctx, Psi_dev, Y, W, Irows, Icols, Dinv)
     try:
         if precon is not None and precon[1]:
             S.apply_precon(*precon)
         if reg is not None and reg[0] is not None and (comm is None or comm.rank == 0):
             S.append_rows(*reg)          # one rank carries the regulariser rows
+        if exchange == "tsqr" and comm is not None and comm.world_size > 1:
+            if factor_solver is not None:
+                raise NotImplementedError("the TSQR exchange is implemented for the :qr solver")
+            return _run_tsqr(S, ctx, comm, Dinv)
         return run_staged(S, comm, ctx.device, want_R, factor_solver, Dinv)
     finally:
         S.close()
+
+
+def _run_tsqr(S, ctx, comm, Dinv):
+    """Row-sharded TSQR with CholeskyQR as the local factorisation: A_p = Q_p R_p on every rank (no exchange), then
+    min |[R_1; ..; R_N] c - [Q_1^T y; ..; Q_N^T y]| on every rank.  One exchange of N n (n + 1) doubles instead of one
+    (n + 1)^2 block per Gram pass; the local factors never see the other ranks' rows, so a rank whose rows alone are rank
+    deficient still contributes a valid (singular) R_p."""
+    paused = comm.attached(ctx)
+    if paused:
+        ctx.comm_pause(True)
+    try:
+        _, Rp, info1 = run_staged(S, None, ctx.device, True, None, None)
+        qty = S.qty()
+        _, ssy_p = S.residual(np.zeros(S.n))           # |y_p|^2 of the local rows
+    finally:
+        if paused:
+            ctx.comm_pause(False)
+    n, N = S.n, comm.world_size
+    buf = np.zeros((N, n, n + 1))
+    buf[comm.rank, :, :n] = np.triu(Rp)
+    buf[comm.rank, :, n] = qty
+    buf = comm.allreduce_numpy(buf)
+    A2 = np.asfortranarray(buf[:, :, :n].reshape(N * n, n))
+    y2 = np.ascontiguousarray(buf[:, :, n].reshape(N * n))
+    P2 = _capi.DeviceMatrix(ctx, N * n, n)
+    try:
+        P2.from_host(A2)
+        S2 = _Solver(ctx, P2, y2, np.ones(N * n), None, None, None)
+        try:
+            if paused:
+                ctx.comm_pause(True)           # the second level is the same on every rank: no exchange either
+            try:
+                c2, R2, info2 = run_staged(S2, None, ctx.device, True, None, None)
+                ssr2 = info2["rel_rms"] ** 2 * float(y2 @ y2)
+            finally:
+                if paused:
+                    ctx.comm_pause(False)
+        finally:
+            S2.close()
+    finally:
+        P2.close()
+    # |A c - y|^2 = |R_stack c - q_stack|^2 + sum_p (|y_p|^2 - |Q_p^T y_p|^2)
+    ssy, tail = comm.allreduce_scalars([ssy_p, max(0.0, ssy_p - float(qty @ qty))])
+    info = dict(info2)
+    info["passes_local"] = info1.get("passes")
+    info["exchange"] = "tsqr"
+    info["rel_rms"] = math.sqrt((ssr2 + tail) / ssy) if ssy > 0 else float("nan")
+    c = c2 if Dinv is None else c2 * Dinv
+    return c, R2, info
 
 
 def get_lsq_system(db: LsqDB, *, verbose=False, Ibasis=None, Itrain=None, E0=None, Vref="default",
@@ -526,7 +582,7 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     # every row selected (`_select` returns sorted unique indices): no index upload, no gather on the device
     Irows_dev = None if len(Irows) == len(W) else Irows
     c, R, info = solve_device(ctx, db.Psi_dev, Y, W, Irows_dev, Icols, Dinv, want_R=True, comm=comm, precon=precon,
-                              factor_solver=factor_solver, reg=reg)
+                              factor_solver=factor_solver, reg=reg, exchange=str(solver.get("exchange", "gram")))
     # `cond(qrPsi.R)` (`src/lsq.jl:469`; computed but only logged there): the device estimate (a lower bound, tight to a few
     # per cent) unless the exact SVD of the n x n factor is asked for (`verbose=True` or solver["exact_cond"])
     if verbose or solver.get("exact_cond") or "cond_R_estimate" not in info:

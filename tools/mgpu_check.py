@@ -68,6 +68,9 @@ def main():
             bit_identical &= bool(n == n1 and np.array_equal(PsiN[r:r + n].view(np.int64), Psi1[r1:r1 + n1].view(np.int64)))
     IPN, infoN = ipf.lsqfit(dbN, weights={k: dict(v) for k, v in weights.items()}, E0=-4.0, Vref=ipf.OneBody(-4.0),
                             error_table=True, comm=comm)
+    # the TSQR exchange: every rank factors its own rows, one exchange of the [R_p | Q_p^T y] blocks
+    IPT, infoT = ipf.lsqfit(dbN, weights={k: dict(v) for k, v in weights.items()}, E0=-4.0, Vref=ipf.OneBody(-4.0),
+                            solver={"solver": "qr", "exchange": "tsqr"}, comm=comm)
     cN, c1 = infoN["c"], info1["c"]
     kappa = float(info1["cond_R"])
     dc = float(np.linalg.norm(cN - c1) / np.linalg.norm(c1))
@@ -83,10 +86,13 @@ def main():
            "psi_shard_rows_bit_identical_on_all_ranks": bool(all(flags)), "coefficients_bit_identical_across_ranks": bool(same_on_all_ranks),
            "coeff_rel_diff_vs_1gpu": dc, "cond_R": kappa, "coeff_tolerance": max(1e-8, 100 * kappa * 2.2e-16),
            "rel_rms_1gpu": float(info1["rel_rms"]), "rel_rms_ngpu": float(infoN["rel_rms"]),
-           "max_rel_diff_rmse_table": drms, "passes": infoN["solve_info"].get("passes")}
+           "max_rel_diff_rmse_table": drms, "passes": infoN["solve_info"].get("passes"),
+           "tsqr_coeff_rel_diff_vs_1gpu": float(np.linalg.norm(infoT["c"] - c1) / np.linalg.norm(c1)),
+           "tsqr_rel_rms": float(infoT["rel_rms"]), "tsqr_local_passes": infoT["solve_info"].get("passes_local")}
     ok = (out["psi_shard_rows_bit_identical_on_all_ranks"] and out["coefficients_bit_identical_across_ranks"]
           and dc <= out["coeff_tolerance"] and abs(out["rel_rms_1gpu"] - out["rel_rms_ngpu"]) <= 1e-8 * out["rel_rms_1gpu"]
-          and drms <= 1e-8)
+          and drms <= 1e-8 and out["tsqr_coeff_rel_diff_vs_1gpu"] <= out["coeff_tolerance"]
+          and abs(out["tsqr_rel_rms"] - out["rel_rms_1gpu"]) <= 1e-8 * out["rel_rms_1gpu"])
     out["ok"] = bool(ok)
     if rank == 0:
         sys.stdout.flush()
