@@ -598,7 +598,7 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
         IPF_CUDA(ctx, cudaGetLastError());
     }
     const int nbs = T->nbs;
-    static const size_t s_budget = getenv("IPF_4B_SCRATCH_GB") ? (size_t)atol(getenv("IPF_4B_SCRATCH_GB")) << 30 : (size_t)4 << 30;
+    static const size_t s_budget = getenv("IPF_4B_SCRATCH_GB") ? (size_t)atol(getenv("IPF_4B_SCRATCH_GB")) << 30 : (size_t)8 << 30;
     const int64_t max_pairs_batch = std::max<int64_t>(nl.maxpairs_cfg, (int64_t)(s_budget / (24 * (size_t)nbs)));
     const size_t s_bytes = (size_t)24 * nbs * (size_t)std::min<int64_t>(max_pairs_batch, nl.npairs);
     int64_t max_sites_batch = 0;
