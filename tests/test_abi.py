@@ -45,3 +45,25 @@ def test_no_cpu_fallback_without_gpu():
     import pytest
     with pytest.raises(_capi.IPFError):
         _capi.Context(0)
+
+
+def test_block_spec_layout_matches_the_c_compiler(tmp_path):
+    """`ipf_block_spec` is passed by pointer from ctypes (and from the Julia shim's `BlockSpec`): size and field offsets of
+    the ctypes mirror must be what gcc lays out for the header."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        import pytest
+        pytest.skip("no C compiler")
+    fields = [f[0] for f in _capi.BlockSpec._fields_]
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "ipf_b200.h"\nint main(void) {\n'
+                   '  printf("%zu", sizeof(ipf_block_spec));\n'
+                   + "".join(f'  printf(" %zu", offsetof(ipf_block_spec, {f}));\n' for f in fields)
+                   + "  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call([cc, "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(v) for v in subprocess.check_output([str(exe)]).split()]
+    assert out[0] == ctypes.sizeof(_capi.BlockSpec)
+    assert out[1:] == [getattr(_capi.BlockSpec, f).offset for f in fields]

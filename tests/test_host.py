@@ -189,3 +189,20 @@ def test_read_xyz_round_trip(tmp_path):
     assert len(data.load_data(fn, verbose=False)) == 5
     with pytest.raises(ValueError):
         data.load_data(str(tmp_path / "train.jld2"))
+
+
+def test_species_and_environment_bases_roundtrip():
+    """Species-resolved and environment-dependent runs: block grouping, dict round trip (the `basis` entry of `_info.json`),
+    symmetry only among equal-species legs, argument checks."""
+    desc = si_desc(2.0)
+    B = ipf.NBodyBasis(ipf.species_nbpolys(2, desc, 3, [14, 6]) + ipf.nbpolys(3, desc, 2, (14, (6, 14)))
+                       + ipf.envpolys(3, desc, 2, 2, ipf.CosCut(2.0, 3.0)) + ipf.nbpolys(2, desc, 2))
+    assert [(b.zc, b.zs, b.env_t) for b in B.blocks] == [(6, (6,), 0), (6, (14,), 0), (14, (6,), 0), (14, (14,), 0),
+                                                          (14, (6, 14), 0), (0, (), 0), (0, (), 1), (0, (), 2), (0, (), 0)]
+    assert ipf.NBodyBasis.read_dict(json.loads(json.dumps(B.write_dict()))) == B
+    # two different neighbour species: no exchange symmetry (all monomials), equal species: the symmetric orbits
+    assert len(ipf.nbpolys(3, desc, 4, (14, (6, 14)))) == 34 and len(ipf.nbpolys(3, desc, 4, (14, (6, 6)))) == len(ipf.nbpolys(3, desc, 4))
+    with pytest.raises(ValueError):
+        ipf.nbpolys(3, desc, 2, (14, (6,)))
+    with pytest.raises(ValueError):
+        ipf.envpolys(3, desc, 2, 1, ipf.CosCut(2.0, desc.rcut + 0.5))
