@@ -25,9 +25,10 @@
  * destroy calls.  Threading: one ipf_ctx = one GPU = one host thread at a time
  * (entry points are not re-entrant on the same ctx; distinct ctxs are independent).
  * Multi-GPU: one ctx per GPU (one process per GPU, or several ctxs in one process, each driven by its own
- * host thread); the only exchange step is the sum of the Gram blocks of a CholeskyQR pass.  With a communicator
- * attached (ipf_comm_init) ipf_solve_gram performs it itself: ncclAllReduce on the ctx stream, no host
- * synchronisation.  Without one the caller may sum the exposed device buffer by any other means.
+ * host thread); the only exchange step is the sum of the Gram blocks of a CholeskyQR pass (plus the n-vector A^T r of a
+ * refinement step and two residual scalars in ipf_solve_finish).  With a communicator attached (ipf_comm_init)
+ * ipf_solve_gram / ipf_solve_finish perform it themselves: ncclAllReduce on the ctx stream, no host synchronisation.
+ * Without one the caller may sum the exposed Gram buffer by any other means (then ipf_solve_finish works on local sums).
  */
 #ifndef IPF_B200_H
 #define IPF_B200_H
