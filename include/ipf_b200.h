@@ -28,7 +28,8 @@
  * host thread); the only exchange step is the sum of the Gram blocks of a CholeskyQR pass (plus the n-vector A^T r of a
  * refinement step and two residual scalars in ipf_solve_finish).  With a communicator attached (ipf_comm_init)
  * ipf_solve_gram / ipf_solve_finish perform it themselves: ncclAllReduce on the ctx stream, no host synchronisation.
- * Without one the caller may sum the exposed Gram buffer by any other means (then ipf_solve_finish works on local sums).
+ * Without one the caller may sum the exposed Gram buffer by any other means, after ipf_solve_set_csne(S, 0), and must sum
+ * the residual scalars of ipf_solve_finish itself.
  */
 #ifndef IPF_B200_H
 #define IPF_B200_H
@@ -246,6 +247,10 @@ int32_t ipf_solve_append_rows(ipf_ctx* ctx, ipf_solver* S, int64_t nextra, const
  * (src/lsq.jl:482-497), whose small dense work (SVD / pivoted QR of the n x n factor) stays on the host. */
 int32_t ipf_solve_qty(ipf_ctx* ctx, ipf_solver* S, double* qty);
 int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double* ssr, double* ssy);
+/* on = 0: never finish on the corrected semi-normal equations (whose refinement steps need the sum of A^T r over all
+ * ranks).  REQUIRED when the ranks' Gram blocks are summed by the caller instead of an attached communicator: the
+ * library then only sees local rows in ipf_solve_finish.  Default on. */
+int32_t ipf_solve_set_csne(ipf_solver* S, int32_t on);
 /* cond(R) (src/lsq.jl:469) of the factor ipf_solve_finish returns, estimated on the device by power / inverse iteration
  * (a lower bound, tight to a few per cent); call after ipf_solve_finish.  The exact value is an SVD of R_out on the host. */
 int32_t ipf_solve_cond(ipf_ctx* ctx, ipf_solver* S, double* kappa);

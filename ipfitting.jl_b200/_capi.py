@@ -92,6 +92,7 @@ SIGNATURES = {
     "ipf_solve_residual": (C.c_int32, [_vp, _vp, _dp, _dp, _dp]),
     "ipf_solve_info": (C.c_int32, [_vp, _ip, _dp, _dp, _dp, _dp]),
     "ipf_solve_cond": (C.c_int32, [_vp, _vp, _dp]),
+    "ipf_solve_set_csne": (C.c_int32, [_vp, C.c_int32]),
     "ipf_solve_destroy": (C.c_int32, [_vp, _vp]),
     "ipf_solve": (C.c_int32, [_vp, _vp, _dp, _dp, _lp, C.c_int64, _lp, C.c_int64, _dp, _dp, _dp, _dp]),
     "ipf_predict": (C.c_int32, [_vp, _vp, _dp, _dp]),

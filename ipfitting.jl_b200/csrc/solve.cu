@@ -60,6 +60,7 @@ struct ipf_solver {
     // conditioned (eps cond << 1) that c = (L L^T)^-1 A^T y followed by refinement steps on the TRUE residual
     // r = y - A c (two streaming passes over A each) is as accurate as another re-orthogonalisation pass
     bool csne = false;
+    bool csne_allowed = true;       // ipf_solve_set_csne: off when the caller sums the Gram blocks itself
     int csne_steps = 0;
     double kappa_hat = 0.0;         // (max / min diagonal of the equilibrated Cholesky factor)^2 of the last pass
     double* rvec = nullptr;         // [Mpad] residual vector (allocated on demand)
@@ -1154,7 +1155,7 @@ int32_t ipf_solve_factor(ipf_ctx* ctx, ipf_solver* S, int32_t* done) {
         // moderately conditioned (the diagonal ratio underestimates cond by up to ~1e2, so eps cond <= 1e-6):
         // finish on this pass with the corrected semi-normal equations instead of one more product + Gram pass
         static const bool no_csne = getenv("IPF_NO_CSNE") != nullptr;
-        if (!final_pass && !no_csne && lo > 0.0 && (hi / lo) * (hi / lo) <= 1e8) { final_pass = true; S->csne = true; }
+        if (!final_pass && !no_csne && S->csne_allowed && lo > 0.0 && (hi / lo) * (hi / lo) <= 1e8) { final_pass = true; S->csne = true; }
     }
     S->kappa_hat = (h[2] > 0.0) ? (h[3] / h[2]) * (h[3] / h[2]) : 0.0;
     unscale_rows_kernel<<<nblk, 256, 0, st>>>(S->L, n, S->dscale);
@@ -1374,6 +1375,12 @@ int32_t ipf_solve_residual(ipf_ctx* ctx, ipf_solver* S, const double* c, double*
     IPF_CUDA(ctx, cudaGetLastError());
     if (ssr) *ssr = h[0];
     if (ssy) *ssy = h[1];
+    return IPF_OK;
+}
+
+int32_t ipf_solve_set_csne(ipf_solver* S, int32_t on) {
+    if (!S) return IPF_EINVAL;
+    S->csne_allowed = on != 0;
     return IPF_OK;
 }
 

@@ -329,6 +329,9 @@ class _Solver:
                                                        C.byref(ssr), C.byref(ssy)))
         return ssr.value, ssy.value
 
+    def set_csne(self, on: bool):
+        self.ctx.check(self.ctx.lib.ipf_solve_set_csne(self.h, 1 if on else 0))
+
     def cond(self) -> float:
         """cond(R) of the returned factor, estimated on the device (power / inverse iteration; after `finish`)."""
         k = C.c_double()
@@ -359,6 +362,8 @@ def run_staged(S, comm=None, device: int = 0, want_R: bool = True, factor_solver
     methods (the gloo tests drive a numpy stand-in through exactly this function).
     `factor_solver(R, qty) -> (c_scaled, info)` replaces the triangular solve by a host-side solve on the factor."""
     multi = comm is not None and comm.world_size > 1
+    if multi and not (hasattr(comm, "attached") and comm.attached()) and hasattr(S, "set_csne"):
+        S.set_csne(False)          # the Gram blocks are summed out here: the library only sees local rows in finish
     while True:
         g, n1 = S.gram()
         if multi:

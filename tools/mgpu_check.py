@@ -7,6 +7,8 @@ GPU.  Asserted:
   * the N-GPU fit (Gram blocks summed by the library's NCCL communicator) returns the same coefficients on every rank
     (bit-identical) and agrees with the single-GPU fit to max(1e-8, 100 cond eps), rel_rms and the per-configtype RMSE
     table to 1e-8.
+  * the same holds for the TSQR exchange and for a context without a library communicator whose Gram blocks the host
+    program sums itself (torch.distributed).
 Prints one JSON line on rank 0.  Used by tests/test_multigpu.py and run by hand for profiles/."""
 import json
 import os
@@ -71,6 +73,12 @@ def main():
     # the TSQR exchange: every rank factors its own rows, one exchange of the [R_p | Q_p^T y] blocks
     IPT, infoT = ipf.lsqfit(dbN, weights={k: dict(v) for k, v in weights.items()}, E0=-4.0, Vref=ipf.OneBody(-4.0),
                             solver={"solver": "qr", "exchange": "tsqr"}, comm=comm)
+    # the exchange left to the caller: a context WITHOUT a library communicator, Gram blocks summed by torch.distributed
+    ctxX = _capi.Context(local)
+    dbX = LsqDB("", basis, shard, ctx=ctxX)
+    IPX, infoX = ipf.lsqfit(dbX, weights={k: dict(v) for k, v in weights.items()}, E0=-4.0, Vref=ipf.OneBody(-4.0),
+                            comm=parallel.Communicator())
+    dbX.delete()
     cN, c1 = infoN["c"], info1["c"]
     kappa = float(info1["cond_R"])
     dc = float(np.linalg.norm(cN - c1) / np.linalg.norm(c1))
@@ -88,11 +96,15 @@ def main():
            "rel_rms_1gpu": float(info1["rel_rms"]), "rel_rms_ngpu": float(infoN["rel_rms"]),
            "max_rel_diff_rmse_table": drms, "passes": infoN["solve_info"].get("passes"),
            "tsqr_coeff_rel_diff_vs_1gpu": float(np.linalg.norm(infoT["c"] - c1) / np.linalg.norm(c1)),
-           "tsqr_rel_rms": float(infoT["rel_rms"]), "tsqr_local_passes": infoT["solve_info"].get("passes_local")}
+           "tsqr_rel_rms": float(infoT["rel_rms"]), "tsqr_local_passes": infoT["solve_info"].get("passes_local"),
+           "external_exchange_coeff_rel_diff_vs_1gpu": float(np.linalg.norm(infoX["c"] - c1) / np.linalg.norm(c1)),
+           "external_exchange_rel_rms": float(infoX["rel_rms"])}
     ok = (out["psi_shard_rows_bit_identical_on_all_ranks"] and out["coefficients_bit_identical_across_ranks"]
           and dc <= out["coeff_tolerance"] and abs(out["rel_rms_1gpu"] - out["rel_rms_ngpu"]) <= 1e-8 * out["rel_rms_1gpu"]
           and drms <= 1e-8 and out["tsqr_coeff_rel_diff_vs_1gpu"] <= out["coeff_tolerance"]
-          and abs(out["tsqr_rel_rms"] - out["rel_rms_1gpu"]) <= 1e-8 * out["rel_rms_1gpu"])
+          and abs(out["tsqr_rel_rms"] - out["rel_rms_1gpu"]) <= 1e-8 * out["rel_rms_1gpu"]
+          and out["external_exchange_coeff_rel_diff_vs_1gpu"] <= out["coeff_tolerance"]
+          and abs(out["external_exchange_rel_rms"] - out["rel_rms_1gpu"]) <= 1e-8 * out["rel_rms_1gpu"])
     out["ok"] = bool(ok)
     if rank == 0:
         sys.stdout.flush()
