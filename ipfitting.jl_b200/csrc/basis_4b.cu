@@ -64,14 +64,14 @@ static_assert(Q_NG == 4, "the flush maps 5 rows x 6 double2 onto a warp and 16 c
 //   w[11]     row of Z2q_2
 //   w[12..14] c12, c13 (0 unless raised) and the weight of S (1/2 for a self-conjugate class): the HIGH words of
 //             the doubles (their low words are zero)
-//   w[15]     a1 | class << 4 | last << 9   (class = 3 c23 + number of raised sides; last entry of its function)
+//   w[15]     class | last << 5 | a1 << 8   (class = 3 c23 + number of raised sides; last entry of its function)
 // (every word is read: a dead word of the prefetched record would be reused by the compiler as a temporary, and that
 //  write-after-write dependency on the load in flight stalled every entry for a full memory latency)
 struct __align__(16) T4Ent {
     uint32_t w[16];
 };
 static_assert(sizeof(T4Ent) == 64, "entry records are read as four 16-byte words");
-constexpr uint32_t ENT_LAST = 1u << 9;
+constexpr uint32_t ENT_LAST = 1u << 5;
 inline uint32_t dbl_hi(double v) { uint64_t u; memcpy(&u, &v, 8); return (uint32_t)(u >> 32); }     // v has a zero low word
 
 struct Site4Args {
@@ -156,12 +156,13 @@ __device__ __forceinline__ void q_flush(const Site4Args& A, const double* __rest
 __host__ __device__ constexpr double q_fact(int k) { return k <= 1 ? 1.0 : (double)k * q_fact(k - 1); }
 __host__ __device__ constexpr int q_tri(int s) { return s * (s + 1) / 2; }
 
-// row t of side SIDE (0 = A, 1 = B) of an entry record
+// byte offset (row << 8) of the 16-bit row number in the low / high half of a record word: one byte permute
+template <int HALF>
+__device__ __forceinline__ uint32_t q_off(uint32_t v) { return __byte_perm(v, 0u, HALF ? 0x4324u : 0x4104u); }
+
+// row t of side SIDE (0 = A, 1 = B) of an entry record, as a byte offset
 template <int SIDE, int T>
-__device__ __forceinline__ uint32_t q_row(const uint32_t (&w)[16]) {
-    const uint32_t v = w[5 * SIDE + T / 2];
-    return (T & 1) ? (v >> 16) : (v & 0xffffu);
-}
+__device__ __forceinline__ uint32_t q_row(const uint32_t (&w)[16]) { return q_off<(T & 1)>(w[5 * SIDE + T / 2]); }
 
 // accumulators of one entry; the sums alternate between two sets so that consecutive terms do not wait for each other
 struct QAcc {
@@ -197,12 +198,12 @@ __device__ __forceinline__ void q_term(const double* __restrict__ pA, const doub
 template <int C, int N0, bool HA, bool HB>
 __device__ __forceinline__ void q_run(const uint32_t (&w)[16], const char* __restrict__ Mb, QAcc& Q) {
     constexpr int SD = C - N0;              // nu1 + nu2 of this run
-    const double* pA = reinterpret_cast<const double*>(Mb + ((size_t)q_row<0, N0 + 1>(w) << 8)) + q_tri(SD) * 32;
-    const double* pB = reinterpret_cast<const double*>(Mb + ((size_t)q_row<1, N0 + 1>(w) << 8)) + q_tri(SD) * 32;
+    const double* pA = reinterpret_cast<const double*>(Mb + q_row<0, N0 + 1>(w)) + q_tri(SD) * 32;
+    const double* pB = reinterpret_cast<const double*>(Mb + q_row<1, N0 + 1>(w)) + q_tri(SD) * 32;
     const double* pRA = nullptr;
     const double* pRB = nullptr;
-    if constexpr (HA) pRA = reinterpret_cast<const double*>(Mb + ((size_t)q_row<0, N0>(w) << 8)) + q_tri(SD + 1) * 32;
-    if constexpr (HB) pRB = reinterpret_cast<const double*>(Mb + ((size_t)q_row<1, N0>(w) << 8)) + q_tri(SD + 1) * 32;
+    if constexpr (HA) pRA = reinterpret_cast<const double*>(Mb + q_row<0, N0>(w)) + q_tri(SD + 1) * 32;
+    if constexpr (HB) pRB = reinterpret_cast<const double*>(Mb + q_row<1, N0>(w)) + q_tri(SD + 1) * 32;
     double ra = 0.0, rb = 0.0;
     if constexpr (HA) ra = pRA[0];
     if constexpr (HB) rb = pRB[0];
@@ -210,17 +211,53 @@ __device__ __forceinline__ void q_run(const uint32_t (&w)[16], const char* __res
     if constexpr (N0 < C) q_run<C, N0 + 1, HA, HB>(w, Mb, Q);
 }
 
-// sum over nu (|nu| = C) of one entry of class CLS = 3 C + (number of raised sides); a raised side needs c12 >= 1
-// (C <= D - 1), two raised sides C <= D - 2
+// one entry of class CLS = 3 C + V (C = c23, V = number of raised sides; a raised side needs c12 >= 1, i.e. C <= D - 1,
+// two raised sides C <= D - 2): the sum over nu (|nu| = C) and the entry's contribution to (S0, S1, T1, T2) of its function.
+// Everything that depends on the class is resolved here: only the accumulators the class uses exist, the k = l rows are
+// the starting values of the sums, and entries without raised products touch neither Z2q nor T.
 template <int CLS>
-__device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __restrict__ Mb, QAcc& Q) {
+__device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __restrict__ Mb, const char* __restrict__ xb,
+                                        double& S0, double& S1, double& T1, double& T2) {
     constexpr int C = CLS / 3, V = CLS % 3;
-    if constexpr (C + V <= G4_D) q_run<C, 0, (V >= 1), (V >= 2)>(w, Mb, Q);
+    if constexpr (C + V <= G4_D) {
+        const double zs = *reinterpret_cast<const double*>(Mb + q_off<0>(w[10]));
+        double z1 = 0.0, z2 = 0.0;
+        if constexpr (V >= 1) {
+            z1 = *reinterpret_cast<const double*>(Mb + q_off<1>(w[10]));
+            z2 = *reinterpret_cast<const double*>(Mb + q_off<0>(w[11]));
+        }
+        const uint32_t xoff = w[15] & 0xf00u;
+        const double xa = *reinterpret_cast<const double*>(xb + xoff);
+        const double xd = *reinterpret_cast<const double*>(xb + xoff + (G4_D + 1) * 256);
+        QAcc Q;
+        Q.s[0] = -zs; Q.s[1] = 0.0;
+        Q.a1[0] = -z1; Q.a1[1] = 0.0; Q.a2[0] = -z2; Q.a2[1] = 0.0;
+        Q.b1[0] = -z1; Q.b1[1] = 0.0; Q.b2[0] = -z2; Q.b2[1] = 0.0;
+        q_run<C, 0, (V >= 1), (V >= 2)>(w, Mb, Q);
+        const double s = C >= 1 ? Q.s[0] + Q.s[1] : Q.s[0];
+        const double ws = __hiloint2double((int)w[14], 0) * s;
+        S0 = fma(xa, ws, S0);
+        S1 = fma(xd, ws, S1);
+        if constexpr (V >= 1) {
+            // c12 (tA - z) + c13 (tB - z)
+            const double cA = __hiloint2double((int)w[12], 0);
+            double u1 = cA * (C >= 1 ? Q.a1[0] + Q.a1[1] : Q.a1[0]);
+            double u2 = cA * (C >= 1 ? Q.a2[0] + Q.a2[1] : Q.a2[0]);
+            if constexpr (V >= 2) {
+                const double cB = __hiloint2double((int)w[13], 0);
+                u1 = fma(cB, C >= 1 ? Q.b1[0] + Q.b1[1] : Q.b1[0], u1);
+                u2 = fma(cB, C >= 1 ? Q.b2[0] + Q.b2[1] : Q.b2[0], u2);
+            }
+            T1 = fma(xa, u1, T1);
+            T2 = fma(xa, u2, T2);
+        }
+    }
 }
 
-__device__ __forceinline__ void q_dispatch(uint32_t cls, const uint32_t (&w)[16], const char* __restrict__ Mb, QAcc& Q) {
+__device__ __forceinline__ void q_dispatch(uint32_t cls, const uint32_t (&w)[16], const char* __restrict__ Mb,
+                                           const char* __restrict__ xb, double& S0, double& S1, double& T1, double& T2) {
     static_assert(G4_D == 8, "one case per class 0 .. 3 (D + 1) - 1");
-#define Q_CASE(K) case K: q_entry<K>(w, Mb, Q); break;
+#define Q_CASE(K) case K: q_entry<K>(w, Mb, xb, S0, S1, T1, T2); break;
     switch (cls) {
         Q_CASE(0) Q_CASE(1) Q_CASE(2) Q_CASE(3) Q_CASE(4) Q_CASE(5) Q_CASE(6) Q_CASE(7) Q_CASE(8)
         Q_CASE(9) Q_CASE(10) Q_CASE(11) Q_CASE(12) Q_CASE(13) Q_CASE(14) Q_CASE(15) Q_CASE(16) Q_CASE(17)
@@ -334,43 +371,9 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
 #pragma unroll
         for (int q = 0; q < 4; ++q) { w[4 * q] = nx[q].x; w[4 * q + 1] = nx[q].y; w[4 * q + 2] = nx[q].z; w[4 * q + 3] = nx[q].w; }
         if (ei + 1 < ei_end) q_load_entry(A.ent + ei + 1, nx);        // the next record is in flight during this entry
-        // operands of the entry's epilogue first: their latency overlaps the term sums
-        const double zs = *reinterpret_cast<const double*>(Mb + ((size_t)(w[10] & 0xffffu) << 8));
-        const double z1 = *reinterpret_cast<const double*>(Mb + ((size_t)(w[10] >> 16) << 8));
-        const double z2 = *reinterpret_cast<const double*>(Mb + ((size_t)(w[11] & 0xffffu) << 8));
-        const uint32_t xoff = (w[15] & 0xfu) << 8;
-        const double xa = *reinterpret_cast<const double*>(xb + xoff);
-        const double xd = *reinterpret_cast<const double*>(xb + xoff + (G4_D + 1) * 256);
-        QAcc Q;
-#pragma unroll
-        for (int q = 0; q < 2; ++q) { Q.s[q] = 0.0; Q.a1[q] = 0.0; Q.a2[q] = 0.0; Q.b1[q] = 0.0; Q.b2[q] = 0.0; }
-        {
-            // c23 = 0 and 1 are 68 % of the entries and have 1 and 3 terms: compare-and-branch instead of the indirect
-            // branch of the switch (jump-table load + BRX latency per entry)
-            const uint32_t cls = (w[15] >> 4) & 0x1fu;
-            if (cls < 3) {
-                if (cls == 0) q_run<0, 0, false, false>(w, Mb, Q);
-                else if (cls == 1) q_run<0, 0, true, false>(w, Mb, Q);
-                else q_run<0, 0, true, true>(w, Mb, Q);
-            } else if (cls < 6) {
-                if (cls == 3) q_run<1, 0, false, false>(w, Mb, Q);
-                else if (cls == 4) q_run<1, 0, true, false>(w, Mb, Q);
-                else q_run<1, 0, true, true>(w, Mb, Q);
-            } else {
-                q_dispatch(cls, w, Mb, Q);
-            }
-        }
-        const double ws = __hiloint2double((int)w[14], 0) * ((Q.s[0] + Q.s[1]) - zs);
-        S0 = fma(xa, ws, S0);
-        S1 = fma(xd, ws, S1);
-        {
-            // c12 (tA - z) + c13 (tB - z); both weights are zero for an entry without raised products (rows 0 are read then)
-            const double cA = __hiloint2double((int)w[12], 0), cB = __hiloint2double((int)w[13], 0);
-            const double u1 = fma(cA, (Q.a1[0] + Q.a1[1]) - z1, cB * ((Q.b1[0] + Q.b1[1]) - z1));
-            const double u2 = fma(cA, (Q.a2[0] + Q.a2[1]) - z2, cB * ((Q.b2[0] + Q.b2[1]) - z2));
-            T1 = fma(xa, u1, T1);
-            T2 = fma(xa, u2, T2);
-        }
+        // the whole entry is specialised on its class (term sums and epilogue); padding entries have class 0, rows 0 and
+        // weight 0
+        q_dispatch(w[15] & 0x1fu, w, Mb, xb, S0, S1, T1, T2);
         if (w[15] & ENT_LAST) {
             const double radial = fma(dfcj, S0, fdx * S1);
             T1 *= tang; T2 *= tang;
@@ -515,7 +518,7 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
                     put16(E, 11, 0, q2);
                 }
                 const uint32_t cls = 3u * (uint32_t)c.c23 + (ha ? 1u : 0u) + (hb ? 1u : 0u);
-                E.w[15] = (uint32_t)c.a1 | cls << 4 | (ic + 1 == fcls[b].size() ? ENT_LAST : 0u);
+                E.w[15] = cls | (ic + 1 == fcls[b].size() ? ENT_LAST : 0u) | (uint32_t)c.a1 << 8;
                 E.w[12] = dbl_hi((double)c.c12);
                 E.w[13] = dbl_hi(hb ? (double)c.c13 : 0.0);
                 E.w[14] = dbl_hi(c.self ? 0.5 : 1.0);
