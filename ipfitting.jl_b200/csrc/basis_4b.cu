@@ -54,7 +54,7 @@ constexpr int Q_ELD = 34;                   // stride of e[function][.]: the fou
                                             // of the kernel's shared-memory traffic, which is what bounds phase 2)
 constexpr int Q_STAGE = 32 * Q_GLD + Q_NG * Q_ELD;  // doubles per worker: g rows, then e[function][row]
 constexpr int Q_THREADS = 32 * G4_NW;
-constexpr size_t Q_SMEM = sizeof(double) * ((size_t)G4_NROWS * 32 + 2 * (size_t)(G4_D + 1) * 32 + (size_t)G4_NW * Q_STAGE);
+constexpr size_t Q_SMEM = sizeof(double) * ((size_t)G4_NROWS * 32 + (size_t)G4_NW * Q_STAGE);
 static_assert(Q_NG == 4, "the flush maps 5 rows x 6 double2 onto a warp and 16 columns onto a half warp");
 
 // one class {m, m'} of monomials of one basis function (m' = m with the two other legs exchanged), 16 words:
@@ -64,7 +64,8 @@ static_assert(Q_NG == 4, "the flush maps 5 rows x 6 double2 onto a warp and 16 c
 //   w[11]     row of Z2q_2
 //   w[12..14] c12, c13 (0 unless raised) and the weight of S (1/2 for a self-conjugate class): the HIGH words of
 //             the doubles (their low words are zero)
-//   w[15]     class | last << 5 | a1 << 8   (class = 3 c23 + number of raised sides; last entry of its function)
+//   w[15]     class | last << 5 | a1 << 8 | max(a1 - 1, 0) << 12   (class = 3 c23 + number of raised sides; last entry of
+//             its function)
 // (every word is read: a dead word of the prefetched record would be reused by the compiler as a temporary, and that
 //  write-after-write dependency on the load in flight stalled every entry for a full memory latency)
 struct __align__(16) T4Ent {
@@ -216,7 +217,7 @@ __device__ __forceinline__ void q_run(const uint32_t (&w)[16], const char* __res
 // Everything that depends on the class is resolved here: only the accumulators the class uses exist, the k = l rows are
 // the starting values of the sums, and entries without raised products touch neither Z2q nor T.
 template <int CLS>
-__device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __restrict__ Mb, const char* __restrict__ xb,
+__device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __restrict__ Mb, double x1, double x2, double x4,
                                         double& S0, double& S1, double& T1, double& T2) {
     constexpr int C = CLS / 3, V = CLS % 3;
     if constexpr (C + V <= G4_D) {
@@ -226,9 +227,14 @@ __device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __r
             z1 = *reinterpret_cast<const double*>(Mb + q_off<1>(w[10]));
             z2 = *reinterpret_cast<const double*>(Mb + q_off<0>(w[11]));
         }
-        const uint32_t xoff = w[15] & 0xf00u;
-        const double xa = *reinterpret_cast<const double*>(xb + xoff);
-        const double xd = *reinterpret_cast<const double*>(xb + xoff + (G4_D + 1) * 256);
+        // x_j^a1 and a1 x_j^(a1-1) from three registers (x, x^2, x^4; a1 <= 8): the combination is bound by shared-memory
+        // traffic, not by arithmetic -- the two table loads per entry this replaces were 10 % of it
+        const uint32_t meta = w[15];
+        double xm = (meta & 0x1000u) ? x1 : 1.0;
+        if (meta & 0x2000u) xm *= x2;
+        if (meta & 0x4000u) xm *= x4;
+        const double xd = (double)(int)((meta >> 8) & 0xfu) * xm;
+        const double xa = (meta & 0xf00u) ? xm * x1 : 1.0;
         QAcc Q;
         Q.s[0] = -zs; Q.s[1] = 0.0;
         Q.a1[0] = -z1; Q.a1[1] = 0.0; Q.a2[0] = -z2; Q.a2[1] = 0.0;
@@ -254,10 +260,12 @@ __device__ __forceinline__ void q_entry(const uint32_t (&w)[16], const char* __r
     }
 }
 
-__device__ __forceinline__ void q_dispatch(uint32_t cls, const uint32_t (&w)[16], const char* __restrict__ Mb,
-                                           const char* __restrict__ xb, double& S0, double& S1, double& T1, double& T2) {
+__device__ __forceinline__ void q_dispatch(uint32_t cls, const uint32_t (&w)[16], const char* __restrict__ Mb, double x1,
+                                           double x2, double x4, double& S0, double& S1, double& T1, double& T2) {
     static_assert(G4_D == 8, "one case per class 0 .. 3 (D + 1) - 1");
-#define Q_CASE(K) case K: q_entry<K>(w, Mb, xb, S0, S1, T1, T2); break;
+    // (a loop-driven body for the rare classes with c23 >= 5 -- 3 % of the entries, 70 % of the code of phase 2, which
+    //  exceeds the 32 KB instruction cache -- was tried: the kernel got 7 % slower, 18 % with c23 >= 4)
+#define Q_CASE(K) case K: q_entry<K>(w, Mb, x1, x2, x4, S0, S1, T1, T2); break;
     switch (cls) {
         Q_CASE(0) Q_CASE(1) Q_CASE(2) Q_CASE(3) Q_CASE(4) Q_CASE(5) Q_CASE(6) Q_CASE(7) Q_CASE(8)
         Q_CASE(9) Q_CASE(10) Q_CASE(11) Q_CASE(12) Q_CASE(13) Q_CASE(14) Q_CASE(15) Q_CASE(16) Q_CASE(17)
@@ -286,8 +294,7 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
 #endif
     extern __shared__ __align__(16) double sm[];
     double* M = sm;                                          // [G4_NROWS][32]
-    double* xp = sm + (size_t)G4_NROWS * 32;                 // [2][G4_D + 1][32]  x_j^e, then e x_j^(e-1)
-    double* stage = xp + 2 * (size_t)(G4_D + 1) * 32;        // [G4_NW][Q_STAGE]
+    double* stage = sm + (size_t)G4_NROWS * 32;              // [G4_NW][Q_STAGE]
     const int lane = threadIdx.x & 31, worker = threadIdx.x >> 5;
     // row blocks start at the first pair of every configuration (the last block of a configuration is short): the
     // partial sums of a block never depend on how the configurations were batched or sharded over GPUs
@@ -319,16 +326,6 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
         E2[1] = Rj2 * E1[0] - Rj0 * E1[2];
         E2[2] = Rj0 * E1[1] - Rj1 * E1[0];
     }
-    if (worker == 0) {
-        double v = 1.0;
-#pragma unroll
-        for (int e = 0; e <= G4_D; ++e) {
-            xp[e * 32 + lane] = v;
-            if (e < G4_D) xp[(G4_D + 2 + e) * 32 + lane] = (double)(e + 1) * v;       // (e + 1) x^e: derivative of x^(e+1)
-            v *= xj;
-        }
-        xp[(G4_D + 1) * 32 + lane] = 0.0;
-    }
     // ---- phase 1: moments of the 32 rows.  The neighbour records of the block's centre atoms (one contiguous run of
     // pairs) are staged in the output staging area, which is idle until phase 2: every worker walks the same records.
     {
@@ -354,7 +351,7 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
 
     // ---- phase 2: basis functions of this worker, entry by entry; 4 scratch columns per staged group
     const char* Mb = reinterpret_cast<const char*>(M + lane);
-    const char* xb = reinterpret_cast<const char*>(xp + lane);
+    const double xj2 = xj * xj, xj4 = xj2 * xj2;
     double* wstage = stage + (size_t)worker * Q_STAGE;
     double* myrow = wstage + lane * Q_GLD;
     double* mye = wstage + 32 * Q_GLD + lane;
@@ -373,7 +370,7 @@ __global__ void __maxnreg__(168) site4b_kernel(Site4Args A) {
         if (ei + 1 < ei_end) q_load_entry(A.ent + ei + 1, nx);        // the next record is in flight during this entry
         // the whole entry is specialised on its class (term sums and epilogue); padding entries have class 0, rows 0 and
         // weight 0
-        q_dispatch(w[15] & 0x1fu, w, Mb, xb, S0, S1, T1, T2);
+        q_dispatch(w[15] & 0x1fu, w, Mb, xj, xj2, xj4, S0, S1, T1, T2);
         if (w[15] & ENT_LAST) {
             const double radial = fma(dfcj, S0, fdx * S1);
             T1 *= tang; T2 *= tang;
@@ -518,7 +515,7 @@ bool build_tables(const BlockDev& blk, Tables4& T) {
                     put16(E, 11, 0, q2);
                 }
                 const uint32_t cls = 3u * (uint32_t)c.c23 + (ha ? 1u : 0u) + (hb ? 1u : 0u);
-                E.w[15] = cls | (ic + 1 == fcls[b].size() ? ENT_LAST : 0u) | (uint32_t)c.a1 << 8;
+                E.w[15] = cls | (ic + 1 == fcls[b].size() ? ENT_LAST : 0u) | (uint32_t)c.a1 << 8 | (uint32_t)std::max(c.a1 - 1, 0) << 12;
                 E.w[12] = dbl_hi((double)c.c12);
                 E.w[13] = dbl_hi(hb ? (double)c.c13 : 0.0);
                 E.w[14] = dbl_hi(c.self ? 0.5 : 1.0);
@@ -652,8 +649,12 @@ int ipf_assemble_block_4b(ipf_ctx* ctx, const BlockDev& blk, const ChunkDev& ch,
     IPF_CUDA(ctx, cudaFuncSetAttribute(site4b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Q_SMEM));
     constexpr size_t g_bytes = sizeof(double) * (32 * G_LDT + G_WARPS * 7 * 32);
     IPF_CUDA(ctx, cudaFuncSetAttribute(gather3b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g_bytes));
-    static const bool no_overlap = getenv("IPF_NO_OVERLAP") != nullptr;
-    cudaStream_t st2 = no_overlap ? ctx->stream : ctx->stream2;
+    // The gather follows its producer on the same stream.  Running it on the side stream next to the producer of the next
+    // batch (IPF_4B_OVERLAP=1) is slower (cfg3 step 834 ms against 824 ms; with the producer's stream at a higher priority
+    // 846 ms): a producer CTA needs a completely free SM, and the many small gather CTAs -- HBM bound, 75 % of the copy
+    // bandwidth on their own -- spread over all SMs and keep the producer's CTAs waiting.
+    static const bool overlap = getenv("IPF_4B_OVERLAP") != nullptr;
+    cudaStream_t st2 = overlap ? ctx->stream2 : ctx->stream;
     cudaEvent_t gathered[2] = {nullptr, nullptr};
     int64_t c0 = 0;
     int ib = 0;

@@ -15,6 +15,7 @@ for rep in range(2):
     nw = lib.ipf_debug_4b_timing(out.ctypes.data_as(C.POINTER(C.c_double)), 1)
     db.delete()
 t = out[:3 * nw].reshape(3, nw)
+print("raw cycle sums: phase-1 end max %.4g  barrier max %.4g  end max %.4g" % (t[0].max(), t[1].max(), t[2].max()))
 print("phase-1 end (cycles / CTA-sum, relative to max):", np.round(t[0] / t[0].max(), 3))
 print("phase-2 duration relative to max:", np.round((t[2] - t[1]) / (t[2] - t[1]).max(), 3))
 print("total relative to max:", np.round(t[2] / t[2].max(), 3), " mean/max %.3f" % (t[2].mean() / t[2].max()))
