@@ -3,9 +3,10 @@
 Mirrors `/root/reference/src/lsq_db.jl:56-138`: `infofile`/`kronfile` (`:56-58`),
 `save_info` (`:96-104`: {"version", "basis", "configs"}), `save_kron`/`load_kron`
 (`:111-132`: HDF5 dataset "A"), `_backupfile` (`:73-80`), version gate (`:84-90`).
-HDF5 (h5py) is not available in this image, so the matrix is stored as
-`<dbpath>_kron.npy` (Fortran-ordered float64, the same bytes as dataset "A");
-`_kron.h5` is read/written when h5py can be imported.
+The matrix goes to `<dbpath>_kron.h5`, dataset "A", as in the reference: through h5py when it can be imported, else
+through the minimal writer / reader of `hdf5_min.py` (version 0 superblock, one contiguous float64 dataset; written
+from the format specification -- no HDF5 library exists in this image to check it against).  `<dbpath>_kron.npy`
+(Fortran-ordered float64, what earlier versions of this package wrote) is still read when no `.h5` file exists.
 """
 from __future__ import annotations
 
@@ -16,6 +17,7 @@ import string
 
 import numpy as np
 
+from . import hdf5_min
 from .basis import NBodyBasis
 from .prototypes import Dat
 
@@ -27,11 +29,15 @@ def infofile(dbpath: str) -> str:
 
 
 def kronfile(dbpath: str) -> str:
+    return dbpath + "_kron.h5"
+
+
+def _have_h5py() -> bool:
     try:
         import h5py  # noqa: F401
-        return dbpath + "_kron.h5"
+        return True
     except Exception:
-        return dbpath + "_kron.npy"
+        return False
 
 
 def _backupfile(fname: str):
@@ -53,13 +59,13 @@ def save(db) -> None:
     kf = kronfile(db.dbpath)
     _backupfile(kf)
     Psi = np.asfortranarray(db.Psi)
-    if kf.endswith(".h5"):
+    if _have_h5py():
         import h5py
         with h5py.File(kf, "w") as f:
             # Julia's column-major "A" appears with reversed dims to row-major readers
             f.create_dataset("A", data=np.ascontiguousarray(Psi.T))
     else:
-        np.save(kf, Psi)
+        hdf5_min.write_matrix(kf, Psi, "A")
 
 
 def load_into(db, dbpath: str) -> None:
@@ -71,12 +77,14 @@ def load_into(db, dbpath: str) -> None:
     db.configs = [Dat.read_dict(c) for c in info["configs"]]
     db.dbpath = dbpath
     kf = kronfile(dbpath)
-    if kf.endswith(".h5"):
+    if not os.path.exists(kf) and os.path.exists(dbpath + "_kron.npy"):
+        Psi = np.load(dbpath + "_kron.npy")
+    elif _have_h5py():
         import h5py
         with h5py.File(kf, "r") as f:
             Psi = np.asfortranarray(np.array(f["A"]).T)
     else:
-        Psi = np.load(kf)
+        Psi = hdf5_min.read_matrix(kf, "A")
     db._Psi_host = np.asfortranarray(Psi, dtype=np.float64)
     db._Psi_dev = None
     db._dev_basis = None
