@@ -509,6 +509,21 @@ def _rrqr_factor_solver(rtol: float):
     return solve
 
 
+def _matrix_p_factor_solver(B: np.ndarray):
+    """`solver["P"]` a full matrix (`src/lsq.jl:450-458,593`: D_inv = pinv(P); Psi <- Psi D_inv; qr; c = D_inv (qr \\ Y)).
+    The device factors the matrix WITHOUT the column transformation, Psi = Q R; then Psi D_inv = Q (R D_inv) and the QR
+    factorisation of the n x n product R D_inv = Q2 R2 gives the factor of the reference's matrix, R2, its right-hand
+    side Q2' (Q'Y), and c = D_inv R2^-1 Q2' Q'Y -- n x n host work instead of an M x n x n product on Psi."""
+    def solve(R, qty):
+        import scipy.linalg as sla
+        Q2, R2 = np.linalg.qr(np.triu(R) @ B)
+        sgn = np.where(np.diag(R2) < 0, -1.0, 1.0)           # a factor with a positive diagonal, as Householder gives up to sign
+        R2 = sgn[:, None] * R2
+        cp = sla.solve_triangular(R2, sgn * (Q2.T @ qty))
+        return B @ cp, {"R_factor": R2}
+    return solve
+
+
 def _regulariser_rows(regularisers, basis, Icols):
     """`_regularise!` (`src/lsq.jl:163-181`): every regulariser is a matrix P (target 0), a pair (P, q), or an object
     with `.matrix(basis) -> (P, q)` (the reference's `Matrix(reg, basis)`); all are stacked.  With `Ibasis` the
@@ -533,13 +548,18 @@ def _regulariser_rows(regularisers, basis, Icols):
     return np.vstack(Ps), np.concatenate(qs)
 
 
+def _is_full_matrix(P) -> bool:
+    P = np.asarray(P, dtype=np.float64)
+    return P.ndim == 2 and not np.array_equal(P, np.diag(np.diag(P)))
+
+
 def _diag_of(P, n) -> Optional[np.ndarray]:
     if P is None:
         return None
     P = np.asarray(P, dtype=np.float64)
     if P.ndim == 2:
-        if not np.allclose(P, np.diag(np.diag(P))):
-            raise NotImplementedError("only diagonal column preconditioners P are supported")
+        if _is_full_matrix(P):
+            raise NotImplementedError("a full matrix P is handled by _matrix_p_factor_solver")
         P = np.diag(P)
     if P.shape != (n,):
         raise ValueError("solver[\"P\"] has the wrong size")
@@ -579,7 +599,16 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
     Y, W, Icfg = collect_observations(db, weights, Vref)
     Irows, Icols = _select(db, Y, W, Icfg, Ibasis, Itrain)
     n = len(db.basis) if Icols is None else len(Icols)
-    Dinv = _diag_of(solver.get("P"), n)
+    if solver.get("P") is not None and _is_full_matrix(solver["P"]):
+        if factor_solver is not None:
+            raise NotImplementedError("a full matrix solver[\"P\"] is supported with the :qr solver (a diagonal P with all)")
+        Pm = np.asarray(solver["P"], dtype=np.float64)
+        if Pm.shape != (n, n):
+            raise ValueError("solver[\"P\"] has the wrong size")
+        Dinv = None
+        factor_solver = _matrix_p_factor_solver(np.linalg.pinv(Pm))         # `D_inv = pinv(P)`, src/lsq.jl:457
+    else:
+        Dinv = _diag_of(solver.get("P"), n)
     if "P" in solver:
         del solver["P"]          # `src/lsq.jl:460-462`
     precon = _precon_blocks(db, weights, Irows)
@@ -590,6 +619,9 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
                               factor_solver=factor_solver, reg=reg, exchange=str(solver.get("exchange", "gram")))
     # `cond(qrPsi.R)` (`src/lsq.jl:469`; computed but only logged there): the device estimate (a lower bound, tight to a few
     # per cent) unless the exact SVD of the n x n factor is asked for (`verbose=True` or solver["exact_cond"])
+    if "R_factor" in info:
+        R = info.pop("R_factor")            # the factor of Psi pinv(P), which is what the reference keeps and conditions
+        info.pop("cond_R_estimate", None)
     if verbose or solver.get("exact_cond") or "cond_R_estimate" not in info:
         kappa = float(np.linalg.cond(R)) if R is not None and R.size else float("nan")
     else:

@@ -102,6 +102,15 @@ def lsqfit_qr(Psi, configs, weights=None, E0=None, Ibasis=None, Itrain=None, P=N
     """Returns c, cond(R), rel_rms, R exactly as the :qr branch computes them."""
     A, Y = get_lsq_system(Psi, configs, weights, E0, Ibasis, Itrain, regularisers)
     n = A.shape[1]
+    if P is not None and np.ndim(P) == 2:
+        # a full matrix (the "Laplacian preconditioning" of `src/lsq.jl:450-458`): D_inv = pinv(P); mul!(Psi, Psi, D_inv)
+        Dm = np.linalg.pinv(np.asarray(P, dtype=float))
+        A = A @ Dm
+        Q, R = sla.qr(A, mode="economic")
+        kappa = np.linalg.cond(R)
+        c = sla.solve_triangular(R, Q.T @ Y)
+        rel_rms = np.linalg.norm(Q @ (R @ c) - Y) / np.linalg.norm(Y)
+        return Dm @ c, kappa, rel_rms, R                     # `c = D_inv * c`, src/lsq.jl:593
     Dinv = np.ones(n) if P is None else np.where(np.asarray(P) != 0, 1.0 / np.asarray(P, dtype=float), 0.0)
     A = A * Dinv[None, :]
     Q, R = sla.qr(A, mode="economic")

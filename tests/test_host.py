@@ -206,3 +206,25 @@ def test_species_and_environment_bases_roundtrip():
         ipf.nbpolys(3, desc, 2, (14, (6,)))
     with pytest.raises(ValueError):
         ipf.envpolys(3, desc, 2, 1, ipf.CosCut(2.0, desc.rcut + 0.5))
+
+
+def test_matrix_p_factor_solver_algebra():
+    """`solver["P"]` as a full matrix (`src/lsq.jl:450-458,593`): the n x n post-processing of the factor of Psi equals
+    the QR solve of Psi pinv(P)."""
+    import scipy.linalg as sla
+    from ipfitting_jl_b200 import lsq
+    rng = np.random.default_rng(0)
+    m, n = 300, 14
+    A = rng.standard_normal((m, n)) * np.logspace(0, -4, n)
+    y = rng.standard_normal(m)
+    P = 2.1 * np.eye(n) - np.diag(np.ones(n - 1), 1) - np.diag(np.ones(n - 1), -1)
+    B = np.linalg.pinv(P)
+    Q, R = np.linalg.qr(A)
+    c, extra = lsq._matrix_p_factor_solver(B)(R, Q.T @ y)
+    Qr, Rr = sla.qr(A @ B, mode="economic")
+    c_ref = B @ sla.solve_triangular(Rr, Qr.T @ y)
+    assert np.linalg.norm(c - c_ref) <= 1e-10 * np.linalg.norm(c_ref)
+    R2 = extra["R_factor"]
+    assert np.all(np.diag(R2) > 0) and np.allclose(np.tril(R2, -1), 0)
+    assert np.abs(np.abs(R2) - np.abs(Rr)).max() <= 1e-12 * np.abs(Rr).max()
+    assert lsq._is_full_matrix(P) and not lsq._is_full_matrix(np.diag(np.arange(1.0, 4.0))) and not lsq._is_full_matrix(np.ones(3))
