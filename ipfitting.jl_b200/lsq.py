@@ -628,7 +628,10 @@ def lsqfit(db: LsqDB, *, solver: Optional[dict] = None, verbose=False, Ibasis=No
         kappa = float(info["cond_R_estimate"])
     if isinstance(saveqr, dict):
         saveqr["R"] = R
-        saveqr["Y"] = (W * Y)[Irows]
+        # the right-hand side of the factored system: weighted observations, then the regulariser targets
+        # (`vcat(Y, Yreg)`, `src/lsq.jl:163-181`).  Rows transformed by a force preconditioner stay on the device and appear
+        # here untransformed; Q (M x n) is not materialised at all (`saveqr["Q"]` is not written).
+        saveqr["Y"] = (W * Y)[Irows] if reg is None or reg[0] is None else np.concatenate([(W * Y)[Irows], reg[1]])
     # combine(db.basis, c) uses the FULL basis (`src/lsq.jl:603`): scatter a subset fit
     cfull = np.zeros(len(db.basis))
     if Icols is None:

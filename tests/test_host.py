@@ -228,3 +228,58 @@ def test_matrix_p_factor_solver_algebra():
     assert np.all(np.diag(R2) > 0) and np.allclose(np.tril(R2, -1), 0)
     assert np.abs(np.abs(R2) - np.abs(Rr)).max() <= 1e-12 * np.abs(Rr).max()
     assert lsq._is_full_matrix(P) and not lsq._is_full_matrix(np.diag(np.arange(1.0, 4.0))) and not lsq._is_full_matrix(np.ones(3))
+
+
+def test_lsqfit_host_logic_with_numpy_stand_in(monkeypatch):
+    """The host side of `lsqfit` around the device solve -- full-matrix `solver["P"]`, `saveqr`, regulariser targets --
+    with a numpy stand-in for `solve_device` (same signature and return values) on the oracle's Psi."""
+    import ipf_oracle as O
+    import lsq_oracle as LO
+    from ipfitting_jl_b200 import lsq
+    from util import rows_for
+    cfgs = synth.rattled_configs("Si", 1, 6, seed=22, calc=synth.StillingerWeber(), configtype="small")
+    B = ipf.nbpolys(2, si_desc(), 4)
+    db = LsqDB("", B, cfgs, _assemble=False)
+    r = rows_for(cfgs)
+    ref = O.assemble(db.basis, cfgs, r["E"], r["F"], r["V"], db.nrows)
+    db._Psi_host = np.asfortranarray(ref)
+    monkeypatch.setattr(db, "_context", lambda: None)
+    monkeypatch.setattr(type(db), "Psi_dev", property(lambda self: self._Psi_host))
+
+    def stand_in(ctx, Psi, Y, W, Irows=None, Icols=None, Dinv=None, want_R=True, comm=None, precon=None,
+                 factor_solver=None, reg=None, exchange="gram"):
+        rows = np.arange(len(W)) if Irows is None else Irows
+        A0 = (W[:, None] * Psi)[rows]
+        y = (W * Y)[rows]
+        if Icols is not None:
+            A0 = A0[:, Icols]
+        if reg is not None and reg[0] is not None:
+            A0 = np.vstack([A0, reg[0]]); y = np.concatenate([y, reg[1]])
+        A = A0 if Dinv is None else A0 * Dinv
+        Q, R = np.linalg.qr(A)
+        qty = Q.T @ y
+        cs, extra = factor_solver(R, qty) if factor_solver is not None else (np.linalg.solve(R, qty), {})
+        c = cs if Dinv is None else cs * Dinv
+        info = {"rel_rms": np.linalg.norm(A0 @ c - y) / np.linalg.norm(y), "cond_R_estimate": -1.0}
+        info.update(extra)
+        return c, R, info
+
+    monkeypatch.setattr(lsq, "solve_device", stand_in)
+    n = len(B)
+    P = 2.5 * np.eye(n) - np.diag(np.ones(n - 1), 1) - np.diag(np.ones(n - 1), -1)
+    w = {"default": {"E": 40.0, "F": 1.0, "V": 0.5}}
+    saveqr = {}
+    solver = {"solver": "qr", "P": P.copy()}
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=0.0, solver=solver, saveqr=saveqr)
+    c_ref, kappa, rel_rms, R = LO.lsqfit_qr(ref, db.configs, w, E0=None, P=P)
+    assert np.linalg.norm(info["c"] - c_ref) <= 1e-10 * np.linalg.norm(c_ref)
+    assert abs(info["cond_R"] - kappa) <= 1e-9 * kappa and abs(info["rel_rms"] - rel_rms) <= 1e-9 * rel_rms
+    assert np.abs(np.abs(saveqr["R"]) - np.abs(R)).max() <= 1e-10 * np.abs(R).max()
+    assert "P" not in solver and "P" not in info                      # `delete!(solver, "P")`, src/lsq.jl:460-462
+    # regulariser rows: targets appended to the saved right-hand side (`vcat(Y, Yreg)`)
+    Preg, q = 0.1 * np.eye(n)[:3], np.array([0.5, -0.25, 0.0])
+    saveqr = {}
+    IP, info = ipf.lsqfit(db, weights=dict(w), E0=0.0, regularisers=[(Preg, q)], saveqr=saveqr)
+    c_ref, _, _, _ = LO.lsqfit_qr(ref, db.configs, w, E0=None, regularisers=[(Preg, q)])
+    assert np.linalg.norm(info["c"] - c_ref) <= 1e-10 * np.linalg.norm(c_ref)
+    assert np.array_equal(saveqr["Y"][-3:], q)
