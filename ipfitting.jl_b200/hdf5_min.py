@@ -60,7 +60,8 @@ def write_matrix(fname: str, A: np.ndarray, name: str = "A") -> None:
     if not nm or b"\0" in nm or b"/" in nm:
         raise ValueError("bad dataset name")
     m, n = A.shape
-    raw = np.asfortranarray(A).tobytes(order="F")
+    rawT = np.asfortranarray(A).T             # C-contiguous view with the HDF5 dims: no copy of a matrix already in Julia order
+    nbytes = rawT.nbytes
     hdf_dims = (n, m)
 
     addr_root, addr_btree = 96, 136
@@ -74,14 +75,14 @@ def write_matrix(fname: str, A: np.ndarray, name: str = "A") -> None:
     name_off = 8
 
     dataspace = struct.pack("<BBB5x", 1, len(hdf_dims), 0) + b"".join(struct.pack("<Q", d) for d in hdf_dims)
-    layout = struct.pack("<BBQQ", 3, 1, _DATA_ADDR, len(raw))          # version 3, class 1 = contiguous
+    layout = struct.pack("<BBQQ", 3, 1, _DATA_ADDR, nbytes)          # version 3, class 1 = contiguous
     dset = _object_header([_message(0x0001, dataspace), _message(0x0003, _F64LE, flags=1), _message(0x0008, layout)])
     if addr_dset + len(dset) > _DATA_ADDR:
         raise ValueError("dataset name too long for the fixed layout")
     root = _object_header([_message(0x0011, struct.pack("<QQ", addr_btree, addr_heap))])
     assert addr_root + len(root) == addr_btree
 
-    eof = _DATA_ADDR + len(raw)
+    eof = _DATA_ADDR + nbytes
     sb = SIGNATURE + bytes([0, 0, 0, 0, 0, 8, 8, 0]) + struct.pack("<HHI", _LEAF_K, _INTERNAL_K, 0)
     sb += struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF)
     sb += struct.pack("<QQII", 0, addr_root, 1, 0) + struct.pack("<QQ", addr_btree, addr_heap)      # root entry, cached
@@ -97,13 +98,13 @@ def write_matrix(fname: str, A: np.ndarray, name: str = "A") -> None:
     head += b"\0" * (_DATA_ADDR - len(head))
     with open(fname, "wb") as f:
         f.write(head)
-        f.write(raw)
+        rawT.tofile(f)
 
 
 # ---------------------------------------------------------------------------------------------------------------
 class _File:
-    def __init__(self, buf: bytes):
-        self.b = buf
+    def __init__(self, buf):
+        self.b = buf                     # bytes or mmap: slices are bytes, struct reads in place
         if buf[:8] != SIGNATURE:
             raise HDF5FormatError("not an HDF5 file (signature at offset 0 expected)")
         ver = buf[8]
@@ -151,7 +152,7 @@ class _File:
             raise HDF5FormatError("local heap signature")
         _, _, data_addr = struct.unpack_from("<QQQ", b, a + 8)
         s = data_addr + self.base + off
-        return b[s:b.index(b"\0", s)]
+        return b[s:b.find(b"\0", s)]
 
     def group_entries(self, btree_addr: int, heap_addr: int):
         """{name: object header address} of a symbol-table group."""
@@ -194,8 +195,19 @@ def _dtype_of(data: bytes) -> np.dtype:
 
 def read_matrix(fname: str, name: str = "A") -> np.ndarray:
     """The Julia array stored as dataset `name` of the root group (Fortran-ordered, float64 for the reference's files)."""
+    import mmap
     with open(fname, "rb") as f:
-        buf = f.read()
+        buf = mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ)      # the matrix can be many GB: one copy, at the end
+    try:
+        return _read_matrix(buf, name)
+    finally:
+        try:
+            buf.close()
+        except BufferError:              # a view is still alive (only on an error path)
+            pass
+
+
+def _read_matrix(buf, name: str) -> np.ndarray:
     F = _File(buf)
     if F.root_cache is not None:
         btree, heap = F.root_cache
@@ -244,10 +256,13 @@ def read_matrix(fname: str, name: str = "A") -> np.ndarray:
     else:
         addr, size = layout
         if addr == UNDEF:
-            raw = b"\0" * (count * dtype.itemsize)                  # never written: fill value zero
-        else:
-            raw = buf[addr + F.base:addr + F.base + count * dtype.itemsize]
+            return np.zeros(dims[::-1], dtype=dtype, order="F")     # never written: fill value zero
+        if addr + F.base + count * dtype.itemsize > len(buf):
+            raise HDF5FormatError("dataset extends beyond the end of the file")
+        a = np.frombuffer(buf, dtype=dtype, count=count, offset=addr + F.base).reshape(dims)
+        out = np.array(a.T, order="F")                                        # Julia's dims and memory order; owns its data
+        del a
+        return out
     if len(raw) < count * dtype.itemsize:
         raise HDF5FormatError("dataset extends beyond the end of the file")
-    a = np.frombuffer(raw, dtype=dtype, count=count).reshape(dims)            # HDF5 (row-major) view
-    return np.asfortranarray(a.T)                                             # Julia's dims and memory order
+    return np.array(np.frombuffer(raw, dtype=dtype, count=count).reshape(dims).T, order="F")
